@@ -1,0 +1,130 @@
+/* mercat2_b200 -- C ABI of the B200-native k-mer counting engine.
+ *
+ * This is the drop-in boundary for MerCat2's hot path.  The reference has no FFI: the path is plain
+ * Python (lib/mercat2_kmers.py, lib/mercat2_Chunker.py, lib/mercat2_metrics.py and the driver glue
+ * bin/mercat2.py:86-137).  Each entry point below names the reference interface it replaces; the
+ * ctypes binding a maintainer would add on the reference side is shown in INTEGRATION.md and is what
+ * mercat2_b200/_native.py implements.
+ *
+ * Conventions: every function returns 0 on success or a negative mc2_status; mc2_last_error() gives
+ * the message for the calling thread's last failure.  No exceptions cross the boundary.  Handles are
+ * created by *_create / count calls and released by the matching *_destroy / *_free.  One host thread
+ * per engine; calls are stream-ordered on the engine's stream and synchronous at return.  Plain
+ * pointers and sizes only -- no torch types.  There is NO CPU fallback: without a CUDA device the
+ * engine cannot be created.
+ */
+#ifndef MERCAT2_B200_H
+#define MERCAT2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mc2_engine mc2_engine;
+typedef struct mc2_table mc2_table;
+typedef struct mc2_metrics mc2_metrics;
+
+enum mc2_status {
+    MC2_OK = 0,
+    MC2_ERR_INVALID = -1,      /* bad argument (k < 1, k too large, NULL pointer ...) */
+    MC2_ERR_CUDA = -2,         /* CUDA runtime failure */
+    MC2_ERR_NON_ASCII = -3,    /* input holds bytes >= 0x80 (the reference would count code points) */
+    MC2_ERR_LIMIT = -4,        /* an engine capacity limit was hit (message says which) */
+    MC2_ERR_IO = -5
+};
+
+/* where a text buffer lives */
+enum mc2_memspace { MC2_HOST = 0, MC2_DEVICE = 1 };
+
+/* ---- engine -------------------------------------------------------------------------------- */
+int mc2_engine_create(int device, mc2_engine** out);
+void mc2_engine_destroy(mc2_engine* e);
+const char* mc2_last_error(void);
+const char* mc2_version(void);
+
+/* Tunables (mostly for tests): "dense_max_bins", "smem_max_bins", "batch_symbols", "force_path"
+ * (0 auto, 1 dense, 2 sparse, 3 wide), "force_encoding" (-1 auto, 0 ACGT 2-bit, 1 A-Z 5-bit, 2 byte). */
+int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value);
+/* Counters: "launches" (kernels launched so far), "h2d_bytes", "d2h_bytes", "chunks", "device_ms"
+ * (CUDA-event time of the last count call, microseconds in "device_us"). */
+int64_t mc2_engine_get_stat(mc2_engine* e, const char* name);
+
+/* Per-kernel device time, measured with CUDA events on the engine's stream while option "profile" is 1
+ * (set it to 2 to clear the totals): a JSON object {"kernel": {"launches": n, "us": t}, ...}.
+ * Call with buf = NULL to get the size. */
+int mc2_engine_profile(mc2_engine* e, char* buf, uint64_t cap, uint64_t* size);
+
+/* ---- counting -------------------------------------------------------------------------------- */
+/* Replaces find_kmers(file, kmer, min_count) (lib/mercat2_kmers.py:32-78) for one file's TEXT (the
+ * bytes the reference would read from the possibly-gunzipped file): parse FASTA, count every k-mer,
+ * keep those with count >= min_count.  `space` says whether `text` is a host or a device pointer. */
+int mc2_count_text(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
+                   mc2_table** out);
+
+/* Replaces calculateKmerCount(seq, kmer) (lib/mercat2_kmers.py:10-28): `symbols` is a raw sequence, no
+ * FASTA parsing (a '>' or newline in it is an ordinary character). */
+int mc2_count_symbols(mc2_engine* e, const void* symbols, uint64_t nbytes, int space, int k, int64_t min_count,
+                      mc2_table** out);
+
+/* Replaces chunk_files + Chunker + one find_kmers per piece + the per-sample sum
+ * (bin/mercat2.py:86-127, lib/mercat2_Chunker.py:39-59): the text is split at the reference's piece
+ * boundaries (virtually: nothing is written), every piece is counted and filtered on its own, the
+ * filtered tables are summed.  chunk_bytes = 0 means "do not chunk" (file smaller than -s, or -s 0).
+ * n_chunks (optional) receives the number of pieces; piece_offsets (optional, capacity
+ * piece_capacity) receives the byte offset where each piece starts. */
+int mc2_count_sample(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
+                     uint64_t chunk_bytes, mc2_table** out, uint64_t* n_chunks, uint64_t* piece_offsets,
+                     uint64_t piece_capacity);
+
+/* Replaces Chunker(path, dest, "<S>M", ">") (lib/mercat2_Chunker.py:14-59) without writing files: the
+ * byte offsets at which the reference would start each piece of this text. */
+int mc2_chunk_offsets(mc2_engine* e, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes,
+                      uint64_t* piece_offsets, uint64_t piece_capacity, uint64_t* n_pieces);
+
+/* Streaming variant of mc2_count_sample for several files / blocks of one sample: begin, add the
+ * text of each FILE (each is chunked and counted independently, like one element of
+ * samples[type][name] in bin/mercat2.py:336-339), finish. */
+typedef struct mc2_sample mc2_sample;
+int mc2_sample_begin(mc2_engine* e, int k, int64_t min_count, mc2_sample** out);
+int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes,
+                        uint64_t* n_chunks);
+int mc2_sample_finish(mc2_sample* s, mc2_table** out);   /* consumes s */
+void mc2_sample_abort(mc2_sample* s);
+
+/* ---- result tables ----------------------------------------------------------------------------
+ * Rows are sorted by k-mer text (byte order == Python str order for ASCII), as
+ * sorted(kmers.items()) in bin/mercat2.py:132. */
+uint64_t mc2_table_rows(const mc2_table* t);
+int mc2_table_k(const mc2_table* t);
+uint64_t mc2_table_total(const mc2_table* t);              /* sum of counts */
+/* kmers: rows*k bytes (no terminators), counts: rows entries */
+int mc2_table_export(mc2_table* t, char* kmers, uint64_t* counts);
+/* The per-sample TSV of bin/mercat2.py:130-133: "k-mer\t<basename>_Count\n" then "kmer\tcount\n" rows.
+ * Writes nothing and returns 1 when the table is empty (the reference writes no file then). */
+int mc2_table_write_tsv(mc2_table* t, const char* path, const char* basename);
+/* Same bytes into memory: call with buf = NULL to get the size. */
+int mc2_table_tsv(mc2_table* t, const char* basename, char* buf, uint64_t cap, uint64_t* size);
+void mc2_table_free(mc2_table* t);
+
+/* ---- protein metrics ----------------------------------------------------------------------------
+ * Replaces the numeric part of plot_sample_metrics (lib/mercat2_figures.py:157-183) and
+ * predict_isoelectric_point_ProMoST / calculate_MW / calculate_hydro (lib/mercat2_metrics.py:57-170)
+ * for every record of one protein FASTA text.  Values are UNROUNDED doubles (the Python layer applies
+ * round(x, 2) exactly like the reference); status[i]: 0 ok, 1 = last residue unknown (reference
+ * returns None), 2 = first residue unknown (reference raises KeyError). */
+int mc2_protein_metrics(mc2_engine* e, const void* text, uint64_t nbytes, int space, mc2_metrics** out);
+/* The scalar functions of lib/mercat2_metrics.py for a batch of raw sequences (host memory):
+ * sequence i is seqs[offsets[i] .. offsets[i+1]).  One output row per sequence; status 255 = empty. */
+int mc2_sequence_metrics(mc2_engine* e, const void* seqs, const uint64_t* offsets, uint64_t nseq, mc2_metrics** out);
+uint64_t mc2_metrics_records(const mc2_metrics* m);
+/* header_off/header_len locate each record's header text (without '>') inside the input text */
+int mc2_metrics_export(const mc2_metrics* m, uint64_t* header_off, uint32_t* header_len, uint64_t* length,
+                       double* pi, double* mw, double* hydro, uint8_t* status);
+void mc2_metrics_free(mc2_metrics* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

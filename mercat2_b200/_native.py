@@ -1,0 +1,310 @@
+"""ctypes binding of include/mercat2_b200.h -- the only way the Python layer reaches the GPU.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device can be opened, the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmercat2_b200.so"
+
+MC2_HOST, MC2_DEVICE = 0, 1
+
+# every symbol include/mercat2_b200.h declares: (name, restype, argtypes)
+_VP, _U64, _I64, _INT = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
+_PP = C.POINTER(C.c_void_p)
+_PU64 = C.POINTER(C.c_uint64)
+SYMBOLS = [
+    ("mc2_engine_create", _INT, [_INT, _PP]),
+    ("mc2_engine_destroy", None, [_VP]),
+    ("mc2_last_error", C.c_char_p, []),
+    ("mc2_version", C.c_char_p, []),
+    ("mc2_engine_set_option", _INT, [_VP, C.c_char_p, _I64]),
+    ("mc2_engine_get_stat", _I64, [_VP, C.c_char_p]),
+    ("mc2_engine_profile", _INT, [_VP, _VP, _U64, _PU64]),
+    ("mc2_count_text", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
+    ("mc2_count_symbols", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
+    ("mc2_count_sample", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _U64, _PP, _PU64, _PU64, _U64]),
+    ("mc2_chunk_offsets", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64, _U64, _PU64]),
+    ("mc2_sample_begin", _INT, [_VP, _INT, _I64, _PP]),
+    ("mc2_sample_add_text", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64]),
+    ("mc2_sample_finish", _INT, [_VP, _PP]),
+    ("mc2_sample_abort", None, [_VP]),
+    ("mc2_table_rows", _U64, [_VP]),
+    ("mc2_table_k", _INT, [_VP]),
+    ("mc2_table_total", _U64, [_VP]),
+    ("mc2_table_export", _INT, [_VP, _VP, _VP]),
+    ("mc2_table_write_tsv", _INT, [_VP, C.c_char_p, C.c_char_p]),
+    ("mc2_table_tsv", _INT, [_VP, C.c_char_p, _VP, _U64, _PU64]),
+    ("mc2_table_free", None, [_VP]),
+    ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
+    ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
+    ("mc2_metrics_records", _U64, [_VP]),
+    ("mc2_metrics_export", _INT, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("mc2_metrics_free", None, [_VP]),
+]
+
+
+class Mc2Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"mercat2_b200 error {code}: {message}")
+        self.code = code
+
+
+class NonAsciiError(Mc2Error, ValueError):
+    """Input holds bytes >= 0x80 (the reference would decode UTF-8 and count code points)."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree library (building it first if it is absent and nvcc exists)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(str(LIB_PATH))
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(lib, name)          # AttributeError here = header and library disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def _check(lib, status):
+    if status < 0:
+        msg = lib.mc2_last_error().decode(errors="replace")
+        raise (NonAsciiError if status == -3 else Mc2Error)(status, msg)
+    return status
+
+
+def _as_buffer(data):
+    """-> (address, nbytes, memspace, keepalive) for bytes-like, numpy or CUDA torch tensors."""
+    if hasattr(data, "is_cuda"):                      # torch tensor (uint8), host or device
+        t = data.contiguous()
+        if t.element_size() != 1:
+            raise TypeError("text tensor must be uint8")
+        return t.data_ptr(), t.numel(), (MC2_DEVICE if t.is_cuda else MC2_HOST), t
+    if isinstance(data, np.ndarray):
+        a = np.ascontiguousarray(data).view(np.uint8)
+        return a.ctypes.data, a.size, MC2_HOST, a
+    if isinstance(data, str):
+        data = data.encode("ascii", errors="surrogateescape")
+    mv = memoryview(data)
+    a = np.frombuffer(mv, dtype=np.uint8)
+    return a.ctypes.data, a.size, MC2_HOST, (mv, a)
+
+
+class Table:
+    """A finished count table (rows sorted by k-mer text)."""
+
+    def __init__(self, engine, handle):
+        self._engine, self._h = engine, handle
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._engine._h:
+            self._engine._lib.mc2_table_free(self._h)
+        self._h = None
+
+    @property
+    def rows(self) -> int:
+        return int(self._engine._lib.mc2_table_rows(self._h))
+
+    @property
+    def k(self) -> int:
+        return int(self._engine._lib.mc2_table_k(self._h))
+
+    @property
+    def total(self) -> int:
+        return int(self._engine._lib.mc2_table_total(self._h))
+
+    def arrays(self):
+        """(kmers as uint8[rows, k], counts as uint64[rows])"""
+        rows, k = self.rows, self.k
+        kmers = np.empty((rows, k), dtype=np.uint8)
+        counts = np.empty(rows, dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_export(self._h, kmers.ctypes.data, counts.ctypes.data))
+        return kmers, counts
+
+    def to_dict(self) -> dict:
+        kmers, counts = self.arrays()
+        k = self.k
+        blob = kmers.tobytes().decode("ascii")
+        return {blob[i * k:(i + 1) * k]: int(c) for i, c in enumerate(counts.tolist())}
+
+    def tsv_bytes(self, basename: str) -> bytes:
+        lib = self._engine._lib
+        size = C.c_uint64(0)
+        _check(lib, lib.mc2_table_tsv(self._h, basename.encode(), None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value)
+        _check(lib, lib.mc2_table_tsv(self._h, basename.encode(), buf, size.value, C.byref(size)))
+        return buf.raw[:size.value]
+
+    def write_tsv(self, path, basename: str) -> bool:
+        """Write the per-sample TSV; returns False (and writes nothing) for an empty table."""
+        lib = self._engine._lib
+        return _check(lib, lib.mc2_table_write_tsv(self._h, os.fsencode(str(path)), basename.encode())) == 0
+
+
+class Engine:
+    """One CUDA device + stream.  Not thread-safe: one host thread per engine."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        handle = C.c_void_p()
+        _check(self._lib, self._lib.mc2_engine_create(device, C.byref(handle)))
+        self._h = handle
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mc2_engine_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        _check(self._lib, self._lib.mc2_engine_set_option(self._h, name.encode(), int(value)))
+
+    def stat(self, name: str) -> int:
+        return int(self._lib.mc2_engine_get_stat(self._h, name.encode()))
+
+    def profile(self) -> dict:
+        """Per-kernel CUDA-event totals gathered while option 'profile' is on."""
+        import json
+        size = C.c_uint64(0)
+        _check(self._lib, self._lib.mc2_engine_profile(self._h, None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value + 1)
+        _check(self._lib, self._lib.mc2_engine_profile(self._h, buf, size.value, C.byref(size)))
+        return json.loads(buf.raw[:size.value].decode())
+
+    def count_text(self, data, k: int, min_count: int) -> Table:
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_count_text(self._h, addr, n, space, k, min_count, C.byref(out)))
+        return Table(self, out)
+
+    def count_symbols(self, data, k: int, min_count: int = 1) -> Table:
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_count_symbols(self._h, addr, n, space, k, min_count, C.byref(out)))
+        return Table(self, out)
+
+    def count_sample(self, data, k: int, min_count: int, chunk_bytes: int = 0):
+        """-> (Table, piece start offsets)"""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        cap = 2 + (n // chunk_bytes if chunk_bytes else 0)
+        offs = (C.c_uint64 * cap)()
+        nchunks = C.c_uint64(0)
+        _check(self._lib, self._lib.mc2_count_sample(self._h, addr, n, space, k, min_count, chunk_bytes,
+                                                     C.byref(out), C.byref(nchunks), offs, cap))
+        return Table(self, out), [int(offs[i]) for i in range(min(cap, nchunks.value))]
+
+    def chunk_offsets(self, data, chunk_bytes: int) -> list:
+        """Byte offsets where the reference's Chunker starts each piece of this text."""
+        addr, n, space, keep = _as_buffer(data)
+        cap = 2 + (n // chunk_bytes if chunk_bytes else 0)
+        offs = (C.c_uint64 * cap)()
+        npieces = C.c_uint64(0)
+        _check(self._lib, self._lib.mc2_chunk_offsets(self._h, addr, n, space, chunk_bytes, offs, cap, C.byref(npieces)))
+        return [int(offs[i]) for i in range(min(cap, npieces.value))]
+
+    def sample(self, k: int, min_count: int) -> "Sample":
+        return Sample(self, k, min_count)
+
+    def _metrics_arrays(self, handle):
+        lib = self._lib
+        try:
+            r = int(lib.mc2_metrics_records(handle))
+            res = {
+                "header_off": np.empty(r, np.uint64), "header_len": np.empty(r, np.uint32),
+                "length": np.empty(r, np.uint64), "pi": np.empty(r, np.float64), "mw": np.empty(r, np.float64),
+                "hydro": np.empty(r, np.float64), "status": np.empty(r, np.uint8),
+            }
+            _check(lib, lib.mc2_metrics_export(handle, *[res[key].ctypes.data for key in
+                                                         ("header_off", "header_len", "length", "pi", "mw", "hydro", "status")]))
+        finally:
+            lib.mc2_metrics_free(handle)
+        return res
+
+    def sequence_metrics(self, seqs):
+        """Unrounded pI / MW / hydropathy for a list of raw sequences (str or bytes)."""
+        blobs = [s.encode("latin-1", errors="replace") if isinstance(s, str) else bytes(s) for s in seqs]
+        offsets = np.zeros(len(blobs) + 1, np.uint64)
+        if blobs:
+            offsets[1:] = np.cumsum([len(b) for b in blobs], dtype=np.uint64)
+        data = np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_sequence_metrics(self._h, data.ctypes.data, offsets.ctypes.data_as(_PU64),
+                                                         len(blobs), C.byref(out)))
+        return self._metrics_arrays(out)
+
+    def protein_metrics(self, data):
+        """-> dict of numpy arrays: header_off, header_len, length, pi, mw, hydro, status (unrounded)."""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_protein_metrics(self._h, addr, n, space, C.byref(out)))
+        return self._metrics_arrays(out)
+
+
+class Sample:
+    """Several files of one sample: each add_text() is chunked and counted like one chunk-file list."""
+
+    def __init__(self, engine: Engine, k: int, min_count: int):
+        self._engine = engine
+        self._h = C.c_void_p()
+        _check(engine._lib, engine._lib.mc2_sample_begin(engine._h, k, min_count, C.byref(self._h)))
+
+    def add_text(self, data, chunk_bytes: int = 0) -> int:
+        addr, n, space, keep = _as_buffer(data)
+        nchunks = C.c_uint64(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_sample_add_text(self._h, addr, n, space, chunk_bytes, C.byref(nchunks)))
+        return int(nchunks.value)
+
+    def finish(self) -> Table:
+        out = C.c_void_p()
+        lib = self._engine._lib
+        h, self._h = self._h, None
+        _check(lib, lib.mc2_sample_finish(h, C.byref(out)))
+        return Table(self._engine, out)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._engine._h:
+            self._engine._lib.mc2_sample_abort(self._h)
+            self._h = None
+
+
+_default_engines: dict = {}
+
+
+def default_engine(device: int | None = None) -> Engine:
+    """Process-wide engine for the drop-in module functions (device from MERCAT2_B200_DEVICE / LOCAL_RANK)."""
+    if device is None:
+        device = int(os.environ.get("MERCAT2_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    eng = _default_engines.get(device)
+    if eng is None:
+        eng = _default_engines[device] = Engine(device)
+    return eng

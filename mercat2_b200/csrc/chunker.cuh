@@ -1,0 +1,104 @@
+// A2 -- virtual Chunker: the split points of lib/mercat2_Chunker.py:39-59 computed on device, without
+// writing piece files.
+//
+// Reference rule (stream_delim): walking the text line by line (text mode, so "\r\n" has already
+// become "\n"), at every line that CONTAINS '>' the size of the current piece is compared with
+// chunksize; if size >= chunksize the line starts a new piece.  Piece size = bytes written so far =
+// translated length, i.e. raw length minus one per "\r\n" pair.
+//
+// Device formulation: a "candidate" is the first '>' of a line; its line start `ls` is found by
+// walking left from the '>' until a terminator (candidate) or another '>' (not the first: dropped),
+// so no cross-tile state is needed.  T(ls) = ls - #{"\r\n" pairs before ls} is the translated
+// offset; candidates come out ordered, T is monotonic, and the sequential rule becomes a chain of
+// lower_bound searches done by one thread (one search per piece).
+#pragma once
+#include "common.cuh"
+
+#define CH_THREADS 256
+#define CH_ITEMS 16
+#define CH_TILE (CH_THREADS * CH_ITEMS)
+
+__device__ __forceinline__ bool ch_is_nl(u32 c) { return c == 10u || c == 13u; }
+
+// returns true and the line start if text[p] == '>' is the first '>' of its line
+__device__ __forceinline__ bool ch_candidate(const u8* __restrict__ text, u64 p, u64& ls) {
+    u64 q = p;
+    while (q > 0) {
+        const u32 c = text[q - 1];
+        if (ch_is_nl(c)) break;
+        if (c == '>') return false;
+        --q;
+    }
+    ls = q;
+    return true;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(CH_THREADS)
+chunk_candidates_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ tile_crlf, u32* __restrict__ tile_cand,
+                        const u64* __restrict__ crlf_off, const u64* __restrict__ cand_off,
+                        u64* __restrict__ cand_ls, u64* __restrict__ cand_t) {
+    __shared__ u32 sm[CH_THREADS / 32 + 1];
+    const u64 first = (u64)blockIdx.x * CH_TILE + (u64)threadIdx.x * CH_ITEMS;
+    u32 ncrlf = 0, ncand = 0;
+    u32 candmask = 0, crlfmask = 0;
+    u64 ls_arr[CH_ITEMS];
+#pragma unroll
+    for (int j = 0; j < CH_ITEMS; ++j) {
+        const u64 p = first + j;
+        ls_arr[j] = 0;
+        if (p < n) {
+            const u32 c = text[p];
+            if (c == 13u && p + 1 < n && text[p + 1] == 10u) { ncrlf++; crlfmask |= 1u << j; }
+            if (c == '>') {
+                u64 ls;
+                if (ch_candidate(text, p, ls)) { ncand++; candmask |= 1u << j; ls_arr[j] = ls; }
+            }
+        }
+    }
+    if (!WRITE) {
+        u32 tc, tk;
+        block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncrlf, sm, &tc);
+        block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncand, sm, &tk);
+        if (threadIdx.x == 0) { tile_crlf[blockIdx.x] = tc; tile_cand[blockIdx.x] = tk; }
+    } else {
+        u64 crlf_before = crlf_off[blockIdx.x] + block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncrlf, sm, nullptr);
+        u64 u = cand_off[blockIdx.x] + block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncand, sm, nullptr);
+#pragma unroll
+        for (int j = 0; j < CH_ITEMS; ++j) {
+            if ((candmask >> j) & 1u) {
+                // no "\r\n" pair lies between the line start and the '>' (no terminators there)
+                cand_ls[u] = ls_arr[j];
+                cand_t[u] = ls_arr[j] - crlf_before;
+                ++u;
+            }
+            if ((crlfmask >> j) & 1u) ++crlf_before;
+        }
+    }
+}
+
+// one thread: bounds[0] = 0; then repeatedly the first candidate whose piece size reached chunk_bytes
+__global__ void chunk_select_kernel(const u64* __restrict__ cand_ls, const u64* __restrict__ cand_t, u64 ncand,
+                                    u64 chunk_bytes, u64* __restrict__ bounds, u64 max_bounds, ull* __restrict__ nbounds) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 nb = 0;
+    bounds[nb++] = 0;
+    u64 piece_t = 0;        // translated offset where the current piece starts
+    u64 from = 0;
+    while (from < ncand) {
+        const u64 target = piece_t + chunk_bytes;
+        u64 lo = from, hi = ncand;               // first j in [from, ncand) with cand_t[j] >= target
+        while (lo < hi) {
+            const u64 mid = lo + (hi - lo) / 2;
+            if (cand_t[mid] >= target) hi = mid; else lo = mid + 1;
+        }
+        if (lo >= ncand) break;
+        if (cand_ls[lo] != 0) {                  // a piece boundary at offset 0 is the file start itself
+            if (nb < max_bounds) bounds[nb] = cand_ls[lo];
+            nb++;
+        }
+        piece_t = cand_t[lo];
+        from = lo + 1;
+    }
+    *nbounds = nb;
+}

@@ -1,0 +1,1044 @@
+// mercat2_b200 engine: host orchestration + the C ABI of include/mercat2_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see mercat2_b200/build.py).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mercat2_b200.h"
+#include "common.cuh"
+#include "parse.cuh"
+#include "extract.cuh"
+#include "radix.cuh"
+#include "wide.cuh"
+#include "chunker.cuh"
+#include "metrics.cuh"
+
+static thread_local std::string g_err;
+
+// =====================================================================================================
+// engine
+// =====================================================================================================
+struct mc2_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int num_sms = 148;
+    // options
+    u64 opt_dense_max_bins = 1ull << 24;
+    u64 opt_smem_max_bins = 32768;
+    u64 opt_batch_symbols = 1ull << 28;
+    int opt_force_path = 0;
+    int opt_force_enc = -1;
+    // stats
+    u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0;
+    double device_us = 0;
+    // pinned scratch
+    void* pin_small = nullptr;                 // 4 KiB for scalar readbacks
+    u8* pin_stage[2] = {nullptr, nullptr};     // H2D staging for pageable sources
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    static constexpr u64 STAGE_BYTES = 32ull << 20;
+    // optional per-kernel timing (option "profile"): CUDA events around every launch on `stream`
+    int profile = 0;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    std::map<std::string, std::pair<u64, double>> prof_total;      // name -> (launches, microseconds)
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t ev = ev_pool.back(); ev_pool.pop_back(); return ev; }
+        cudaEvent_t ev;
+        CUDA_CHECK(cudaEventCreate(&ev));
+        return ev;
+    }
+    void resolve_profile() {
+        if (prof_pending.empty()) return;
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (auto& r : prof_pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+                auto& t = prof_total[r.name];
+                t.first++;
+                t.second += ms * 1000.0;
+            }
+            ev_pool.push_back(r.a);
+            ev_pool.push_back(r.b);
+        }
+        prof_pending.clear();
+    }
+};
+
+#define LAUNCHN(e, name, kern, grid, block, smem, ...)                            \
+    do {                                                                          \
+        cudaEvent_t _pa = nullptr, _pb = nullptr;                                 \
+        if ((e)->profile) {                                                       \
+            _pa = (e)->get_event();                                               \
+            _pb = (e)->get_event();                                               \
+            cudaEventRecord(_pa, (e)->stream);                                    \
+        }                                                                         \
+        kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);              \
+        if ((e)->profile) {                                                       \
+            cudaEventRecord(_pb, (e)->stream);                                    \
+            (e)->prof_pending.push_back({name, _pa, _pb});                        \
+            if ((e)->prof_pending.size() >= 4096) (e)->resolve_profile();         \
+        }                                                                         \
+        (e)->launches++;                                                          \
+        CUDA_CHECK(cudaGetLastError());                                           \
+    } while (0)
+#define LAUNCH(e, kern, grid, block, smem, ...) LAUNCHN(e, #kern, kern, grid, block, smem, __VA_ARGS__)
+
+template <typename T>
+struct DBuf {
+    mc2_engine* e = nullptr;
+    T* p = nullptr;
+    u64 n = 0;
+    DBuf() {}
+    DBuf(mc2_engine* e_, u64 n_) { alloc(e_, n_); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : e(o.e), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); e = o.e; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    void alloc(mc2_engine* e_, u64 n_) {
+        release();
+        e = e_;
+        n = n_;
+        u64 bytes = n * sizeof(T);
+        if (bytes < 256) bytes = 256;
+        CUDA_CHECK(cudaMallocAsync((void**)&p, bytes, e->stream));
+    }
+    void zero() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, std::max<u64>(n * sizeof(T), 1), e->stream)); }
+    void release() {
+        if (p) cudaFreeAsync(p, e->stream);
+        p = nullptr;
+        n = 0;
+    }
+    ~DBuf() { release(); }
+};
+
+template <typename T>
+static T read_scalar(mc2_engine* e, const T* dev) {
+    CUDA_CHECK(cudaMemcpyAsync(e->pin_small, dev, sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->d2h_bytes += sizeof(T);
+    T v;
+    memcpy(&v, e->pin_small, sizeof(T));
+    return v;
+}
+
+template <typename T>
+static void d2h(mc2_engine* e, T* host, const T* dev, u64 n) {
+    if (!n) return;
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->d2h_bytes += n * sizeof(T);
+}
+
+// ---- scans ---------------------------------------------------------------------------------------
+template <typename T, typename O>
+static void dev_exclusive_scan(mc2_engine* e, const T* in, O* out, u64 n, ull* total_dev) {
+    if (n == 0) {
+        if (total_dev) CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(ull), e->stream));
+        return;
+    }
+    const u64 ntiles = div_up(n, SCAN_TILE);
+    DBuf<u64> sums(e, ntiles);
+    LAUNCH(e, scan_reduce_kernel<T>, (unsigned)ntiles, SCAN_THREADS, 0, in, n, sums.p);
+    LAUNCH(e, scan_sums_kernel, 1, SCAN1_THREADS, 0, sums.p, (u32)ntiles, total_dev);
+    auto down = scan_down_kernel<T, O>;
+    LAUNCHN(e, "scan_down_kernel", down, (unsigned)ntiles, SCAN_THREADS, 0, in, out, n, sums.p);
+}
+
+// ---- radix sort ----------------------------------------------------------------------------------
+// Sorts n keys (and payloads) on bits [begin_bit, end_bit); returns which of the two buffers holds the
+// result (0 -> k0/v0, 1 -> k1/v1).
+template <typename V, bool HAS_V>
+static int radix_sort(mc2_engine* e, u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int end_bit) {
+    if (n >= (1ull << 32)) throw Mc2Error(MC2_ERR_LIMIT, "radix_sort: more than 2^32-1 keys in one batch");
+    if (n <= 1 || end_bit <= begin_bit) return 0;
+    const u32 ntiles = (u32)div_up(n, RS_TILE);
+    DBuf<u32> hist(e, 256ull * ntiles);
+    u64* kk[2] = {k0, k1};
+    V* vv[2] = {v0, v1};
+    int cur = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        LAUNCH(e, rs_hist_kernel, ntiles, RS_THREADS, 0, kk[cur], (u32)n, shift, hist.p, ntiles);
+        dev_exclusive_scan<u32, u32>(e, hist.p, hist.p, 256ull * ntiles, nullptr);
+        auto sc = rs_scatter_kernel<V, HAS_V>;
+        LAUNCHN(e, "rs_scatter_kernel", sc, ntiles, RS_THREADS, 0, kk[cur], kk[1 - cur], vv[cur], vv[1 - cur], (u32)n, shift, hist.p, ntiles);
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// ---- compaction helper: tile counts -> offsets + total (synchronises) ---------------------------
+static u64 offsets_from_counts(mc2_engine* e, const u32* tile_cnt, u64* tile_off, u64 ntiles) {
+    DBuf<ull> total(e, 1);
+    dev_exclusive_scan<u32, u64>(e, tile_cnt, tile_off, ntiles, total.p);
+    return (u64)read_scalar<ull>(e, total.p);
+}
+
+// =====================================================================================================
+// tables and sample accumulators
+// =====================================================================================================
+struct FastPart {          // sorted, unique (key, count) rows in the sample's fast encoding
+    DBuf<u64> keys, counts;
+    u64 n = 0;
+};
+struct WidePart {          // sorted, unique k-byte rows
+    DBuf<u8> rows;
+    DBuf<u64> counts;
+    u64 n = 0;
+};
+
+enum : int { PATH_UNSET = 0, PATH_DENSE = 1, PATH_SPARSE = 2, PATH_WIDE = 3 };
+enum : int { KEY_CODE = 0, KEY_DENSE_AA = 1 };   // how FastPart keys decode
+
+struct Plan {
+    int enc = -1;
+    int path = PATH_UNSET;
+    u32 bins = 0;
+    bool smem = false;
+    u32 nrep = 1;
+};
+
+struct mc2_sample {
+    mc2_engine* e = nullptr;
+    int k = 0;
+    u64 c = 1;
+    Plan plan;
+    DBuf<u64> dense_sample;
+    DBuf<u32> dense_chunk;
+    DBuf<u64> dense_chunk64;
+    std::vector<FastPart> fast;
+    std::vector<WidePart> wide;
+    u64 n_chunks = 0;
+};
+
+struct mc2_table {
+    mc2_engine* e = nullptr;
+    int k = 0;
+    int enc = ENC_NT2;
+    int key_kind = KEY_CODE;
+    FastPart fast;
+    WidePart wide;
+    // host side (filled by ensure_host)
+    bool on_host = false;
+    std::vector<char> kmers;
+    std::vector<u64> counts;
+    u64 total = 0;
+};
+
+// =====================================================================================================
+// K1 parse
+// =====================================================================================================
+struct Parsed {
+    DBuf<u8> sym;
+    u64 nsym = 0;
+    ParseStats stats;
+};
+
+static void parse_text(mc2_engine* e, const u8* dtext, u64 len, int toupper, Parsed& out) {
+    memset(&out.stats, 0, sizeof out.stats);
+    out.nsym = 0;
+    if (len == 0) return;
+    const u64 mis = (u64)(uintptr_t)dtext & 15ull;
+    const u64 ntiles = div_up(mis + len, PARSE_TILE);
+    if (ntiles >= (1ull << 31)) throw Mc2Error(MC2_ERR_LIMIT, "parse: text larger than 8 TiB");
+    DBuf<u8> tf(e, ntiles), tr(e, ntiles);
+    DBuf<u32> cnt(e, ntiles);
+    DBuf<u64> off(e, ntiles);
+    DBuf<ParseStats> st(e, 1);
+    st.zero();
+    LAUNCH(e, parse_summarize_kernel, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, st.p);
+    LAUNCH(e, parse_scan_tiles_kernel, 1, SCAN1_THREADS, 0, tf.p, tr.p, (u32)ntiles);
+    LAUNCH(e, parse_emit_kernel<false>, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, cnt.p,
+           (const u64*)nullptr, (u8*)nullptr, st.p, toupper);
+    dev_exclusive_scan<u32, u64>(e, cnt.p, off.p, ntiles, &st.p->n_sym);
+    out.stats = read_scalar<ParseStats>(e, st.p);
+    if (out.stats.n_bad)
+        throw Mc2Error(MC2_ERR_NON_ASCII, "input contains " + std::to_string(out.stats.n_bad) +
+                                              " non-ASCII byte(s); only 7-bit ASCII FASTA text is supported");
+    out.nsym = out.stats.n_sym;
+    out.sym.alloc(e, (out.nsym + 64) & ~15ull);
+    if (out.nsym)
+        LAUNCH(e, parse_emit_kernel<true>, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, cnt.p,
+               (const u64*)off.p, out.sym.p, st.p, toupper);
+}
+
+// =====================================================================================================
+// planning
+// =====================================================================================================
+static int enc_bits(int enc) { return enc == ENC_NT2 ? 2 : enc == ENC_AA5 ? 5 : 8; }
+
+static void make_plan(mc2_engine* e, const ParseStats& st, int k, Plan& plan) {
+    int enc;
+    if (e->opt_force_enc >= 0) enc = e->opt_force_enc;
+    else if (st.n_ascii == 0 || st.n_acgt * 10 >= st.n_ascii * 9) enc = ENC_NT2;
+    else if (st.n_upper * 2 >= st.n_ascii) enc = ENC_AA5;
+    else enc = ENC_BYTE;
+    plan.enc = enc;
+    const int kb = k * enc_bits(enc);
+    int path = kb <= 64 ? PATH_SPARSE : PATH_WIDE;
+    u64 bins = 0;
+    if (path == PATH_SPARSE && enc != ENC_BYTE) {
+        const u64 base = enc == ENC_NT2 ? 4 : 26;
+        bins = 1;
+        for (int i = 0; i < k && bins <= (1ull << 40); ++i) bins *= base;
+        if (bins <= e->opt_dense_max_bins && bins < (1ull << 31)) path = PATH_DENSE;
+    }
+    if (e->opt_force_path == PATH_SPARSE && kb <= 64) path = PATH_SPARSE;
+    if (e->opt_force_path == PATH_WIDE) path = PATH_WIDE;
+    if (e->opt_force_path == PATH_DENSE && bins && bins < (1ull << 31)) path = PATH_DENSE;
+    plan.path = path;
+    plan.bins = path == PATH_DENSE ? (u32)bins : 0;
+    plan.smem = path == PATH_DENSE && bins <= e->opt_smem_max_bins && bins * 4 <= 200 * 1024;
+    plan.nrep = 1;
+    if (plan.smem) {
+        u64 r = (48 * 1024) / (bins * 4);
+        plan.nrep = (u32)std::min<u64>(EX_WARPS, std::max<u64>(1, r));
+    }
+}
+
+// =====================================================================================================
+// reductions over sorted sequences
+// =====================================================================================================
+// unit weights: survivors of a sorted sequence of m items; returns count and fills start/count buffers
+template <class Acc>
+static u64 rle_threshold(mc2_engine* e, Acc acc, u64 m, u64 c, DBuf<u64>& start, DBuf<u64>& count) {
+    const u64 ntiles = div_up(m, RLE_THREADS);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, rle_count_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, c, tc.p);
+    const u64 ns = offsets_from_counts(e, tc.p, to.p, ntiles);
+    start.alloc(e, ns);
+    count.alloc(e, ns);
+    if (ns) LAUNCH(e, rle_write_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, c, (const u64*)to.p, start.p, count.p);
+    return ns;
+}
+
+// weighted: sorted items with weights w_sorted[i]; survivors have weight sum >= c
+template <class Acc>
+static u64 seg_reduce(mc2_engine* e, Acc acc, u64 m, const u64* w_sorted, u64 c, DBuf<u64>& start, DBuf<u64>& count) {
+    const u64 ntiles = div_up(m, RLE_THREADS);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, seg_count_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, tc.p);
+    const u64 nseg = offsets_from_counts(e, tc.p, to.p, ntiles);
+    DBuf<u64> seg_start(e, nseg), seg_sum(e, nseg);
+    LAUNCH(e, seg_write_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, (const u64*)to.p, seg_start.p);
+    DBuf<u64> wprefix(e, m);
+    DBuf<ull> wtotal(e, 1);
+    dev_exclusive_scan<u64, u64>(e, w_sorted, wprefix.p, m, wtotal.p);
+    const u64 wt = (u64)read_scalar<ull>(e, wtotal.p);
+    const u64 nt2 = div_up(nseg, RLE_THREADS);
+    DBuf<u32> tc2(e, nt2);
+    DBuf<u64> to2(e, nt2);
+    LAUNCH(e, seg_sum_count_kernel, (unsigned)nt2, RLE_THREADS, 0, (const u64*)seg_start.p, nseg, m, (const u64*)wprefix.p, wt, c,
+           seg_sum.p, tc2.p);
+    const u64 ns = offsets_from_counts(e, tc2.p, to2.p, nt2);
+    start.alloc(e, ns);
+    count.alloc(e, ns);
+    if (ns)
+        LAUNCH(e, seg_compact_kernel, (unsigned)nt2, RLE_THREADS, 0, (const u64*)seg_start.p, (const u64*)seg_sum.p, nseg, c,
+               (const u64*)to2.p, start.p, count.p);
+    return ns;
+}
+
+// merge several (key, count) parts: concat, sort pairs, sum equal keys, keep sums >= c
+static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int key_bits, u64 c, FastPart& out) {
+    u64 M = 0;
+    for (auto& p : parts) M += p.n;
+    out.n = 0;
+    if (M == 0) return;
+    if (parts.size() == 1 && c <= 1) { out = std::move(parts[0]); return; }
+    DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(k0.p + at, p.keys.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(v0.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += p.n;
+    }
+    const int r = radix_sort<u64, true>(e, k0.p, k1.p, v0.p, v1.p, M, 0, std::min(64, (key_bits + 7) & ~7));
+    const u64* ks = r ? k1.p : k0.p;
+    const u64* vs = r ? v1.p : v0.p;
+    DBuf<u64> start, count;
+    KeyEq acc{ks};
+    const u64 ns = seg_reduce(e, acc, M, vs, c, start, count);
+    out.n = ns;
+    out.keys.alloc(e, ns);
+    out.counts = std::move(count);
+    if (ns) LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, out.keys.p);
+}
+
+// order m windows (k bytes each, at src + pos[i]) and reduce; weights == nullptr means unit weights
+static void wide_reduce(mc2_engine* e, const u8* src, const u64* pos, const u64* weights, u64 m, int k, u64 c, WidePart& out) {
+    out.n = 0;
+    if (m == 0) return;
+    if (m >= (1ull << 32)) throw Mc2Error(MC2_ERR_LIMIT, "wide path: more than 2^32-1 windows in one batch");
+    DBuf<u32> i0(e, m), i1(e, m);
+    DBuf<u64> k0(e, m), k1(e, m);
+    LAUNCH(e, iota_u32_kernel, (unsigned)div_up(m, 256), 256, 0, i0.p, m);
+    u32* idx[2] = {i0.p, i1.p};
+    int cur = 0;
+    const int L = (k + 7) / 8;
+    for (int limb = L - 1; limb >= 0; --limb) {
+        LAUNCH(e, wide_gather_limb_kernel, (unsigned)div_up(m, 256), 256, 0, src, pos, (const u32*)idx[cur], m, k, limb, k0.p);
+        const int nb = std::min(8, k - 8 * limb);
+        const int r = radix_sort<u32, true>(e, k0.p, k1.p, idx[cur], idx[1 - cur], m, 8 * (8 - nb), 64);
+        if (r) cur ^= 1;     // an odd number of passes leaves the payload in the other buffer
+    }
+    const u32* sidx = idx[cur];
+    WindowEq acc{src, pos, sidx, k};
+    DBuf<u64> start, count;
+    u64 ns;
+    if (!weights) {
+        ns = rle_threshold(e, acc, m, c, start, count);
+    } else {
+        DBuf<u64> ws(e, m);
+        LAUNCH(e, gather_u64_by_u32_kernel, (unsigned)div_up(m, 256), 256, 0, weights, sidx, m, ws.p);
+        ns = seg_reduce(e, acc, m, (const u64*)ws.p, c, start, count);
+    }
+    out.n = ns;
+    out.rows.alloc(e, ns * (u64)k);
+    out.counts = std::move(count);
+    if (ns)
+        LAUNCH(e, wide_gather_rows_kernel, (unsigned)div_up(ns * (u64)k, 256), 256, 0, src, pos, sidx, (const u64*)start.p, ns, k,
+               out.rows.p);
+}
+
+static void reduce_wide_parts(mc2_engine* e, std::vector<WidePart>& parts, int k, u64 c, WidePart& out) {
+    u64 M = 0;
+    for (auto& p : parts) M += p.n;
+    out.n = 0;
+    if (M == 0) return;
+    if (parts.size() == 1 && c <= 1) { out = std::move(parts[0]); return; }
+    DBuf<u8> rows(e, M * (u64)k);
+    DBuf<u64> w(e, M), pos(e, M);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(rows.p + at * k, p.rows.p, p.n * (u64)k, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(w.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += p.n;
+    }
+    LAUNCH(e, wide_row_positions_kernel, (unsigned)div_up(M, 256), 256, 0, pos.p, M, k);
+    wide_reduce(e, rows.p, pos.p, w.p, M, k, c, out);
+}
+
+// =====================================================================================================
+// per-chunk counting
+// =====================================================================================================
+template <int ENC>
+static void dense_batch(mc2_engine* e, const Plan& plan, SymView v, u64 s0, u64 s1, int k, u32* table) {
+    const u64 ntiles = div_up(s1 - s0, EX_TILE);
+    if (plan.smem) {
+        auto kern = dense_smem_kernel<ENC>;
+        const size_t smem = (size_t)plan.bins * plan.nrep * 4;
+        static thread_local bool attr_set[3] = {false, false, false};
+        if (!attr_set[ENC]) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ENC] = true;
+        }
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        const u64 grid = std::min<u64>(ntiles, (u64)e->num_sms * per_sm);
+        LAUNCHN(e, "dense_smem_kernel", kern, (unsigned)grid, EX_THREADS, smem, v, s0, s1, k, plan.bins, plan.nrep, table);
+    } else {
+        auto kern = dense_global_kernel<ENC>;
+        LAUNCHN(e, "dense_global_kernel", kern, (unsigned)ntiles, EX_THREADS, 0, v, s0, s1, k, table);
+    }
+}
+
+template <int ENC>
+static void sparse_chunk(mc2_engine* e, mc2_sample* s, SymView v) {
+    const int k = s->k;
+    const int kb = k * EncTraits<ENC>::BITS;
+    const u64 batch = std::max<u64>(EX_TILE, e->opt_batch_symbols / EX_TILE * EX_TILE);
+    const u64 nb = div_up(v.n, batch);
+    std::vector<FastPart> partial;
+    for (u64 b = 0; b < nb; ++b) {
+        const u64 s0 = b * batch, s1 = std::min(v.n, s0 + batch);
+        const u64 cap = s1 - s0;
+        DBuf<u64> k0(e, cap), k1(e, cap);
+        DBuf<ull> nk(e, 1);
+        nk.zero();
+        auto kern = extract_keys_kernel<ENC>;
+        LAUNCHN(e, "extract_keys_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, 0, v, s0, s1, k, k0.p, nk.p);
+        const u64 m = (u64)read_scalar<ull>(e, nk.p);
+        if (!m) continue;
+        const int r = radix_sort<NoVal, false>(e, k0.p, k1.p, (NoVal*)nullptr, (NoVal*)nullptr, m, 0, std::min(64, (kb + 7) & ~7));
+        const u64* ks = r ? k1.p : k0.p;
+        KeyEq acc{ks};
+        DBuf<u64> start, count;
+        const u64 ns = rle_threshold(e, acc, m, nb == 1 ? s->c : 1, start, count);
+        if (!ns) continue;
+        FastPart part;
+        part.n = ns;
+        part.keys.alloc(e, ns);
+        part.counts = std::move(count);
+        LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, part.keys.p);
+        (nb == 1 ? s->fast : partial).push_back(std::move(part));
+    }
+    if (nb > 1 && !partial.empty()) {
+        FastPart merged;
+        // force the merge path even for a single partial so that the chunk threshold is applied
+        if (partial.size() == 1) partial.emplace_back();
+        reduce_fast_parts(e, partial, kb, s->c, merged);
+        if (merged.n) s->fast.push_back(std::move(merged));
+    }
+}
+
+template <int ENC>
+static void dense_chunk(mc2_engine* e, mc2_sample* s, SymView v) {
+    const Plan& plan = s->plan;
+    const u64 batch = std::max<u64>(EX_TILE, std::min<u64>(e->opt_batch_symbols, 1ull << 31) / EX_TILE * EX_TILE);
+    const u64 nb = div_up(v.n, batch);
+    const unsigned fgrid = (unsigned)div_up(plan.bins, 256);
+    for (u64 b = 0; b < nb; ++b) {
+        const u64 s0 = b * batch, s1 = std::min(v.n, s0 + batch);
+        dense_batch<ENC>(e, plan, v, s0, s1, s->k, s->dense_chunk.p);
+        if (nb > 1) {
+            if (!s->dense_chunk64.p) { s->dense_chunk64.alloc(e, plan.bins); s->dense_chunk64.zero(); }
+            LAUNCH(e, dense_fold_batch_kernel, fgrid, 256, 0, s->dense_chunk.p, s->dense_chunk64.p, plan.bins);
+        }
+    }
+    if (nb > 1) LAUNCH(e, dense_fold64_kernel, fgrid, 256, 0, s->dense_chunk64.p, s->dense_sample.p, plan.bins, s->c);
+    else LAUNCH(e, dense_fold_kernel, fgrid, 256, 0, s->dense_chunk.p, s->dense_sample.p, plan.bins, s->c);
+}
+
+// exception / all-window positions -> wide reduce -> append
+template <int ENC, int MODE>
+static void wide_chunk(mc2_engine* e, mc2_sample* s, SymView v, u64 cap_hint) {
+    const int k = s->k;
+    const u64 batch = std::max<u64>(EX_TILE, e->opt_batch_symbols / EX_TILE * EX_TILE);
+    const u64 nb = div_up(v.n, batch);
+    std::vector<WidePart> partial;
+    for (u64 b = 0; b < nb; ++b) {
+        const u64 s0 = b * batch, s1 = std::min(v.n, s0 + batch);
+        u64 cap = std::min<u64>(s1 - s0, cap_hint);
+        DBuf<ull> np(e, 1);
+        u64 m = 0;
+        DBuf<u64> pos;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            pos.alloc(e, cap);
+            np.zero();
+            auto kern = extract_positions_kernel<ENC, MODE>;
+            LAUNCHN(e, "extract_positions_kernel", kern, (unsigned)div_up(s1 - s0, EX_TILE), EX_THREADS, 0, v, s0, s1, k, pos.p, cap, np.p);
+            m = (u64)read_scalar<ull>(e, np.p);
+            if (m <= cap) break;
+            cap = m;                       // hint was too small: rerun with the exact size
+        }
+        if (!m) continue;
+        WidePart part;
+        wide_reduce(e, v.sym, pos.p, nullptr, m, k, nb == 1 ? s->c : 1, part);
+        if (part.n) (nb == 1 ? s->wide : partial).push_back(std::move(part));
+    }
+    if (nb > 1 && !partial.empty()) {
+        WidePart merged;
+        if (partial.size() == 1) partial.emplace_back();
+        reduce_wide_parts(e, partial, k, s->c, merged);
+        if (merged.n) s->wide.push_back(std::move(merged));
+    }
+}
+
+// raw symbol stream (calculateKmerCount: no FASTA parsing): copy into an aligned buffer + statistics
+static void adopt_symbols(mc2_engine* e, const u8* dsym, u64 len, Parsed& out) {
+    memset(&out.stats, 0, sizeof out.stats);
+    out.nsym = len;
+    if (!len) return;
+    out.sym.alloc(e, (len + 64) & ~15ull);
+    CUDA_CHECK(cudaMemcpyAsync(out.sym.p, dsym, len, cudaMemcpyDeviceToDevice, e->stream));
+    DBuf<ParseStats> st(e, 1);
+    st.zero();
+    LAUNCH(e, symbol_stats_kernel, (unsigned)std::min<u64>(div_up(len, 256 * 16), 4096), 256, 0, (const u8*)out.sym.p, len, st.p);
+    out.stats = read_scalar<ParseStats>(e, st.p);
+    if (out.stats.n_bad)
+        throw Mc2Error(MC2_ERR_NON_ASCII, "sequence contains non-ASCII characters; only 7-bit ASCII is supported");
+}
+
+static void count_chunk(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, bool raw_symbols = false) {
+    s->n_chunks++;
+    e->chunks++;
+    Parsed ps;
+    if (raw_symbols) adopt_symbols(e, dtext, len, ps);
+    else parse_text(e, dtext, len, 0, ps);
+    if (ps.nsym == 0) return;
+    if (s->plan.path == PATH_UNSET) {
+        if (ps.stats.n_ascii == 0) return;           // only separators so far: decide on a later chunk
+        make_plan(e, ps.stats, s->k, s->plan);
+        if (s->plan.path == PATH_DENSE) {
+            s->dense_sample.alloc(e, s->plan.bins);
+            s->dense_sample.zero();
+            s->dense_chunk.alloc(e, s->plan.bins);
+            s->dense_chunk.zero();
+        }
+    }
+    const Plan& plan = s->plan;
+    SymView v{ps.sym.p, ps.nsym};
+    const u64 n_fast_syms = plan.enc == ENC_NT2 ? ps.stats.n_acgt : plan.enc == ENC_AA5 ? ps.stats.n_upper : ps.stats.n_ascii;
+    const u64 n_slow_syms = ps.stats.n_ascii - n_fast_syms;
+    if (plan.path == PATH_WIDE) {
+        wide_chunk<ENC_BYTE, 1>(e, s, v, ~0ull);
+        return;
+    }
+    if (plan.path == PATH_DENSE) {
+        if (plan.enc == ENC_NT2) dense_chunk<ENC_NT2>(e, s, v); else dense_chunk<ENC_AA5>(e, s, v);
+    } else {
+        if (plan.enc == ENC_NT2) sparse_chunk<ENC_NT2>(e, s, v);
+        else if (plan.enc == ENC_AA5) sparse_chunk<ENC_AA5>(e, s, v);
+        else sparse_chunk<ENC_BYTE>(e, s, v);
+    }
+    if (n_slow_syms) {
+        const u64 hint = std::max<u64>(1024, n_slow_syms * (u64)s->k);
+        if (plan.enc == ENC_NT2) wide_chunk<ENC_NT2, 0>(e, s, v, hint);
+        else if (plan.enc == ENC_AA5) wide_chunk<ENC_AA5, 0>(e, s, v, hint);
+    }
+}
+
+// =====================================================================================================
+// text upload and chunk boundaries
+// =====================================================================================================
+static const u8* to_device(mc2_engine* e, const void* text, u64 nbytes, int space, DBuf<u8>& holder) {
+    if (space == MC2_DEVICE || nbytes == 0) return (const u8*)text;
+    holder.alloc(e, nbytes + 16);
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, text) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned) {
+        CUDA_CHECK(cudaMemcpyAsync(holder.p, text, nbytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        // pageable source: double-buffered pinned staging so the CPU copy overlaps the DMA
+        const u8* src = (const u8*)text;
+        int slot = 0;
+        for (u64 at = 0; at < nbytes; at += mc2_engine::STAGE_BYTES, slot ^= 1) {
+            const u64 nb = std::min<u64>(mc2_engine::STAGE_BYTES, nbytes - at);
+            CUDA_CHECK(cudaEventSynchronize(e->stage_ev[slot]));
+            memcpy(e->pin_stage[slot], src + at, nb);
+            CUDA_CHECK(cudaMemcpyAsync(holder.p + at, e->pin_stage[slot], nb, cudaMemcpyHostToDevice, e->stream));
+            CUDA_CHECK(cudaEventRecord(e->stage_ev[slot], e->stream));
+        }
+    }
+    e->h2d_bytes += nbytes;
+    return holder.p;
+}
+
+static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 chunk_bytes) {
+    std::vector<u64> bounds(1, 0);
+    if (chunk_bytes == 0 || n == 0) return bounds;
+    const u64 ntiles = div_up(n, CH_TILE);
+    DBuf<u32> tcr(e, ntiles), tca(e, ntiles);
+    DBuf<u64> ocr(e, ntiles), oca(e, ntiles);
+    LAUNCH(e, chunk_candidates_kernel<false>, (unsigned)ntiles, CH_THREADS, 0, dtext, n, tcr.p, tca.p, (const u64*)nullptr,
+           (const u64*)nullptr, (u64*)nullptr, (u64*)nullptr);
+    dev_exclusive_scan<u32, u64>(e, tcr.p, ocr.p, ntiles, nullptr);
+    const u64 ncand = offsets_from_counts(e, tca.p, oca.p, ntiles);
+    if (!ncand) return bounds;
+    DBuf<u64> cls(e, ncand), ct(e, ncand);
+    LAUNCH(e, chunk_candidates_kernel<true>, (unsigned)ntiles, CH_THREADS, 0, dtext, n, tcr.p, tca.p, (const u64*)ocr.p,
+           (const u64*)oca.p, cls.p, ct.p);
+    const u64 max_bounds = n / chunk_bytes + 2;
+    DBuf<u64> db(e, max_bounds);
+    DBuf<ull> nbd(e, 1);
+    LAUNCH(e, chunk_select_kernel, 1, 32, 0, (const u64*)cls.p, (const u64*)ct.p, ncand, chunk_bytes, db.p, max_bounds, nbd.p);
+    const u64 nbounds = (u64)read_scalar<ull>(e, nbd.p);
+    if (nbounds > max_bounds) throw Mc2Error(MC2_ERR_LIMIT, "chunker: boundary buffer overflow");
+    bounds.resize(nbounds);
+    d2h(e, bounds.data(), db.p, nbounds);
+    return bounds;
+}
+
+static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u64 chunk_bytes, u64* n_chunks,
+                       std::vector<u64>* bounds_out) {
+    mc2_engine* e = s->e;
+    DBuf<u8> holder;
+    const u8* d = to_device(e, text, nbytes, space, holder);
+    std::vector<u64> bounds = chunk_bounds(e, d, nbytes, chunk_bytes);
+    for (size_t i = 0; i < bounds.size(); ++i) {
+        const u64 a = bounds[i], b = i + 1 < bounds.size() ? bounds[i + 1] : nbytes;
+        count_chunk(e, s, d + a, b - a);
+    }
+    if (n_chunks) *n_chunks = bounds.size();
+    if (bounds_out) *bounds_out = bounds;
+}
+
+static mc2_table* sample_finish(mc2_sample* s) {
+    mc2_engine* e = s->e;
+    std::unique_ptr<mc2_table> t(new mc2_table);
+    t->e = e;
+    t->k = s->k;
+    t->enc = s->plan.enc < 0 ? ENC_NT2 : s->plan.enc;
+    if (s->plan.path == PATH_DENSE) {
+        const u32 bins = s->plan.bins;
+        const u64 ntiles = div_up(bins, 256);
+        DBuf<u32> tc(e, ntiles);
+        DBuf<u64> to(e, ntiles);
+        LAUNCH(e, dense_nonzero_count_kernel, (unsigned)ntiles, 256, 0, (const u64*)s->dense_sample.p, bins, tc.p);
+        const u64 ns = offsets_from_counts(e, tc.p, to.p, ntiles);
+        t->fast.n = ns;
+        t->fast.keys.alloc(e, ns);
+        t->fast.counts.alloc(e, ns);
+        if (ns)
+            LAUNCH(e, dense_nonzero_write_kernel, (unsigned)ntiles, 256, 0, (const u64*)s->dense_sample.p, bins, (const u64*)to.p,
+                   t->fast.keys.p, t->fast.counts.p);
+        t->key_kind = s->plan.enc == ENC_AA5 ? KEY_DENSE_AA : KEY_CODE;
+    } else if (!s->fast.empty()) {
+        reduce_fast_parts(e, s->fast, s->k * enc_bits(t->enc), 1, t->fast);
+    }
+    if (!s->wide.empty()) reduce_wide_parts(e, s->wide, s->k, 1, t->wide);
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    return t.release();
+}
+
+// =====================================================================================================
+// export
+// =====================================================================================================
+static void decode_key(const mc2_table* t, u64 key, char* out) {
+    const int k = t->k;
+    if (t->key_kind == KEY_DENSE_AA) {
+        for (int j = k - 1; j >= 0; --j) { out[j] = (char)('A' + key % 26); key /= 26; }
+    } else if (t->enc == ENC_NT2) {
+        for (int j = k - 1; j >= 0; --j) { out[j] = "ACGT"[key & 3]; key >>= 2; }
+    } else if (t->enc == ENC_AA5) {
+        for (int j = k - 1; j >= 0; --j) { out[j] = (char)('A' + (key & 31)); key >>= 5; }
+    } else {
+        for (int j = k - 1; j >= 0; --j) { out[j] = (char)(key & 255); key >>= 8; }
+    }
+}
+
+static void ensure_host(mc2_table* t) {
+    if (t->on_host) return;
+    mc2_engine* e = t->e;
+    const u64 nf = t->fast.n, nw = t->wide.n, k = t->k;
+    std::vector<u64> fk(nf), fc(nf), wc(nw);
+    std::vector<u8> wr(nw * k);
+    d2h(e, fk.data(), t->fast.keys.p, nf);
+    d2h(e, fc.data(), t->fast.counts.p, nf);
+    d2h(e, wc.data(), t->wide.counts.p, nw);
+    d2h(e, wr.data(), t->wide.rows.p, nw * k);
+    t->kmers.resize((nf + nw) * k);
+    t->counts.resize(nf + nw);
+    std::vector<char> tmp(k + 1);
+    u64 i = 0, j = 0, o = 0, total = 0;
+    bool have = false;
+    while (i < nf || j < nw) {
+        bool take_fast;
+        if (i < nf && !have) { decode_key(t, fk[i], tmp.data()); have = true; }
+        if (i >= nf) take_fast = false;
+        else if (j >= nw) take_fast = true;
+        else take_fast = memcmp(tmp.data(), wr.data() + j * k, k) < 0;     // the two sets are disjoint
+        if (take_fast) { memcpy(&t->kmers[o * k], tmp.data(), k); t->counts[o] = fc[i]; ++i; have = false; }
+        else { memcpy(&t->kmers[o * k], wr.data() + j * k, k); t->counts[o] = wc[j]; ++j; }
+        total += t->counts[o];
+        ++o;
+    }
+    t->total = total;
+    t->on_host = true;
+}
+
+static std::string tsv_of(mc2_table* t, const char* basename) {
+    ensure_host(t);
+    const u64 rows = t->counts.size(), k = t->k;
+    std::string s;
+    s.reserve(32 + strlen(basename) + rows * (k + 12));
+    s += "k-mer\t";
+    s += basename;
+    s += "_Count\n";
+    char num[32];
+    for (u64 r = 0; r < rows; ++r) {
+        s.append(&t->kmers[r * k], k);
+        s += '\t';
+        int len = snprintf(num, sizeof num, "%llu", (ull)t->counts[r]);
+        s.append(num, len);
+        s += '\n';
+    }
+    return s;
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define API_BEGIN try {
+#define API_END                                                   \
+    }                                                             \
+    catch (const Mc2Error& err) { g_err = err.what(); return err.code; } \
+    catch (const std::exception& err) { g_err = err.what(); return MC2_ERR_INVALID; } \
+    return MC2_OK;
+
+extern "C" {
+
+const char* mc2_last_error(void) { return g_err.c_str(); }
+const char* mc2_version(void) { return "mercat2_b200 0.1 (sm_100a)"; }
+
+int mc2_engine_create(int device, mc2_engine** out) {
+    API_BEGIN
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        throw Mc2Error(MC2_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(st) +
+                                         "); mercat2_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) throw Mc2Error(MC2_ERR_INVALID, "bad device index");
+    CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<mc2_engine> e(new mc2_engine);
+    e->device = device;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaMallocHost(&e->pin_small, 4096));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_CHECK(cudaMallocHost((void**)&e->pin_stage[i], mc2_engine::STAGE_BYTES));
+        CUDA_CHECK(cudaEventCreateWithFlags(&e->stage_ev[i], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreate(&e->ev0));
+    CUDA_CHECK(cudaEventCreate(&e->ev1));
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    u64 thresh = ~0ull;                       // keep freed blocks cached in the pool
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    *out = e.release();
+    API_END
+}
+
+void mc2_engine_destroy(mc2_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (e->pin_stage[i]) cudaFreeHost(e->pin_stage[i]);
+        if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
+    }
+    if (e->pin_small) cudaFreeHost(e->pin_small);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
+    API_BEGIN
+    if (!e || !name) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    const std::string n(name);
+    if (n == "dense_max_bins") e->opt_dense_max_bins = (u64)value;
+    else if (n == "smem_max_bins") e->opt_smem_max_bins = (u64)value;
+    else if (n == "batch_symbols") e->opt_batch_symbols = (u64)std::max<int64_t>(value, EX_TILE);
+    else if (n == "force_path") e->opt_force_path = (int)value;
+    else if (n == "force_encoding") e->opt_force_enc = (int)value;
+    else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
+    else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);
+    API_END
+}
+
+int64_t mc2_engine_get_stat(mc2_engine* e, const char* name) {
+    if (!e || !name) return -1;
+    const std::string n(name);
+    if (n == "launches") return (int64_t)e->launches;
+    if (n == "h2d_bytes") return (int64_t)e->h2d_bytes;
+    if (n == "d2h_bytes") return (int64_t)e->d2h_bytes;
+    if (n == "chunks") return (int64_t)e->chunks;
+    if (n == "device_us") return (int64_t)e->device_us;
+    if (n == "num_sms") return e->num_sms;
+    return -1;
+}
+
+int mc2_engine_profile(mc2_engine* e, char* buf, uint64_t cap, uint64_t* size) {
+    API_BEGIN
+    if (!e) throw Mc2Error(MC2_ERR_INVALID, "engine is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    e->resolve_profile();
+    std::string js = "{";
+    bool first = true;
+    for (auto& kv : e->prof_total) {
+        char tmp[256];
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %llu, \"us\": %.3f}", first ? "" : ", ", kv.first.c_str(),
+                 (ull)kv.second.first, kv.second.second);
+        js += tmp;
+        first = false;
+    }
+    js += "}";
+    if (size) *size = js.size();
+    if (buf) {
+        if (cap < js.size()) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+        memcpy(buf, js.data(), js.size());
+    }
+    API_END
+}
+
+static void check_count_args(mc2_engine* e, const void* text, u64 nbytes, int k) {
+    if (!e) throw Mc2Error(MC2_ERR_INVALID, "engine is NULL");
+    if (!text && nbytes) throw Mc2Error(MC2_ERR_INVALID, "text is NULL");
+    if (k < 1) throw Mc2Error(MC2_ERR_INVALID, "k must be >= 1");
+    if (k > 128) throw Mc2Error(MC2_ERR_LIMIT, "k > 128 is not supported");
+}
+
+int mc2_sample_begin(mc2_engine* e, int k, int64_t min_count, mc2_sample** out) {
+    API_BEGIN
+    check_count_args(e, "", 0, k);
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    mc2_sample* s = new mc2_sample;
+    s->e = e;
+    s->k = k;
+    s->c = min_count < 1 ? 1 : (u64)min_count;
+    *out = s;
+    API_END
+}
+
+int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes, uint64_t* n_chunks) {
+    API_BEGIN
+    if (!s) throw Mc2Error(MC2_ERR_INVALID, "sample is NULL");
+    check_count_args(s->e, text, nbytes, s->k);
+    CUDA_CHECK(cudaSetDevice(s->e->device));
+    u64 nc = 0;
+    sample_add(s, text, nbytes, space, chunk_bytes, &nc, nullptr);
+    if (n_chunks) *n_chunks = nc;
+    API_END
+}
+
+int mc2_sample_finish(mc2_sample* s, mc2_table** out) {
+    API_BEGIN
+    if (!s || !out) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    std::unique_ptr<mc2_sample> guard(s);
+    CUDA_CHECK(cudaSetDevice(s->e->device));
+    *out = sample_finish(s);
+    API_END
+}
+
+void mc2_sample_abort(mc2_sample* s) {
+    if (!s) return;
+    cudaSetDevice(s->e->device);
+    delete s;
+}
+
+int mc2_count_sample(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
+                     uint64_t chunk_bytes, mc2_table** out, uint64_t* n_chunks, uint64_t* piece_offsets,
+                     uint64_t piece_capacity) {
+    API_BEGIN
+    check_count_args(e, text, nbytes, k);
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_sample> s(new mc2_sample);
+    s->e = e;
+    s->k = k;
+    s->c = min_count < 1 ? 1 : (u64)min_count;
+    CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
+    u64 nc = 0;
+    std::vector<u64> bounds;
+    sample_add(s.get(), text, nbytes, space, chunk_bytes, &nc, &bounds);
+    mc2_table* t = sample_finish(s.get());
+    CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+    CUDA_CHECK(cudaEventSynchronize(e->ev1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->device_us = ms * 1000.0;
+    e->resolve_profile();
+    if (n_chunks) *n_chunks = nc;
+    if (piece_offsets)
+        for (u64 i = 0; i < bounds.size() && i < piece_capacity; ++i) piece_offsets[i] = bounds[i];
+    *out = t;
+    API_END
+}
+
+int mc2_count_text(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, mc2_table** out) {
+    return mc2_count_sample(e, text, nbytes, space, k, min_count, 0, out, nullptr, nullptr, 0);
+}
+
+int mc2_count_symbols(mc2_engine* e, const void* symbols, uint64_t nbytes, int space, int k, int64_t min_count, mc2_table** out) {
+    API_BEGIN
+    check_count_args(e, symbols, nbytes, k);
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_sample> s(new mc2_sample);
+    s->e = e;
+    s->k = k;
+    s->c = min_count < 1 ? 1 : (u64)min_count;
+    DBuf<u8> holder;
+    const u8* d = to_device(e, symbols, nbytes, space, holder);
+    count_chunk(e, s.get(), d, nbytes, true);
+    *out = sample_finish(s.get());
+    API_END
+}
+
+int mc2_chunk_offsets(mc2_engine* e, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes,
+                      uint64_t* piece_offsets, uint64_t piece_capacity, uint64_t* n_pieces) {
+    API_BEGIN
+    if (!e || (!text && nbytes)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    DBuf<u8> holder;
+    const u8* d = to_device(e, text, nbytes, space, holder);
+    const std::vector<u64> bounds = chunk_bounds(e, d, nbytes, chunk_bytes);
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (n_pieces) *n_pieces = bounds.size();
+    if (piece_offsets)
+        for (u64 i = 0; i < bounds.size() && i < piece_capacity; ++i) piece_offsets[i] = bounds[i];
+    API_END
+}
+
+uint64_t mc2_table_rows(const mc2_table* t) { return t ? t->fast.n + t->wide.n : 0; }
+int mc2_table_k(const mc2_table* t) { return t ? t->k : 0; }
+uint64_t mc2_table_total(const mc2_table* t) {
+    if (!t) return 0;
+    try { ensure_host(const_cast<mc2_table*>(t)); } catch (...) { return 0; }
+    return t->total;
+}
+
+int mc2_table_export(mc2_table* t, char* kmers, uint64_t* counts) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "table is NULL");
+    CUDA_CHECK(cudaSetDevice(t->e->device));
+    ensure_host(t);
+    if (kmers && !t->kmers.empty()) memcpy(kmers, t->kmers.data(), t->kmers.size());
+    if (counts && !t->counts.empty()) memcpy(counts, t->counts.data(), t->counts.size() * 8);
+    API_END
+}
+
+int mc2_table_tsv(mc2_table* t, const char* basename, char* buf, uint64_t cap, uint64_t* size) {
+    API_BEGIN
+    if (!t || !basename) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(t->e->device));
+    const std::string s = tsv_of(t, basename);
+    if (size) *size = s.size();
+    if (buf) {
+        if (cap < s.size()) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+        memcpy(buf, s.data(), s.size());
+    }
+    API_END
+}
+
+int mc2_table_write_tsv(mc2_table* t, const char* path, const char* basename) {
+    try {
+        if (!t || !path || !basename) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+        if (mc2_table_rows(t) == 0) return 1;
+        CUDA_CHECK(cudaSetDevice(t->e->device));
+        const std::string s = tsv_of(t, basename);
+        FILE* f = fopen(path, "wb");
+        if (!f) throw Mc2Error(MC2_ERR_IO, std::string("cannot open ") + path);
+        const size_t w = fwrite(s.data(), 1, s.size(), f);
+        fclose(f);
+        if (w != s.size()) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
+    } catch (const Mc2Error& err) { g_err = err.what(); return err.code; }
+    catch (const std::exception& err) { g_err = err.what(); return MC2_ERR_INVALID; }
+    return MC2_OK;
+}
+
+void mc2_table_free(mc2_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->e->device);
+    delete t;
+}
+
+}  // extern "C"
+
+#include "metrics_api.inl"

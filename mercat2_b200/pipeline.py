@@ -1,0 +1,54 @@
+"""The reference's per-sample driver glue (bin/mercat2.py:86-137) on top of the engine.
+
+``chunk_files`` -> a chunk size instead of piece files (virtual chunking), ``countKmers`` /
+``run_mercat2`` -> one engine sample per input sample: every file is split at the reference's piece
+boundaries on device, each piece is counted and filtered with ``-c`` on its own, the filtered
+tables are summed, the sorted TSV is written."""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+
+from . import _native
+from .mercat2_kmers import read_text_bytes
+
+
+def chunk_trigger(filename, chunk_size_mb: int) -> int:
+    """bin/mercat2.py:101 (+ ``-s 0`` at :314/:417): chunk only if the ON-DISK size (gz size for
+    .gz files) reaches ``chunk_size_mb`` MiB.  Returns the chunk size in bytes, 0 = do not chunk."""
+    if chunk_size_mb and chunk_size_mb > 0 and os.stat(filename).st_size >= chunk_size_mb * 1024 * 1024:
+        return chunk_size_mb * 1024 * 1024
+    return 0
+
+
+def count_files(files, kmer: int, min_count: int, chunk_size_mb: int = 0, engine=None):
+    """-> (Table, number of pieces counted) for one sample given its original file(s)."""
+    engine = engine or _native.default_engine()
+    sample = engine.sample(kmer, min_count)
+    pieces = 0
+    for file in files:
+        pieces += sample.add_text(read_text_bytes(Path(file)), chunk_trigger(file, chunk_size_mb))
+    return sample.finish(), pieces
+
+
+def countKmers(file, kmer, min_count):
+    """bin/mercat2.py:112-114"""
+    from .mercat2_kmers import find_kmers
+    return find_kmers(Path(file), kmer, min_count)
+
+
+def run_mercat2(basename: str, files: list, out_file, kmer, min_count, num_cores=None, chunk_size_mb: int = 0,
+                engine=None, quiet: bool = False):
+    """bin/mercat2.py:115-137.  ``files`` are the sample's files: either the reference's piece files
+    (then ``chunk_size_mb`` stays 0) or the original file with ``chunk_size_mb`` = ``-s``.
+    Returns ``(basename, out_file)`` or ``(basename, None)`` when no k-mer survives (no file written)."""
+    table, _ = count_files(files, kmer, min_count, chunk_size_mb, engine)
+    rows = table.rows
+    if rows:
+        if not quiet:
+            print(f"Significant k-mers: {rows}")
+        table.write_tsv(out_file, basename)
+        return basename, out_file
+    if not quiet:
+        print("No significant k-mers found")
+    return basename, None

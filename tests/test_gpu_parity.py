@@ -1,0 +1,368 @@
+"""GPU parity: the CUDA path through the C ABI against the oracle and the reference's golden vectors.
+Bit-exact for counts (integer/byte work); pI / MW / hydropathy compared after the reference's own
+round(x, 2) and additionally within 1e-6 relative on the unrounded values."""
+import gzip
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, read_maybe_gz
+from oracle import mercat2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import mercat2_b200
+    eng = mercat2_b200.Engine(0)
+    yield eng
+    eng.close()
+
+
+def reset(engine):
+    engine.set_option("force_path", 0)
+    engine.set_option("force_encoding", -1)
+    engine.set_option("batch_symbols", 1 << 28)
+    engine.set_option("dense_max_bins", 1 << 24)
+    engine.set_option("smem_max_bins", 32768)
+
+
+def diff_msg(got, want):
+    missing = sorted(set(want) - set(got))[:5]
+    extra = sorted(set(got) - set(want))[:5]
+    wrong = [(k, got[k], want[k]) for k in sorted(set(got) & set(want)) if got[k] != want[k]][:5]
+    return f"rows got={len(got)} want={len(want)} missing={missing} extra={extra} wrong={wrong}"
+
+
+def check(engine, text, k, c, want, label):
+    got = engine.count_text(text, k, c).to_dict()
+    assert got == want, f"{label}: {diff_msg(got, want)}"
+
+
+# ---- 1. the edge-case corpus, every path --------------------------------------------------------
+def test_edge_cases_auto(engine, edge_cases):
+    reset(engine)
+    for case in edge_cases:
+        check(engine, case["text"], case["k"], case["min_count"], case["expected"],
+              f"{case['name']} k={case['k']} c={case['min_count']}")
+
+
+@pytest.mark.parametrize("path", [2, 3])
+def test_edge_cases_forced_paths(engine, edge_cases, path):
+    reset(engine)
+    engine.set_option("force_path", path)
+    try:
+        for case in edge_cases:
+            check(engine, case["text"], case["k"], case["min_count"], case["expected"],
+                  f"path={path} {case['name']} k={case['k']} c={case['min_count']}")
+    finally:
+        reset(engine)
+
+
+@pytest.mark.parametrize("enc", [0, 1, 2])
+def test_edge_cases_forced_encodings(engine, edge_cases, enc):
+    reset(engine)
+    engine.set_option("force_encoding", enc)
+    try:
+        for case in edge_cases:
+            check(engine, case["text"], case["k"], case["min_count"], case["expected"],
+                  f"enc={enc} {case['name']} k={case['k']} c={case['min_count']}")
+    finally:
+        reset(engine)
+
+
+def test_misaligned_device_and_host_buffers(engine, edge_cases):
+    import torch
+    reset(engine)
+    case = next(c for c in edge_cases if c["name"] == "multi_line_wrapped" and c["k"] == 12)
+    for shift in (1, 3, 7, 15, 16, 17):
+        host = np.frombuffer(b"#" * shift + case["text"], dtype=np.uint8)
+        got = engine.count_text(host[shift:], case["k"], case["min_count"]).to_dict()
+        assert got == case["expected"], f"host shift {shift}"
+        dev = torch.from_numpy(host.copy()).cuda()
+        got = engine.count_text(dev[shift:], case["k"], case["min_count"]).to_dict()
+        assert got == case["expected"], f"device shift {shift}"
+
+
+def test_non_ascii_is_rejected(engine):
+    import mercat2_b200
+    with pytest.raises(mercat2_b200.NonAsciiError):
+        engine.count_text(">r\nAC\xc3\xa9GT\n".encode("latin-1"), 2, 1)
+    with pytest.raises(mercat2_b200.Mc2Error):
+        engine.count_text(b">r\nACGT\n", 0, 1)
+
+
+def test_calculate_kmer_count(engine):
+    from mercat2_b200 import mercat2_kmers
+    reset(engine)
+    rng = random.Random(5)
+    for seq, k in [("ACGTACGTAC", 3), ("AC", 3), ("MKV*LA>G\nX", 2), ("acgtNNACGT" * 30, 12),
+                   ("".join(rng.choice("ACGT") for _ in range(5000)), 31),
+                   ("".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(3000)), 4)]:
+        assert mercat2_kmers.calculateKmerCount(seq, k) == orc.calculate_kmer_count(seq, k), (seq[:20], k)
+
+
+# ---- 2. BASELINE configs --------------------------------------------------------------------------
+@pytest.mark.parametrize("base", ["DJ_pro", "GIC31_pro", "RW1_pro", "RW2_pro", "Rleg_pro"])
+def test_config2_protein_k3_c10(engine, base, golden_configs):
+    reset(engine)
+    text = read_maybe_gz(GOLDEN / "data/faa_gz" / f"{base}.faa.gz")
+    table = engine.count_text(text, 3, 10)
+    want = golden_configs["protein_k3_c10"][base]
+    assert table.rows == want["rows"] and table.total == want["total"]
+    tsv = table.tsv_bytes(base)
+    assert tsv == gzip.open(GOLDEN / "expected" / f"{base}_k3_c10.tsv.gz", "rb").read()
+    assert md5(tsv) == want["tsv_md5"]
+
+
+@pytest.mark.parametrize("base", ["DJ", "GIC31", "RW1", "RW2", "Rleg"])
+def test_config1_nucleotide_k3_c10(engine, base, golden_configs, tmp_path):
+    from mercat2_b200 import mercat2_fasta, mercat2_kmers
+    reset(engine)
+    clean, _ = mercat2_fasta.removeN(GOLDEN / "data/fna_gz" / f"{base}.fna.gz", tmp_path / "clean", False)
+    text = mercat2_kmers.read_text_bytes(clean)
+    assert md5(text) == golden_configs["removeN"][base]["clean_md5"]
+    table = engine.count_text(text, 3, 10)
+    want = golden_configs["nucleotide_k3_c10"][base]
+    assert table.rows == want["rows"] and table.total == want["total"]
+    tsv = table.tsv_bytes(base)
+    assert tsv == (GOLDEN / "expected" / f"{base}_k3_c10.tsv").read_bytes()
+    # the same file through the other counting paths
+    for path in (2, 3):
+        engine.set_option("force_path", path)
+        try:
+            if path == 3 and base not in ("RW1",):
+                continue
+            assert md5(engine.count_text(text, 3, 10).tsv_bytes(base)) == want["tsv_md5"], f"path {path}"
+        finally:
+            reset(engine)
+
+
+def test_config3_test_r1_k12(engine, golden_configs, tmp_path):
+    from mercat2_b200 import mercat2_fasta, mercat2_kmers
+    reset(engine)
+    fna = mercat2_fasta.fq2fa(str(GOLDEN / "data/Test_R1.fastq.gz"), str(tmp_path / "clean"), "Test_R1")
+    text = mercat2_kmers.read_text_bytes(fna)
+    for force in (0, 2, 3):
+        engine.set_option("force_path", force)
+        try:
+            for c in (1, 2, 10):
+                table = engine.count_text(text, 12, c)
+                want = golden_configs["test_r1_k12"][f"c{c}"]
+                assert table.rows == want["rows"], (force, c)
+                assert table.total == want["total"], (force, c)
+                assert md5(table.tsv_bytes("Test_R1")) == want["tsv_md5"], (force, c)
+                if c == 2:
+                    assert table.tsv_bytes("Test_R1") == (GOLDEN / "expected/Test_R1_k12_c2.tsv").read_bytes()
+        finally:
+            reset(engine)
+    # drop-in entry point + "no TSV when nothing survives"
+    d = mercat2_kmers.find_kmers(__import__("pathlib").Path(fna), 12, 1)
+    assert len(d) == golden_configs["test_r1_k12"]["c1"]["rows"] and sum("N" in w for w in d) == 19
+    assert engine.count_text(text, 12, 10).write_tsv(tmp_path / "none.tsv", "Test_R1") is False
+    assert not (tmp_path / "none.tsv").exists()
+
+
+# ---- 3. the reference's committed result tree: k=5 c=10, -s 1 and -s 10 ------------------------------
+@pytest.mark.parametrize("base", ["DJ_pro", "GIC31_pro", "RW1_pro", "RW2_pro", "Rleg_pro"])
+def test_protein_k5_chunked_and_unchunked(engine, base, reference_results, tmp_path):
+    from mercat2_b200 import pipeline
+    reset(engine)
+    text = read_maybe_gz(GOLDEN / "data/faa_gz" / f"{base}.faa.gz")
+    src = tmp_path / f"{base}.faa"
+    src.write_bytes(text)
+    # -s 10: no file reaches 10 MiB -> one piece
+    want = reference_results["faa-5genomes-10"]["tsv"][base]
+    name, out = pipeline.run_mercat2(base, [src], tmp_path / "u.tsv", 5, 10, chunk_size_mb=10, engine=engine, quiet=True)
+    blob = open(out, "rb").read()
+    assert blob.count(b"\n") - 1 == want["rows"] and md5(blob) == want["tsv_md5"]
+    # -s 1: virtual pieces must equal the reference's piece files, and the per-piece filter applies
+    run = reference_results["faa-5genomes-1"]
+    chunk_bytes = pipeline.chunk_trigger(src, 1)
+    offsets = engine.chunk_offsets(text, chunk_bytes) if chunk_bytes else [0]
+    sizes = [b - a for a, b in zip(offsets, offsets[1:] + [len(text)])]
+    want_sizes = [p["bytes"] for p in run["chunks"].get(base, [{"bytes": len(text)}])]
+    assert sizes == want_sizes
+    for (a, n), piece in zip(zip(offsets, sizes), run["chunks"].get(base, [])):
+        assert md5(text[a:a + n]) == piece["md5"]
+    name, out = pipeline.run_mercat2(base, [src], tmp_path / "c.tsv", 5, 10, chunk_size_mb=1, engine=engine, quiet=True)
+    blob = open(out, "rb").read()
+    want = run["tsv"][base]
+    assert blob.count(b"\n") - 1 == want["rows"] and md5(blob) == want["tsv_md5"]
+
+
+@pytest.mark.parametrize("base", ["RW1", "Rleg", "DJ"])
+def test_nucleotide_k5_gz_chunked(engine, base, reference_results, tmp_path):
+    from mercat2_b200 import mercat2_fasta, pipeline
+    reset(engine)
+    clean, _ = mercat2_fasta.removeN(GOLDEN / "data/fna_gz" / f"{base}.fna.gz", tmp_path / "clean", False)
+    for s in (1, 10):
+        want = reference_results[f"fna-5genomes_gz-{s}"]["tsv"][base]
+        name, out = pipeline.run_mercat2(base, [clean], tmp_path / f"{s}.tsv", 5, 10, chunk_size_mb=s, engine=engine, quiet=True)
+        blob = open(out, "rb").read()
+        assert blob.count(b"\n") - 1 == want["rows"] and md5(blob) == want["tsv_md5"], s
+    if base == "Rleg":
+        text = gzip.open(clean, "rb").read()
+        pieces = reference_results["fna-5genomes_gz-1"]["chunks"]["Rleg"]
+        offsets = engine.chunk_offsets(text, 1 << 20)
+        sizes = [b - a for a, b in zip(offsets, offsets[1:] + [len(text)])]
+        assert sizes == [p["bytes"] for p in pieces]
+
+
+# ---- 4. synthetic data against the oracle -----------------------------------------------------------
+def synth_reads(n_reads, read_len, seed, n_rate=0.0, lower_rate=0.0, genome_len=200000):
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, genome_len, dtype=np.uint8)
+    starts = rng.integers(0, genome_len - read_len, n_reads)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lines = []
+    for i, s in enumerate(starts):
+        seq = lut[genome[s:s + read_len]].copy()
+        if n_rate:
+            seq[rng.random(read_len) < n_rate] = ord("N")
+        if lower_rate and rng.random() < lower_rate:
+            seq = np.frombuffer(seq.tobytes().lower(), dtype=np.uint8)
+        lines.append(b">r%010d\n" % i + seq.tobytes() + b"\n")
+    return b"".join(lines)
+
+
+@pytest.mark.parametrize("k,c", [(31, 1), (31, 2), (32, 2), (21, 3), (13, 2), (12, 2), (33, 2), (40, 1)])
+def test_synthetic_reads_vs_oracle(engine, k, c):
+    reset(engine)
+    text = synth_reads(6000, 150, seed=k * 7 + c, n_rate=0.002, lower_rate=0.01)
+    want = orc.find_kmers_text(text.decode(), k, c)
+    check(engine, text, k, c, want, f"reads k={k} c={c}")
+    if k <= 32:
+        engine.set_option("batch_symbols", 65536)          # several batches per chunk
+        try:
+            check(engine, text, k, c, want, f"reads batched k={k} c={c}")
+        finally:
+            reset(engine)
+
+
+@pytest.mark.parametrize("k,c", [(3, 10), (5, 2), (6, 2), (12, 2), (13, 1)])
+def test_synthetic_protein_vs_oracle(engine, k, c):
+    reset(engine)
+    rng = np.random.default_rng(100 + k)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXBZUO", dtype=np.uint8)
+    recs = []
+    for i in range(800):
+        n = int(rng.integers(20, 900))
+        seq = letters[rng.integers(0, 20 if i % 50 else 25, n)].tobytes()
+        body = b"\n".join(seq[j:j + 60] for j in range(0, n, 60))
+        recs.append(b">p%d some protein\n" % i + body + b"*\n")
+    text = b"".join(recs)
+    want = orc.find_kmers_text(text.decode(), k, c)
+    check(engine, text, k, c, want, f"protein k={k} c={c}")
+    for path in (2, 3):
+        engine.set_option("force_path", path)
+        engine.set_option("batch_symbols", 32768)
+        try:
+            check(engine, text, k, c, want, f"protein path={path} k={k} c={c}")
+        finally:
+            reset(engine)
+
+
+def test_virtual_chunking_vs_oracle(engine, tmp_path):
+    """Chunker split points + per-piece filter + sum on synthetic reads with CRLF line ends."""
+    reset(engine)
+    text = synth_reads(20000, 100, seed=11, genome_len=3000).replace(b"\n", b"\r\n")
+    src = tmp_path / "reads.fna"
+    src.write_bytes(text)
+    for chunk in (1 << 20, 300000, 100000):
+        pieces = orc.chunker_pieces(open(src, "r"), chunk)
+        sizes = []
+        want = orc.merge_counts(orc.find_kmers_text("".join(p), 9, 5) for p in pieces)
+        # raw byte size of each piece: every line regains its "\r"
+        raw_sizes = [sum(len(l) + 1 for l in p) for p in pieces]
+        offsets = engine.chunk_offsets(text, chunk)
+        got_sizes = [b - a for a, b in zip(offsets, offsets[1:] + [len(text)])]
+        assert got_sizes == raw_sizes, chunk
+        table, offs2 = engine.count_sample(text, 9, 5, chunk)
+        assert offs2 == offsets
+        got = table.to_dict()
+        assert got == want, f"chunk={chunk}: {diff_msg(got, want)}"
+
+
+def test_large_dense_and_sparse_properties(engine):
+    """Size-independent properties at a larger size: sum of counts == number of windows; forcing
+    another path gives the same table; c filter is monotone."""
+    reset(engine)
+    n_reads, L = 200000, 150
+    text = synth_reads(n_reads, L, seed=3, genome_len=2_000_000)
+    for k in (4, 12, 31):
+        table = engine.count_text(text, k, 1)
+        assert table.total == n_reads * (L - k + 1), k
+        kmers, counts = table.arrays()
+        order = np.lexsort(kmers.T[::-1])
+        assert (order == np.arange(len(order))).all(), "rows must be sorted by k-mer text"
+        engine.set_option("force_path", 2)
+        try:
+            t2 = engine.count_text(text, k, 1)
+            k2, c2 = t2.arrays()
+            assert (k2 == kmers).all() and (c2 == counts).all()
+        finally:
+            reset(engine)
+        t3 = engine.count_text(text, k, 3)
+        k3, c3 = t3.arrays()
+        keep = counts >= 3
+        assert (k3 == kmers[keep]).all() and (c3 == counts[keep]).all()
+
+
+# ---- 5. protein metrics -----------------------------------------------------------------------------
+def test_metrics_golden_table(engine):
+    from mercat2_b200 import mercat2_metrics
+    rows = gzip.open(GOLDEN / "metrics_DJ_pro.tsv.gz", "rt").read().splitlines()[1:]
+    want = {}
+    for row in rows:
+        header, name, length, pi, mw, hydro = row.split("\t")
+        want[header] = (name, float(length), float(pi), float(mw), float(hydro))
+    got = mercat2_metrics.file_metrics(GOLDEN / "data/faa_gz/DJ_pro.faa.gz", engine)
+    assert len(got) == len(want) == 4852
+    lengths = [r[2] for r in got]
+    assert lengths == sorted(lengths, reverse=True)
+    bad = [(h, (n, l, pi, mw, hy), want[h]) for h, n, l, pi, mw, hy in got if want[h] != (n, l, pi, mw, hy)]
+    assert not bad, bad[:3]
+
+
+def test_metrics_unrounded_vs_oracle(engine):
+    text = read_maybe_gz(GOLDEN / "data/faa_gz/RW1_pro.faa.gz")
+    res = engine.protein_metrics(text)
+    recs = [(n, s) for n, s in orc.protein_records(text.decode().splitlines(True)) if s]
+    assert len(recs) == len(res["length"])
+    for i, (name, seq) in enumerate(recs):
+        off, ln = int(res["header_off"][i]), int(res["header_len"][i])
+        assert text[off:off + ln].decode() == name
+        assert int(res["length"][i]) == len(seq)
+        assert res["pi"][i] == orc.isoelectric_point_unrounded(seq)          # same bisection path
+        assert abs(res["mw"][i] - orc.molecular_weight_unrounded(seq)) <= 1e-6 * abs(res["mw"][i])
+        assert abs(res["hydro"][i] - orc.hydropathy_unrounded(seq)) <= 1e-6 * max(1.0, abs(res["hydro"][i]))
+
+
+def test_metrics_scalar_entry_points(engine, capsys):
+    from mercat2_b200 import mercat2_metrics as mm
+    for item in json.load(open(GOLDEN / "metrics_odd.json")):
+        assert mm.predict_isoelectric_point_ProMoST(item["seq"]) == item["pI"], item
+        assert mm.calculate_MW(item["seq"]) == item["MW"], item
+        assert mm.calculate_hydro(item["seq"]) == item["hydro"], item
+    with pytest.raises(KeyError):
+        mm.predict_isoelectric_point_ProMoST("*MK")
+    with pytest.raises(IndexError):
+        mm.predict_isoelectric_point_ProMoST("")
+    odd = ">a x\n  MK*L*  \n*\nAB *\n>b\n\n>c\nMKV\r\n"
+    got = mm.file_metrics_text(odd.encode(), engine)
+    want = []
+    for name, seq in orc.protein_records(odd.splitlines(True)):
+        if seq:
+            want.append((name, name.split()[0], float(len(seq)), orc.predict_isoelectric_point_ProMoST(seq),
+                         orc.calculate_MW(seq), orc.calculate_hydro(seq)))
+    assert sorted(got) == sorted(want)

@@ -1,0 +1,91 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host helpers (human2bytes, piece names, removeN, fastq->fasta) match golden vectors
+made by the reference, and the product refuses to run without a GPU (no CPU fallback)."""
+import gzip
+import hashlib
+import re
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+def test_library_exports_every_declared_symbol():
+    from mercat2_b200 import _native
+    header = (ROOT / "include" / "mercat2_b200.h").read_text()
+    declared = set(re.findall(r"\b(mc2_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in _native.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.mc2_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mercat2_b200 import _native, mercat2_kmers
+    with pytest.raises(_native.Mc2Error):
+        _native.Engine(0)
+    with pytest.raises(_native.Mc2Error):
+        mercat2_kmers.calculateKmerCount("ACGTACGT", 3)
+
+
+def test_product_does_not_import_oracle():
+    for path in (ROOT / "mercat2_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_human2bytes_and_piece_names():
+    from mercat2_b200.mercat2_Chunker import human2bytes, piece_name
+    assert human2bytes("0 B") == 0 and human2bytes("1 K") == 1024 and human2bytes("1M") == 1 << 20
+    assert human2bytes("1 Gi") == 1 << 30 and human2bytes("1 tera") == 1 << 40
+    assert human2bytes("0.5kilo") == 512 and human2bytes("0.1  byte") == 0 and human2bytes("1 k") == 1024
+    with pytest.raises(ValueError):
+        human2bytes("12 foo")
+    assert piece_name("x/c.fna", 0) == "c.00000"
+    assert piece_name("x/c_clean.fna.gz", 2) == "c_clean.00002.fna"
+    assert piece_name("DJ_pro.faa", 1) == "DJ_pro.00001"
+
+
+@pytest.mark.parametrize("base", ["RW1", "GIC31"])
+def test_removeN_matches_reference(base, golden_configs, tmp_path):
+    from mercat2_b200.mercat2_fasta import removeN
+    out, stats = removeN(GOLDEN / "data/fna_gz" / f"{base}.fna.gz", tmp_path / "clean", False)
+    assert out.name == f"{base}_clean.fna.gz"
+    blob = gzip.open(out, "rb").read()
+    want = golden_configs["removeN"][base]
+    assert len(blob) == want["clean_bytes"] and md5(blob) == want["clean_md5"]
+    assert 0.0 < stats["GC Content"] < 100.0
+
+
+@pytest.mark.parametrize("toupper", [False, True])
+def test_removeN_scaffolds_with_N_runs(toupper, golden_configs, tmp_path):
+    from mercat2_b200.mercat2_fasta import removeN
+    src = tmp_path / "Scaffolds_with-NNN.fna"
+    src.write_bytes(gzip.open(GOLDEN / "data/Scaffolds_with-NNN.fna.gz", "rb").read())
+    out, _ = removeN(src, tmp_path / "clean", toupper)
+    blob = gzip.open(out, "rb").read()
+    want = golden_configs["removeN"]["Scaffolds_toupper" if toupper else "Scaffolds"]
+    assert len(blob) == want["clean_bytes"] and md5(blob) == want["clean_md5"]
+
+
+def test_fq2fa_matches_reference(golden_configs, tmp_path):
+    from mercat2_b200.mercat2_fasta import fq2fa
+    out = fq2fa(str(GOLDEN / "data/Test_R1.fastq.gz"), str(tmp_path / "clean"), "Test_R1")
+    assert out.endswith("Test_R1.fna.gz")
+    assert md5(gzip.open(out, "rb").read()) == golden_configs["test_r1_k12"]["fasta_md5"]
+
+
+def test_chunk_trigger(tmp_path):
+    from mercat2_b200.pipeline import chunk_trigger
+    f = tmp_path / "x.fa"
+    f.write_bytes(b"A" * (1 << 20))
+    assert chunk_trigger(f, 1) == 1 << 20 and chunk_trigger(f, 2) == 0 and chunk_trigger(f, 0) == 0
