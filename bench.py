@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("-c", type=int, default=10)
     ap.add_argument("-s", type=int, default=100, help="chunk size in MB (reference default 100)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU sample (0 = auto)")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of the 1 Gbp metagenome to synthesise (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -231,7 +232,7 @@ def main():
 
     n_reads = args.reads_per_gpu
     bases_per_step = n_reads * READ_LEN
-    genomes = make_genomes(device)
+    genomes = make_genomes(device, args.genome_scale)
     text = make_reads_text(device, genomes, n_reads, rank * n_reads)
     torch.cuda.synchronize()
     nbytes = text.numel()

@@ -39,9 +39,16 @@ static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 // Returns the combination of all elements before this thread (identity for thread 0); *total (if
 // given) receives the combination over the whole block.
 // ---------------------------------------------------------------------------------------------
+//
+// NOTE on convergence: every block-/warp-collective helper here starts with __syncwarp().  Measured on
+// B200 (sm_100a, CUDA 12.9): after a data-dependent loop with early exits the compiler's
+// BSSY/BSYNC.RECONVERGENT pair did NOT leave the warp converged for the SHFL / BAR.RED that followed
+// (shuffle-based scans returned garbage, __syncthreads_count under-counted); an explicit WARPSYNC
+// fixes both.  For the same reason __syncthreads_count/_or are not used: see block_count().
 template <class Op, int NWARPS>
 __device__ __forceinline__ u32 block_exclusive_scan(u32 x, u32* smem /*NWARPS+1 words*/, u32* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncwarp();
     u32 incl = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -81,6 +88,7 @@ struct OpAdd {
 template <int NWARPS>
 __device__ __forceinline__ u64 block_exclusive_sum64(u64 x, u64* smem /*NWARPS+1*/, u64* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncwarp();
     u64 incl = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -106,6 +114,26 @@ __device__ __forceinline__ u64 block_exclusive_sum64(u64 x, u64* smem /*NWARPS+1
     u64 base = smem[warp];
     if (total) *total = smem[NWARPS];
     return base + excl;
+}
+
+// number of threads of the block whose predicate is true (all threads must call; <= 32 warps)
+__device__ __forceinline__ u32 block_count(bool pred) {
+    __shared__ u32 s_block_count[33];
+    __syncwarp();
+    const u32 b = __ballot_sync(0xffffffffu, pred);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_block_count[warp] = __popc(b);
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        u32 v = lane < nw ? s_block_count[lane] : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) s_block_count[32] = v;
+    }
+    __syncthreads();
+    return s_block_count[32];
 }
 
 __device__ __forceinline__ uint4 ld_nc_16(const void* p) {

@@ -18,6 +18,7 @@
 #define EX_THREADS 256
 #define EX_WARPS (EX_THREADS / 32)
 #define EX_TILE (EX_THREADS * 16)
+#define EX_HALO 8                    // halo threads left of a tile: 128 symbols >= k-1 for k <= 128
 
 enum : int { ENC_NT2 = 0, ENC_AA5 = 1, ENC_BYTE = 2 };
 
@@ -89,30 +90,38 @@ struct TileCtx {
     u32 run_nosep;   // same for non-separator symbols
 };
 
-// smem: s_code[EX_THREADS + 2], s_meta[EX_THREADS + 2]
+// smem: s_code[EX_THREADS + EX_HALO], s_meta[EX_THREADS + EX_HALO]
 template <int ENC>
-__device__ __forceinline__ void tile_begin(const SymView& v, u64 tile_start, u64* s_code, u32* s_meta, TileCtx<ENC>& ctx) {
+__device__ __forceinline__ void tile_begin(const SymView& v, u64 tile_start, int k, u64* s_code, u32* s_meta, TileCtx<ENC>& ctx) {
     const int t = threadIdx.x;
     load_sym16(v, (i64)tile_start + 16 * t, ctx.w);
     u64 code; u32 meta;
     summarize_sym16<ENC>(ctx.w, code, meta);
-    s_code[t + 2] = code;
-    s_meta[t + 2] = meta;
-    if (t < 2) {                                   // the 32 symbols left of the tile
+    s_code[t + EX_HALO] = code;
+    s_meta[t + EX_HALO] = meta;
+    if (t < EX_HALO) {                             // the 128 symbols left of the tile
         u32 hw[4];
-        load_sym16(v, (i64)tile_start - 16 * (2 - t), hw);
+        load_sym16(v, (i64)tile_start - 16 * (EX_HALO - t), hw);
         u64 hc; u32 hm;
         summarize_sym16<ENC>(hw, hc, hm);
         s_code[t] = hc;
         s_meta[t] = hm;
     }
     __syncthreads();
-    const u64 c1 = s_code[t + 1], c2 = s_code[t];
-    const u32 m1 = s_meta[t + 1], m2 = s_meta[t];
+    const u64 c1 = s_code[t + EX_HALO - 1], c2 = s_code[t + EX_HALO - 2];
     ctx.code = (EncTraits<ENC>::BITS == 2) ? ((c2 << 32) | (c1 & 0xFFFFFFFFull)) : c1;
-    const u32 f1 = m1 & 0xFFu, f2 = m2 & 0xFFu, n1 = m1 >> 8, n2 = m2 >> 8;
-    ctx.run_fast = f1 < 16 ? f1 : 16 + f2;
-    ctx.run_nosep = n1 < 16 ? n1 : 16 + n2;
+    // run lengths ending just before this thread: walk left while whole 16-symbol groups qualify
+    const int need = min(EX_HALO, (k + 14) / 16);          // ceil((k-1)/16) groups can matter
+    u32 rf = 0, rs = 0;
+    bool open_f = true, open_s = true;
+    for (int j = 1; j <= need; ++j) {
+        const u32 m = s_meta[t + EX_HALO - j];
+        const u32 f = m & 0xFFu, n = m >> 8;
+        if (open_f) { rf += f; open_f = f == 16; }
+        if (open_s) { rs += n; open_s = n == 16; }
+    }
+    ctx.run_fast = rf;
+    ctx.run_nosep = rs;
 }
 
 // Walk the thread's 16 symbols.  f(i, code, is_fast_window, is_exception_window) is called for every
@@ -127,8 +136,8 @@ __device__ __forceinline__ void tile_walk(TileCtx<ENC>& ctx, int k, F&& f) {
         const u32 c = (ctx.w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
         const bool fast = E::fast(c);
         code = (code << E::BITS) | (fast ? E::digit(c) : 0u);
-        rf = fast ? min(rf + 1, 64u) : 0u;
-        rs = (c != MC2_SEP) ? min(rs + 1, 64u) : 0u;
+        rf = fast ? min(rf + 1, 255u) : 0u;
+        rs = (c != MC2_SEP) ? min(rs + 1, 255u) : 0u;
         if (rs >= (u32)k) f(i, code, rf >= (u32)k);
     }
 }
@@ -150,8 +159,8 @@ __global__ void __launch_bounds__(EX_THREADS)
 dense_smem_kernel(SymView v, u64 s0, u64 s1, int k, u32 bins, u32 nrep, u32* __restrict__ table) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* hist = reinterpret_cast<u32*>(dyn);                 // [nrep][bins]
-    __shared__ u64 s_code[EX_THREADS + 2];
-    __shared__ u32 s_meta[EX_THREADS + 2];
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     for (u32 i = threadIdx.x; i < bins * nrep; i += EX_THREADS) hist[i] = 0;
     __syncthreads();
     const u64 mask = (2 * k >= 64) ? ~0ull : ((1ull << (2 * k)) - 1);
@@ -160,7 +169,7 @@ dense_smem_kernel(SymView v, u64 s0, u64 s1, int k, u32 bins, u32 nrep, u32* __r
     for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u64 tile_start = s0 + tile * EX_TILE;
         TileCtx<ENC> ctx;
-        tile_begin<ENC>(v, tile_start, s_code, s_meta, ctx);
+        tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
         const u64 first = tile_start + 16ull * threadIdx.x;
         tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
             if (fast && first + i < s1) atomicAdd(&my[dense_index<ENC>(code, k, mask)], 1u);
@@ -179,12 +188,12 @@ dense_smem_kernel(SymView v, u64 s0, u64 s1, int k, u32 bins, u32 nrep, u32* __r
 template <int ENC>
 __global__ void __launch_bounds__(EX_THREADS)
 dense_global_kernel(SymView v, u64 s0, u64 s1, int k, u32* __restrict__ table) {
-    __shared__ u64 s_code[EX_THREADS + 2];
-    __shared__ u32 s_meta[EX_THREADS + 2];
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     const u64 mask = (2 * k >= 64) ? ~0ull : ((1ull << (2 * k)) - 1);
     const u64 tile_start = s0 + (u64)blockIdx.x * EX_TILE;
     TileCtx<ENC> ctx;
-    tile_begin<ENC>(v, tile_start, s_code, s_meta, ctx);
+    tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
     const u64 first = tile_start + 16ull * threadIdx.x;
     tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
         if (fast && first + i < s1) atomicAdd(&table[dense_index<ENC>(code, k, mask)], 1u);
@@ -212,7 +221,7 @@ __global__ void dense_fold64_kernel(u64* __restrict__ chunk64, u64* __restrict__
 
 __global__ void __launch_bounds__(256) dense_nonzero_count_kernel(const u64* __restrict__ sample, u32 bins, u32* __restrict__ tile_cnt) {
     const u32 b = blockIdx.x * 256 + threadIdx.x;
-    const u32 total = __syncthreads_count(b < bins && sample[b] != 0);
+    const u32 total = block_count(b < bins && sample[b] != 0);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 __global__ void __launch_bounds__(256)
@@ -228,8 +237,8 @@ dense_nonzero_write_kernel(const u64* __restrict__ sample, u32 bins, const u64* 
 template <int ENC>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_keys_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ keys, ull* __restrict__ nkeys) {
-    __shared__ u64 s_code[EX_THREADS + 2];
-    __shared__ u32 s_meta[EX_THREADS + 2];
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     __shared__ u64 s_keys[EX_TILE];
     __shared__ u32 sm[EX_WARPS + 1];
     __shared__ ull s_base;
@@ -237,7 +246,7 @@ extract_keys_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ keys, ul
     const u64 mask = kb >= 64 ? ~0ull : ((1ull << kb) - 1);
     const u64 tile_start = s0 + (u64)blockIdx.x * EX_TILE;
     TileCtx<ENC> ctx;
-    tile_begin<ENC>(v, tile_start, s_code, s_meta, ctx);
+    tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
     const u64 first = tile_start + 16ull * threadIdx.x;
     u64 mine[16];
     u32 valid = 0;
@@ -261,13 +270,13 @@ extract_keys_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ keys, ul
 template <int ENC, int MODE>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_positions_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ pos, u64 cap, ull* __restrict__ npos) {
-    __shared__ u64 s_code[EX_THREADS + 2];
-    __shared__ u32 s_meta[EX_THREADS + 2];
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     __shared__ u32 sm[EX_WARPS + 1];
     __shared__ ull s_base;
     const u64 tile_start = s0 + (u64)blockIdx.x * EX_TILE;
     TileCtx<ENC> ctx;
-    tile_begin<ENC>(v, tile_start, s_code, s_meta, ctx);
+    tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
     const u64 first = tile_start + 16ull * threadIdx.x;
     u32 sel = 0;
     tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {

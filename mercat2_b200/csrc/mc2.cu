@@ -1,6 +1,7 @@
 // mercat2_b200 engine: host orchestration + the C ABI of include/mercat2_b200.h.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a (see mercat2_b200/build.py).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>

@@ -43,7 +43,7 @@ mt_lines_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ tile_cnt, 
     const u64 p = (u64)blockIdx.x * 256 + threadIdx.x;
     const bool is_start = p < n && (p == 0 || mt_is_nl(text[p - 1]));
     if (!WRITE) {
-        const u32 total = __syncthreads_count(is_start);
+        const u32 total = block_count(is_start);
         if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
     } else {
         const u32 off = block_exclusive_scan<OpAdd, 8>(is_start ? 1u : 0u, sm, nullptr);
@@ -105,7 +105,7 @@ mt_headers_kernel(const LineStat* __restrict__ ls, u64 nlines, u32* __restrict__
     const u64 l = (u64)blockIdx.x * 256 + threadIdx.x;
     const bool h = l < nlines && ls[l].is_header;
     if (!WRITE) {
-        const u32 total = __syncthreads_count(h);
+        const u32 total = block_count(h);
         if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
     } else {
         const u32 off = block_exclusive_scan<OpAdd, 8>(h ? 1u : 0u, sm, nullptr);

@@ -122,6 +122,7 @@ __device__ __forceinline__ u64 classify16(const u32 w[4], u32& fwd, u32& rev, u3
 // there is none (caller substitutes the tile's follow class).  smem: PARSE_WARPS words.
 __device__ __forceinline__ u32 block_follow_class(u32 rev, u32* smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncwarp();
     const u32 nn = __ballot_sync(0xffffffffu, rev != R_NONE);
     const u32 first_lane = nn ? (u32)(__ffs(nn) - 1) : 0u;
     const u32 warp_first = __shfl_sync(0xffffffffu, rev, first_lane);
@@ -157,11 +158,12 @@ parse_summarize_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ ti
     block_exclusive_scan<FwdOp, PARSE_WARPS>(fwd, sm, &total);
     // first non-NONE over the block, in order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncwarp();
     const u32 nn = __ballot_sync(0xffffffffu, rev != R_NONE);
     const u32 first_lane = nn ? (u32)(__ffs(nn) - 1) : 0u;
     const u32 wf = __shfl_sync(0xffffffffu, rev, first_lane);
     if (lane == 0) sm2[warp] = nn ? wf : R_NONE;
-    const u32 anybad = __syncthreads_or(nbad != 0);
+    const u32 anybad = block_count(nbad != 0);
     if (threadIdx.x == 0) {
         u32 r = R_NONE;
         for (int i = 0; i < PARSE_WARPS; ++i) if (sm2[i] != R_NONE) { r = sm2[i]; break; }
@@ -304,6 +306,7 @@ __global__ void __launch_bounds__(256) symbol_stats_kernel(const u8* __restrict_
         acgt += (b == 'A' || b == 'C' || b == 'G' || b == 'T');
         bad += (b >= 128u);
     }
+    __syncwarp();
     for (int d = 16; d; d >>= 1) {
         acgt += __shfl_xor_sync(0xffffffffu, acgt, d);
         upper += __shfl_xor_sync(0xffffffffu, upper, d);

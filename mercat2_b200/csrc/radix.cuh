@@ -100,6 +100,7 @@ rs_scatter_kernel(const u64* __restrict__ kin, u64* __restrict__ kout, const V* 
     const u32 seg = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
     u64 key[RS_ITEMS];
     u32 rank[RS_ITEMS];
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const u32 i = seg + r * 32 + lane;
@@ -169,7 +170,7 @@ template <class Acc>
 __global__ void __launch_bounds__(RLE_THREADS) rle_count_kernel(Acc acc, u64 m, u64 c, u32* __restrict__ tile_cnt) {
     const u64 i = (u64)blockIdx.x * RLE_THREADS + threadIdx.x;
     const bool s = i < m && rle_survivor_head(acc, i, m, c);
-    const u32 total = __syncthreads_count(s);
+    const u32 total = block_count(s);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
@@ -204,7 +205,7 @@ template <class Acc>
 __global__ void __launch_bounds__(RLE_THREADS) seg_count_kernel(Acc acc, u64 m, u32* __restrict__ tile_cnt) {
     const u64 i = (u64)blockIdx.x * RLE_THREADS + threadIdx.x;
     const bool h = i < m && (i == 0 || !acc.eq(i - 1, i));
-    const u32 total = __syncthreads_count(h);
+    const u32 total = block_count(h);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 template <class Acc>
@@ -229,7 +230,7 @@ seg_sum_count_kernel(const u64* __restrict__ seg_start, u64 nseg, u64 m, const u
         seg_sum[s] = sum;
         keep = sum >= c;
     }
-    const u32 total = __syncthreads_count(keep);
+    const u32 total = block_count(keep);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 __global__ void __launch_bounds__(RLE_THREADS)
