@@ -1,0 +1,269 @@
+// K3 (hash variant) -- large-k counting by hash partitioning + shared-memory hash tables.
+//
+// Replaces  kmerlist[k] += 1  over ~10^8 mostly distinct 64-bit keys per chunk
+// (lib/mercat2_kmers.py:56-60) followed by the per-file  count >= min_count  filter (:73-78).
+//
+// Sized from measurements on B200 (tools/microbench.cu, profiles/r01_microbench.txt): random
+// shared-memory atomics run at ~1.5 T/s chip-wide and coalesced traffic at ~6.2 TB/s, while random
+// 8-byte global stores reach only ~25-50 G/s and an LSD radix sort needs 8 passes.  So keys are
+// hash-partitioned with COALESCED writes in two levels (nb1 <= 512 buckets, then 128 sub-buckets each)
+// until a sub-bucket (~7k keys) fits a 16384-slot open-addressing table in shared memory; one CTA
+// counts one sub-bucket entirely on chip and emits only the keys whose count reaches the threshold.
+//
+//   hc_hist     symbols -> histogram over all nb1*nb2 sub-buckets          (reads sym once)
+//   hc_scan     exact sub-bucket / bucket offsets, cursors, tile map       (one CTA)
+//   hc_scatter1 symbols -> keys grouped by level-1 bucket                  (reads sym, writes 8 B/key)
+//   hc_scatter2 level-1 groups -> keys grouped by sub-bucket               (reads 8, writes 8 B/key)
+//   hc_count    per sub-bucket: smem hash insert, threshold, emit          (reads 8 B/key)
+//
+// Offsets are exact (two passes over the symbols), so skewed inputs cannot overflow a bucket's memory;
+// a sub-bucket with more distinct keys than the table holds is reported in an overflow list and redone
+// by the sort path.  Output rows are unordered (sorted once per sample at the end).
+#pragma once
+#include "common.cuh"
+#include "extract.cuh"
+
+#define HC_SLOTS 16384u
+#define HC_THREADS 1024
+#define HC_LIMIT 12288u                 // distinct keys per table before a bucket is declared overflowed
+#define HC_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define HC_NB2_LOG2 7
+#define HC_NB2 (1u << HC_NB2_LOG2)
+#define HC_MAX_NB1 512u
+#define HC_TILE 4096u
+
+__device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb) {
+    const u32 h = (u32)((key * 0x9E3779B97F4A7C15ull) >> 32);
+    return __umulhi(h, nb);                               // uniform in [0, nb)
+}
+__device__ __forceinline__ u32 hc_slot(u64 key) {
+    return (u32)((key * 0xD6E8FEB86659FD93ull) >> 43) & (HC_SLOTS - 1);
+}
+
+// ---- hc_hist -------------------------------------------------------------------------------------------
+template <int ENC>
+__global__ void __launch_bounds__(EX_THREADS)
+hc_hist_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32* __restrict__ ghist) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* hist = reinterpret_cast<u32*>(dyn);
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
+    for (u32 i = threadIdx.x; i < nb; i += EX_THREADS) hist[i] = 0;
+    __syncthreads();
+    const int kb = k * EncTraits<ENC>::BITS;
+    const u64 mask = kb >= 64 ? ~0ull : ((1ull << kb) - 1);
+    const u64 ntiles = (s1 - s0 + EX_TILE - 1) / EX_TILE;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 tile_start = s0 + tile * EX_TILE;
+        TileCtx<ENC> ctx;
+        tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
+        const u64 first = tile_start + 16ull * threadIdx.x;
+        tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
+            if (fast && first + i < s1) atomicAdd(&hist[hc_bucket(code & mask, nb)], 1u);
+        });
+        __syncthreads();
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < nb; b += EX_THREADS) {
+        const u32 n = hist[b];
+        if (n) atomicAdd(&ghist[b], n);
+    }
+}
+
+// ---- hc_scan (one CTA) ------------------------------------------------------------------------------------
+// sub_base[b] (b <= nb): start of sub-bucket b in the level-2 array (== level-1 array position of its
+// bucket when b % nb2 == 0); cur1[b1] / cur2[b]: running cursors for the two scatters;
+// tile_pref[b1] (b1 <= nb1): first level-2-scatter tile of bucket b1.
+__global__ void __launch_bounds__(1024)
+hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __restrict__ sub_base, u32* __restrict__ cur1,
+               u32* __restrict__ cur2, u32* __restrict__ tile_pref, ull* __restrict__ total_out) {
+    __shared__ u64 sm[1024 / 32 + 1];
+    __shared__ u32 s_l1[HC_MAX_NB1 + 1];
+    const u32 per = (nb + 1023) / 1024;
+    const u32 t0 = min(nb, threadIdx.x * per), t1 = min(nb, t0 + per);
+    u64 acc = 0;
+    for (u32 t = t0; t < t1; ++t) acc += ghist[t];
+    u64 total;
+    u64 base = block_exclusive_sum64<32>(acc, sm, &total);
+    for (u32 t = t0; t < t1; ++t) {
+        sub_base[t] = (u32)base;
+        cur2[t] = (u32)base;
+        if (t % nb2 == 0) { cur1[t / nb2] = (u32)base; s_l1[t / nb2] = (u32)base; }
+        base += ghist[t];
+    }
+    if (threadIdx.x == 0) { sub_base[nb] = (u32)total; s_l1[nb1] = (u32)total; *total_out = total; }
+    __syncthreads();
+    // tiles per level-1 bucket -> exclusive prefix
+    u64 tl = 0;
+    if (threadIdx.x < nb1) tl = (s_l1[threadIdx.x + 1] - s_l1[threadIdx.x] + HC_TILE - 1) / HC_TILE;
+    u64 ttotal;
+    const u64 tp = block_exclusive_sum64<32>(tl, sm, &ttotal);
+    if (threadIdx.x < nb1) tile_pref[threadIdx.x] = (u32)tp;
+    if (threadIdx.x == 0) tile_pref[nb1] = (u32)ttotal;
+}
+
+// ---- shared helper: group up to 16 keys per thread by a small digit and write coalesced runs -----------------
+// cnt / loff / gbase: ND words each.  Every thread calls; `valid` bit i says mine[i] holds a key with digit
+// dig(i).  cursors[d] is advanced atomically by the tile's count for digit d.
+template <int ND_MAX, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u32* cnt,
+                                                   u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
+                                                   u64* __restrict__ out) {
+    // ranks within (tile, digit): shared-memory atomics with return
+    u32 rk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rk[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if ((valid >> i) & 1u) {
+            const u32 r = atomicAdd(&cnt[dig(mine[i])], 1u);
+            rk[i >> 1] |= r << (16 * (i & 1));
+        }
+    __syncthreads();
+    // exclusive scan of cnt[0..nd): thread t owns entries [t*per, t*per+per)
+    const u32 per = (nd + EX_THREADS - 1) / EX_THREADS;
+    u32 acc = 0;
+    for (u32 j = 0; j < per; ++j) { const u32 d = threadIdx.x * per + j; if (d < nd) acc += cnt[d]; }
+    u32 total;
+    u32 run = block_exclusive_scan<OpAdd, EX_WARPS>(acc, sm, &total);
+    for (u32 j = 0; j < per; ++j) {
+        const u32 d = threadIdx.x * per + j;
+        if (d < nd) {
+            const u32 c = cnt[d];
+            loff[d] = run;
+            gbase[d] = c ? atomicAdd(&cursors[d], c) : 0u;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if ((valid >> i) & 1u) stage[loff[dig(mine[i])] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu)] = mine[i];
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < total; i += EX_THREADS) {
+        const u64 key = stage[i];
+        const u32 d = dig(key);
+        out[gbase[d] + (i - loff[d])] = key;
+    }
+}
+
+// ---- hc_scatter1: symbols -> level-1 groups ----------------------------------------------------------------
+template <int ENC>
+__global__ void __launch_bounds__(EX_THREADS)
+hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
+    __shared__ u64 s_code[EX_THREADS + EX_HALO];
+    __shared__ u32 s_meta[EX_THREADS + EX_HALO];
+    __shared__ u64 stage[EX_TILE];
+    __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
+    __shared__ u32 sm[EX_WARPS + 1];
+    for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
+    const int kb = k * EncTraits<ENC>::BITS;
+    const u64 mask = kb >= 64 ? ~0ull : ((1ull << kb) - 1);
+    const u64 tile_start = s0 + (u64)blockIdx.x * EX_TILE;
+    TileCtx<ENC> ctx;
+    tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);        // contains the barrier that publishes cnt = 0
+    const u64 first = tile_start + 16ull * threadIdx.x;
+    u64 mine[16];
+    u32 valid = 0;
+    tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
+        mine[i] = code & mask;
+        if (fast && first + i < s1) valid |= 1u << i;
+    });
+    auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };      // nb == nb1 * HC_NB2
+    hc_group_and_write<HC_MAX_NB1>(mine, valid, nb1, dig, stage, cnt, loff, gbase, sm, cur1, keys1);
+}
+
+// ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
+__global__ void __launch_bounds__(EX_THREADS)
+hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
+                   u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
+    __shared__ u64 stage[HC_TILE];
+    __shared__ u32 cnt[HC_NB2], loff[HC_NB2], gbase[HC_NB2];
+    __shared__ u32 sm[EX_WARPS + 1];
+    __shared__ u32 s_b1;
+    if (blockIdx.x >= tile_pref[nb1]) return;
+    if (threadIdx.x == 0) {                      // last b1 with tile_pref[b1] <= blockIdx.x
+        u32 lo = 0, hi = nb1;
+        while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (tile_pref[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+        s_b1 = lo;
+    }
+    for (u32 i = threadIdx.x; i < nb2; i += EX_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const u32 b1 = s_b1;
+    const u32 lo = sub_base[b1 * nb2], hi = sub_base[min(nb, (b1 + 1) * nb2)];
+    const u32 t_in = blockIdx.x - tile_pref[b1];
+    const u32 base = lo + t_in * HC_TILE;
+    u64 mine[16];
+    u32 valid = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u32 i = base + j * EX_THREADS + threadIdx.x;
+        mine[j] = 0;
+        if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
+    }
+    auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
+    hc_group_and_write<HC_NB2>(mine, valid, nb2, dig, stage, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+}
+
+// ---- hc_count: one CTA per sub-bucket -------------------------------------------------------------------------
+__global__ void __launch_bounds__(HC_THREADS)
+hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
+                u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
+    extern __shared__ __align__(16) u8 dyn[];
+    ull* tkeys = reinterpret_cast<ull*>(dyn);                       // HC_SLOTS
+    u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC_SLOTS * 8);   // HC_SLOTS
+    __shared__ u32 sm[HC_THREADS / 32 + 1];
+    __shared__ u32 s_empty, s_distinct, s_overflow;
+    __shared__ ull s_out;
+    for (u32 b = blockIdx.x; b < nb; b += gridDim.x) {
+        const u32 lo = sub_base[b], n = sub_base[b + 1] - lo;
+        if (n == 0) continue;                                      // uniform for the CTA
+        for (u32 i = threadIdx.x; i < HC_SLOTS; i += HC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
+        if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += HC_THREADS) {
+            const ull key = keys2[lo + i];
+            if (key == HC_EMPTY) { atomicAdd(&s_empty, 1u); continue; }   // the all-ones key (T^32) is counted aside
+            if (*(volatile u32*)&s_overflow) break;
+            u32 p = hc_slot(key);
+            while (true) {
+                ull cur = tkeys[p];
+                if (cur == HC_EMPTY) {
+                    cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+                    if (cur == HC_EMPTY) {
+                        if (atomicAdd(&s_distinct, 1u) >= HC_LIMIT) s_overflow = 1;
+                        cur = key;
+                    }
+                }
+                if (cur == key) { atomicAdd(&tcnt[p], 1u); break; }
+                p = (p + 1) & (HC_SLOTS - 1);
+            }
+        }
+        __syncthreads();
+        if (s_overflow) {
+            if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
+        } else {
+            // emit slots with count >= c (16 slots per thread), plus the all-ones key
+            u32 mine = 0;
+#pragma unroll
+            for (int j = 0; j < (int)(HC_SLOTS / HC_THREADS); ++j) mine += tcnt[j * HC_THREADS + threadIdx.x] >= c;
+            const bool extra = threadIdx.x == 0 && s_empty >= c && s_empty > 0;
+            mine += extra;
+            u32 total;
+            u32 off = block_exclusive_scan<OpAdd, HC_THREADS / 32>(mine, sm, &total);
+            if (threadIdx.x == 0) s_out = total ? atomicAdd(out_n, (ull)total) : 0ull;
+            __syncthreads();
+            const u64 ob = s_out;
+            if (ob + total <= out_cap) {
+                if (extra) { out_keys[ob + off] = HC_EMPTY; out_cnt[ob + off] = s_empty; ++off; }
+#pragma unroll
+                for (int j = 0; j < (int)(HC_SLOTS / HC_THREADS); ++j) {
+                    const u32 s = j * HC_THREADS + threadIdx.x;
+                    const u32 n2 = tcnt[s];
+                    if (n2 >= c) { out_keys[ob + off] = tkeys[s]; out_cnt[ob + off] = n2; ++off; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}

@@ -15,6 +15,7 @@
 #include "radix.cuh"
 #include "wide.cuh"
 #include "chunker.cuh"
+#include "hashcount.cuh"
 #include "metrics.cuh"
 
 static thread_local std::string g_err;
@@ -33,6 +34,8 @@ struct mc2_engine {
     u64 opt_batch_symbols = 1ull << 28;
     int opt_force_path = 0;
     int opt_force_enc = -1;
+    int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
+    u64 opt_hash_bucket_keys = 7000;       // target keys per shared-memory table
     // stats
     u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0;
     double device_us = 0;
@@ -186,9 +189,10 @@ static u64 offsets_from_counts(mc2_engine* e, const u32* tile_cnt, u64* tile_off
 // =====================================================================================================
 // tables and sample accumulators
 // =====================================================================================================
-struct FastPart {          // sorted, unique (key, count) rows in the sample's fast encoding
+struct FastPart {          // unique (key, count) rows in the sample's fast encoding
     DBuf<u64> keys, counts;
     u64 n = 0;
+    bool sorted = true;    // rows ordered by key (the hash path emits unordered rows)
 };
 struct WidePart {          // sorted, unique k-byte rows
     DBuf<u8> rows;
@@ -356,7 +360,12 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
     for (auto& p : parts) M += p.n;
     out.n = 0;
     if (M == 0) return;
-    if (parts.size() == 1 && c <= 1) { out = std::move(parts[0]); return; }
+    if (c <= 1) {
+        FastPart* only = nullptr;
+        int nonempty = 0;
+        for (auto& p : parts) if (p.n) { only = &p; nonempty++; }
+        if (nonempty == 1 && only->sorted) { out = std::move(*only); return; }
+    }
     DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
     u64 at = 0;
     for (auto& p : parts) {
@@ -372,6 +381,7 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
     KeyEq acc{ks};
     const u64 ns = seg_reduce(e, acc, M, vs, c, start, count);
     out.n = ns;
+    out.sorted = true;
     out.keys.alloc(e, ns);
     out.counts = std::move(count);
     if (ns) LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, out.keys.p);
@@ -457,8 +467,99 @@ static void dense_batch(mc2_engine* e, const Plan& plan, SymView v, u64 s0, u64 
     }
 }
 
+// sort + RLE of an already materialised key range (fallback for overflowed hash buckets)
+static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys, u64 m, int kb) {
+    if (!m) return;
+    DBuf<u64> k0(e, m), k1(e, m);
+    CUDA_CHECK(cudaMemcpyAsync(k0.p, keys, m * 8, cudaMemcpyDeviceToDevice, e->stream));
+    const int r = radix_sort<NoVal, false>(e, k0.p, k1.p, (NoVal*)nullptr, (NoVal*)nullptr, m, 0, std::min(64, (kb + 7) & ~7));
+    const u64* ks = r ? k1.p : k0.p;
+    KeyEq acc{ks};
+    DBuf<u64> start, count;
+    const u64 ns = rle_threshold(e, acc, m, s->c, start, count);
+    if (!ns) return;
+    FastPart part;
+    part.n = ns;
+    part.keys.alloc(e, ns);
+    part.counts = std::move(count);
+    LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, part.keys.p);
+    s->fast.push_back(std::move(part));
+}
+
+// hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch
+template <int ENC>
+static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v) {
+    const int k = s->k;
+    const int kb = k * EncTraits<ENC>::BITS;
+    const u64 cap = v.n;                                       // upper bound on the number of windows
+    const u32 nb1 = (u32)std::min<u64>(400, std::max<u64>(1, div_up(cap, e->opt_hash_bucket_keys * HC_NB2)));
+    const u32 nb = nb1 * HC_NB2;
+    const u64 ntiles = div_up(cap, EX_TILE);
+    DBuf<u32> ghist(e, nb), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
+    struct Tail { ull total, out_n; u32 ovf_n, pad; };
+    DBuf<Tail> tail(e, 1);
+    ghist.zero();
+    tail.zero();
+    {
+        auto kern = hc_hist_kernel<ENC>;
+        const size_t smem = (size_t)nb * 4;
+        static thread_local bool attr_set[3] = {false, false, false};
+        if (!attr_set[ENC]) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            attr_set[ENC] = true;
+        }
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, smem));
+        const u64 grid = std::min<u64>(ntiles, (u64)e->num_sms * std::max(per_sm, 1));
+        LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, smem, v, (u64)0, v.n, k, nb, ghist.p);
+    }
+    LAUNCH(e, hc_scan_kernel, 1, 1024, 0, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
+    DBuf<u64> keys1(e, cap), keys2(e, cap);
+    {
+        auto kern = hc_scatter1_kernel<ENC>;
+        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)ntiles, EX_THREADS, 0, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
+    }
+    LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, 0, (const u64*)keys1.p, (const u32*)sub_base.p,
+           (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+    const u64 out_cap = cap / s->c + 2;
+    FastPart part;
+    part.keys.alloc(e, out_cap);
+    part.counts.alloc(e, out_cap);
+    {
+        static thread_local bool attr_set = false;
+        const size_t smem = (size_t)HC_SLOTS * 12;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(hc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        LAUNCH(e, hc_count_kernel, (unsigned)std::min<u64>(nb, (u64)e->num_sms), HC_THREADS, smem, (const u64*)keys2.p,
+               (const u32*)sub_base.p, nb, s->c, part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
+    }
+    const Tail t = read_scalar<Tail>(e, tail.p);
+    if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
+    if (t.out_n) {
+        part.n = t.out_n;
+        part.sorted = false;
+        s->fast.push_back(std::move(part));
+    }
+    if (t.ovf_n) {                                             // tables that filled up: redo those ranges by sorting
+        std::vector<u32> ovf(t.ovf_n), base(nb + 1);
+        d2h(e, ovf.data(), ovf_list.p, t.ovf_n);
+        d2h(e, base.data(), sub_base.p, nb + 1);
+        for (u32 b : ovf) count_key_range_sorted(e, s, keys2.p + base[b], base[b + 1] - base[b], kb);
+    }
+}
+
 template <int ENC>
 static void sparse_chunk(mc2_engine* e, mc2_sample* s, SymView v) {
+    {
+        const u64 hash_max = 400ull * HC_NB2 * e->opt_hash_bucket_keys;
+        const bool want_hash = e->opt_sparse_algo == 2 || (e->opt_sparse_algo == 0 && s->c >= 2);
+        if (want_hash && v.n <= std::min<u64>(hash_max, e->opt_batch_symbols) && v.n < (1ull << 32)) {
+            sparse_chunk_hash<ENC>(e, s, v);
+            return;
+        }
+    }
     const int k = s->k;
     const int kb = k * EncTraits<ENC>::BITS;
     const u64 batch = std::max<u64>(EX_TILE, e->opt_batch_symbols / EX_TILE * EX_TILE);
@@ -837,6 +938,8 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "batch_symbols") e->opt_batch_symbols = (u64)std::max<int64_t>(value, EX_TILE);
     else if (n == "force_path") e->opt_force_path = (int)value;
     else if (n == "force_encoding") e->opt_force_enc = (int)value;
+    else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
+    else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);
     API_END

@@ -34,6 +34,8 @@ def reset(engine):
     engine.set_option("batch_symbols", 1 << 28)
     engine.set_option("dense_max_bins", 1 << 24)
     engine.set_option("smem_max_bins", 32768)
+    engine.set_option("sparse_algo", 0)
+    engine.set_option("hash_bucket_keys", 7000)
 
 
 def diff_msg(got, want):
@@ -64,6 +66,20 @@ def test_edge_cases_forced_paths(engine, edge_cases, path):
         for case in edge_cases:
             check(engine, case["text"], case["k"], case["min_count"], case["expected"],
                   f"path={path} {case['name']} k={case['k']} c={case['min_count']}")
+    finally:
+        reset(engine)
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_edge_cases_sparse_algorithms(engine, edge_cases, algo):
+    """force the sparse path with the radix-sort (1) and the hash-table (2) counting kernels"""
+    reset(engine)
+    engine.set_option("force_path", 2)
+    engine.set_option("sparse_algo", algo)
+    try:
+        for case in edge_cases:
+            check(engine, case["text"], case["k"], case["min_count"], case["expected"],
+                  f"algo={algo} {case['name']} k={case['k']} c={case['min_count']}")
     finally:
         reset(engine)
 
@@ -252,6 +268,15 @@ def test_synthetic_reads_vs_oracle(engine, k, c):
             check(engine, text, k, c, want, f"reads batched k={k} c={c}")
         finally:
             reset(engine)
+        for algo, bucket_keys in ((1, 7000), (2, 7000), (2, 64), (2, 1000000)):
+            # 64 keys/bucket: many level-1 buckets; 10^6: every table overflows -> sort fallback
+            engine.set_option("force_path", 2)
+            engine.set_option("sparse_algo", algo)
+            engine.set_option("hash_bucket_keys", bucket_keys)
+            try:
+                check(engine, text, k, c, want, f"reads algo={algo} bucket_keys={bucket_keys} k={k} c={c}")
+            finally:
+                reset(engine)
 
 
 @pytest.mark.parametrize("k", [8, 9, 12, 17, 33])
@@ -332,10 +357,16 @@ def test_large_dense_and_sparse_properties(engine):
             assert (k2 == kmers).all() and (c2 == counts).all()
         finally:
             reset(engine)
-        t3 = engine.count_text(text, k, 3)
-        k3, c3 = t3.arrays()
-        keep = counts >= 3
-        assert (k3 == kmers[keep]).all() and (c3 == counts[keep]).all()
+        for algo in (1, 2):
+            engine.set_option("sparse_algo", algo)
+            engine.set_option("force_path", 2)
+            try:
+                t3 = engine.count_text(text, k, 3)
+                k3, c3 = t3.arrays()
+                keep = counts >= 3
+                assert (k3 == kmers[keep]).all() and (c3 == counts[keep]).all(), (k, algo)
+            finally:
+                reset(engine)
 
 
 # ---- 5. protein metrics -----------------------------------------------------------------------------
