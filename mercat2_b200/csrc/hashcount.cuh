@@ -205,65 +205,121 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
     hc_group_and_write<HC_NB2>(mine, valid, nb2, dig, stage, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
 }
 
-// ---- hc_count: one CTA per sub-bucket -------------------------------------------------------------------------
-__global__ void __launch_bounds__(HC_THREADS)
+// ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
+// The table is initialised once per CTA; every claimed slot is logged in `claimed`, so thresholding and
+// clean-up touch only the distinct keys of the bucket (not all 16384 slots).  The keys of the NEXT bucket
+// are prefetched into registers while the current one is inserted.
+#define HC_PREFETCH 8
+#define HC_CLAIM_CAP (HC_LIMIT + HC_THREADS)
+#define HC_COUNT_SMEM ((size_t)HC_SLOTS * 12 + (size_t)HC_CLAIM_CAP * 2)
+
+__device__ __forceinline__ void hc_insert(ull key, ull* tkeys, u32* tcnt, u16* claimed, u32* s_distinct, u32* s_overflow) {
+    u32 p = hc_slot(key);
+    while (true) {
+        ull cur = tkeys[p];
+        if (cur == HC_EMPTY) {
+            cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+            if (cur == HC_EMPTY) {
+                const u32 d = atomicAdd(s_distinct, 1u);
+                if (d < HC_CLAIM_CAP) claimed[d] = (u16)p;
+                if (d >= HC_LIMIT) *s_overflow = 1;
+                cur = key;
+            }
+        }
+        if (cur == key) { atomicAdd(&tcnt[p], 1u); return; }
+        p = (p + 1) & (HC_SLOTS - 1);
+    }
+}
+
+__global__ void __launch_bounds__(HC_THREADS, 1)
 hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
                 u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
     extern __shared__ __align__(16) u8 dyn[];
-    ull* tkeys = reinterpret_cast<ull*>(dyn);                       // HC_SLOTS
-    u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC_SLOTS * 8);   // HC_SLOTS
-    __shared__ u32 sm[HC_THREADS / 32 + 1];
+    ull* tkeys = reinterpret_cast<ull*>(dyn);                               // HC_SLOTS
+    u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC_SLOTS * 8);           // HC_SLOTS
+    u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC_SLOTS * 12);       // HC_CLAIM_CAP
     __shared__ u32 s_empty, s_distinct, s_overflow;
-    __shared__ ull s_out;
-    for (u32 b = blockIdx.x; b < nb; b += gridDim.x) {
-        const u32 lo = sub_base[b], n = sub_base[b + 1] - lo;
-        if (n == 0) continue;                                      // uniform for the CTA
-        for (u32 i = threadIdx.x; i < HC_SLOTS; i += HC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
-        if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
-        __syncthreads();
-        for (u32 i = threadIdx.x; i < n; i += HC_THREADS) {
-            const ull key = keys2[lo + i];
-            if (key == HC_EMPTY) { atomicAdd(&s_empty, 1u); continue; }   // the all-ones key (T^32) is counted aside
+    for (u32 i = threadIdx.x; i < HC_SLOTS; i += HC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
+    if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
+    const int lane = threadIdx.x & 31;
+    ull knext[HC_PREFETCH];
+    u32 b = blockIdx.x;
+    u32 lo_n = 0, n_n = 0;
+    if (b < nb) {
+        lo_n = sub_base[b];
+        n_n = sub_base[b + 1] - lo_n;
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) {
+            const u32 i = j * HC_THREADS + threadIdx.x;
+            knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+        }
+    }
+    __syncthreads();
+    for (; b < nb; b += gridDim.x) {
+        const u32 lo = lo_n, n = n_n;
+        ull kcur[HC_PREFETCH];
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) kcur[j] = knext[j];
+        const u32 bn = b + gridDim.x;                       // prefetch the next bucket of this CTA
+        if (bn < nb) {
+            lo_n = sub_base[bn];
+            n_n = sub_base[bn + 1] - lo_n;
+#pragma unroll
+            for (int j = 0; j < HC_PREFETCH; ++j) {
+                const u32 i = j * HC_THREADS + threadIdx.x;
+                knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) {
+            const u32 i = j * HC_THREADS + threadIdx.x;
+            if (i < n && !*(volatile u32*)&s_overflow) {
+                if (kcur[j] == HC_EMPTY) atomicAdd(&s_empty, 1u);      // the all-ones key (T^32) is counted aside
+                else hc_insert(kcur[j], tkeys, tcnt, claimed, &s_distinct, &s_overflow);
+            }
+        }
+        for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {   // oversized buckets
             if (*(volatile u32*)&s_overflow) break;
-            u32 p = hc_slot(key);
-            while (true) {
-                ull cur = tkeys[p];
-                if (cur == HC_EMPTY) {
-                    cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
-                    if (cur == HC_EMPTY) {
-                        if (atomicAdd(&s_distinct, 1u) >= HC_LIMIT) s_overflow = 1;
-                        cur = key;
-                    }
+            const ull key = keys2[lo + i];
+            if (key == HC_EMPTY) atomicAdd(&s_empty, 1u);
+            else hc_insert(key, tkeys, tcnt, claimed, &s_distinct, &s_overflow);
+        }
+        __syncthreads();
+        const u32 nd = min(s_distinct, (u32)HC_CLAIM_CAP);
+        const bool ovf = s_overflow != 0;
+        const u32 n_empty = s_empty;
+        if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
+        // threshold + clean-up over the claimed slots (warp-aggregated output reservation)
+        for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC_THREADS) {
+            const u32 i = i0 + threadIdx.x;
+            ull key = 0;
+            u32 cnt = 0;
+            if (i < nd) {
+                const u32 p = claimed[i];
+                key = tkeys[p];
+                cnt = tcnt[p];
+                tkeys[p] = HC_EMPTY;
+                tcnt[p] = 0;
+            } else if (i == nd && n_empty) {
+                key = HC_EMPTY;
+                cnt = n_empty;
+            }
+            const bool keep = !ovf && cnt >= c && cnt > 0;
+            __syncwarp();
+            const u32 m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                ull base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(out_n, (ull)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (keep) {
+                    const u64 o = base + __popc(m & ((1u << lane) - 1u));
+                    if (o < out_cap) { out_keys[o] = key; out_cnt[o] = cnt; }
                 }
-                if (cur == key) { atomicAdd(&tcnt[p], 1u); break; }
-                p = (p + 1) & (HC_SLOTS - 1);
             }
         }
         __syncthreads();
-        if (s_overflow) {
-            if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
-        } else {
-            // emit slots with count >= c (16 slots per thread), plus the all-ones key
-            u32 mine = 0;
-#pragma unroll
-            for (int j = 0; j < (int)(HC_SLOTS / HC_THREADS); ++j) mine += tcnt[j * HC_THREADS + threadIdx.x] >= c;
-            const bool extra = threadIdx.x == 0 && s_empty >= c && s_empty > 0;
-            mine += extra;
-            u32 total;
-            u32 off = block_exclusive_scan<OpAdd, HC_THREADS / 32>(mine, sm, &total);
-            if (threadIdx.x == 0) s_out = total ? atomicAdd(out_n, (ull)total) : 0ull;
-            __syncthreads();
-            const u64 ob = s_out;
-            if (ob + total <= out_cap) {
-                if (extra) { out_keys[ob + off] = HC_EMPTY; out_cnt[ob + off] = s_empty; ++off; }
-#pragma unroll
-                for (int j = 0; j < (int)(HC_SLOTS / HC_THREADS); ++j) {
-                    const u32 s = j * HC_THREADS + threadIdx.x;
-                    const u32 n2 = tcnt[s];
-                    if (n2 >= c) { out_keys[ob + off] = tkeys[s]; out_cnt[ob + off] = n2; ++off; }
-                }
-            }
-        }
+        if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
         __syncthreads();
     }
 }

@@ -527,7 +527,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v) {
     part.counts.alloc(e, out_cap);
     {
         static thread_local bool attr_set = false;
-        const size_t smem = (size_t)HC_SLOTS * 12;
+        const size_t smem = HC_COUNT_SMEM;
         if (!attr_set) {
             CUDA_CHECK(cudaFuncSetAttribute(hc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
