@@ -33,28 +33,52 @@ __device__ __forceinline__ bool ch_candidate(const u8* __restrict__ text, u64 p,
     return true;
 }
 
+__device__ __forceinline__ u32 ch_nz(u32 x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ u32 ch_eq(u32 w, u32 c4) { return ~ch_nz(w ^ c4) & 0x80808080u; }
+__device__ __forceinline__ u32 ch_movemask(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+// Each thread owns 16 bytes (aligned 16-byte loads; `text` itself may be misaligned).  Groups without
+// '>' and '\r' -- nearly all of them -- cost two SWAR tests per word.
 template <bool WRITE>
 __global__ void __launch_bounds__(CH_THREADS)
 chunk_candidates_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ tile_crlf, u32* __restrict__ tile_cand,
                         const u64* __restrict__ crlf_off, const u64* __restrict__ cand_off,
                         u64* __restrict__ cand_ls, u64* __restrict__ cand_t) {
     __shared__ u32 sm[CH_THREADS / 32 + 1];
-    const u64 first = (u64)blockIdx.x * CH_TILE + (u64)threadIdx.x * CH_ITEMS;
-    u32 ncrlf = 0, ncand = 0;
-    u32 candmask = 0, crlfmask = 0;
-    u64 ls_arr[CH_ITEMS];
-#pragma unroll
-    for (int j = 0; j < CH_ITEMS; ++j) {
-        const u64 p = first + j;
-        ls_arr[j] = 0;
-        if (p < n) {
-            const u32 c = text[p];
-            if (c == 13u && p + 1 < n && text[p + 1] == 10u) { ncrlf++; crlfmask |= 1u << j; }
-            if (c == '>') {
-                u64 ls;
-                if (ch_candidate(text, p, ls)) { ncand++; candmask |= 1u << j; ls_arr[j] = ls; }
-            }
+    const u64 mis = (u64)(uintptr_t)text & 15ull;
+    const u8* aligned = text - mis;
+    const u64 v0 = (u64)blockIdx.x * CH_TILE + (u64)threadIdx.x * CH_ITEMS;      // virtual position of byte 0
+    u32 w[4] = {0, 0, 0, 0};
+    if (v0 >= mis && v0 + 16 <= mis + n) {
+        const uint4 q = *reinterpret_cast<const uint4*>(aligned + v0);
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else if (v0 + 16 > mis && v0 < mis + n) {
+        for (int i = 0; i < 16; ++i) {
+            const u64 v = v0 + i;
+            if (v >= mis && v < mis + n) w[i >> 2] |= (u32)aligned[v] << (8 * (i & 3));
         }
+    }
+    u32 gt = 0, cr = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        gt |= ch_movemask(ch_eq(w[q], 0x3E3E3E3Eu)) << (4 * q);
+        cr |= ch_movemask(ch_eq(w[q], 0x0D0D0D0Du)) << (4 * q);
+    }
+    u32 ncrlf = 0, ncand = 0, candmask = 0, crlfmask = 0;
+    u64 ls_arr[CH_ITEMS];
+    u32 m = cr;
+    while (m) {                                               // "\r\n" pairs (the '\n' may be in the next group)
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const u64 p = v0 + j - mis;
+        if (p + 1 < n && text[p + 1] == 10u) { ncrlf++; crlfmask |= 1u << j; }
+    }
+    m = gt;
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        u64 ls;
+        if (ch_candidate(text, v0 + j - mis, ls)) { ncand++; candmask |= 1u << j; ls_arr[j] = ls; }
     }
     if (!WRITE) {
         u32 tc, tk;
@@ -64,8 +88,10 @@ chunk_candidates_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ ti
     } else {
         u64 crlf_before = crlf_off[blockIdx.x] + block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncrlf, sm, nullptr);
         u64 u = cand_off[blockIdx.x] + block_exclusive_scan<OpAdd, CH_THREADS / 32>(ncand, sm, nullptr);
-#pragma unroll
-        for (int j = 0; j < CH_ITEMS; ++j) {
+        u32 both = candmask | crlfmask;
+        while (both) {
+            const int j = __ffs(both) - 1;
+            both &= both - 1;
             if ((candmask >> j) & 1u) {
                 // no "\r\n" pair lies between the line start and the '>' (no terminators there)
                 cand_ls[u] = ls_arr[j];

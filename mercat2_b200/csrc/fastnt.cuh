@@ -1,0 +1,293 @@
+// K1f + packed extraction -- the nucleotide fast lane.
+//
+// Same semantics as parse.cuh (reference parser lib/mercat2_kmers.py:47-63) restricted to "simple" FASTA
+// text: line ends '\n', '\r\n' or '\r', no other whitespace/control byte, no '*', 7-bit ASCII.  Any
+// other byte raises the `complex` flag and the chunk is redone by the general parser, so results never
+// depend on this lane.  What it buys: the byte-granular work is done once, with SWAR on 32-bit words
+// (about 11 ALU ops per text byte instead of ~55), and everything downstream works on 2-bit packed
+// symbols: a k-mer is two funnel shifts instead of a 16-step rolling loop.
+//
+// Output of K1f: `codes` (u32, 16 symbols per word, symbol i at bits 2(i%16)) and `bad` (u32, one bit per
+// symbol: record separator or non-ACGT symbol).  A window of k symbols is countable on the fast lane iff
+// none of its bad bits is set.  Keys are extracted in stream order (first symbol in the LOW bits); the
+// hash tables do not care, and surviving rows are converted to the order-preserving big-endian code by
+// fn_canon_kernel.
+#pragma once
+#include "common.cuh"
+#include "parse.cuh"
+#include "hashcount.cuh"
+
+#define FN_THREADS 256
+#define FN_WARPS (FN_THREADS / 32)
+#define FN_TILE (FN_THREADS * 16)
+#define FN_LOOKBACK_ITERS 2048          // x 32 bytes: how far a tile looks left for its line start
+
+struct FnStats {
+    ull n_sym;      // symbols emitted (kept bytes + one separator per header line)
+    ull packed;     // low 32 bits: kept bytes; high 32 bits: kept bytes outside {A,C,G,T}
+    ull complex;    // != 0: text is not "simple" -> use the general parser
+};
+
+__device__ __forceinline__ u32 fn_nz(u32 x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ u32 fn_eq(u32 w, u32 c4) { return ~fn_nz(w ^ c4) & 0x80808080u; }
+__device__ __forceinline__ u32 fn_lt21(u32 w) { return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & 0x80808080u; }
+__device__ __forceinline__ u32 fn_movemask(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+struct FnMasks {
+    u32 nl, gt, acgt;   // 16-bit masks over the thread's 16 bytes
+    u32 codes;          // 2-bit code of every byte (garbage where the byte is not ACGT)
+    u32 cx;             // != 0: a byte outside the simple subset
+};
+
+__device__ __forceinline__ FnMasks fn_classify(const u32 w[4]) {
+    FnMasks m;
+    m.nl = m.gt = m.acgt = m.codes = m.cx = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const u32 x = w[q];
+        const u32 mnl = fn_eq(x, 0x0A0A0A0Au) | fn_eq(x, 0x0D0D0D0Du);
+        const u32 mgt = fn_eq(x, 0x3E3E3E3Eu);
+        m.cx |= (fn_lt21(x) & ~mnl) | fn_eq(x, 0x2A2A2A2Au) | (x & 0x80808080u);
+        m.nl |= fn_movemask(mnl) << (4 * q);
+        m.gt |= fn_movemask(mgt) << (4 * q);
+        const u32 t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;            // A,C,G,T -> 0,1,2,3 per byte
+        u32 p = t | (t >> 6);
+        p = (p | (p >> 12)) & 0xFFu;
+        m.codes |= p << (8 * q);
+        u32 sel = (t | (t >> 4)) & 0x00330033u;
+        sel = (sel | (sel >> 8)) & 0x3333u;
+        const u32 back = __byte_perm(0x54474341u, 0u, sel);            // "ACGT"[code] for the four bytes
+        m.acgt |= (fn_movemask(fn_nz(back ^ x)) ^ 0xFu) << (4 * q);
+    }
+    return m;
+}
+
+// forward summary of 16 bytes under the simple rules (header <=> first byte of the line is '>')
+__device__ __forceinline__ u32 fn_summary(const FnMasks& m) {
+    if (m.nl == 0) return (m.gt & 1u) ? ST_H : ST_Q;
+    if (m.nl >> 15) return ST_S0 | 4u;
+    const int ls = 32 - __clz(m.nl);                  // first byte after the last terminator
+    return (((m.gt >> ls) & 1u) ? ST_H : ST_Q) | 4u;
+}
+
+struct FnEmit {
+    u32 emit;      // bytes that become symbols (kept bytes + header starts)
+    u32 bad;       // symbols that stop a fast window (header start, or kept byte outside ACGT)
+    u32 hs;        // header starts
+    u32 keep;
+};
+
+__device__ __forceinline__ FnEmit fn_emit_masks(const FnMasks& m, u32 state) {
+    const u32 open = ~m.nl;                                            // upper 16 bits are ones: carries run off the top
+    const u32 ls = ((m.nl << 1) | (state == ST_S0 ? 1u : 0u)) & 0xFFFFu;
+    const u32 hs = m.gt & ls;
+    const u32 seed = hs | ((state == ST_H && !(m.nl & 1u)) ? 1u : 0u);
+    const u32 hdr = (open & ~(open + seed)) & 0xFFFFu;                 // from each seed up to the next terminator
+    FnEmit e;
+    e.keep = ~hdr & ~m.nl & 0xFFFFu;
+    e.hs = hs;
+    e.emit = e.keep | hs;
+    e.bad = hs | (e.keep & ~m.acgt);
+    return e;
+}
+
+// line state at the first byte of a tile: walk left to the previous terminator (warp 0)
+__device__ __forceinline__ u32 fn_tile_state(const u8* text, u64 idx /*text index of the tile's first byte*/, bool& complex) {
+    const int lane = threadIdx.x & 31;
+    if (idx == 0) return ST_S0;
+    u64 line_start = 0;
+    bool found = false;
+    for (int it = 0; it < FN_LOOKBACK_ITERS; ++it) {
+        const u64 back = (u64)it * 32 + lane + 1;
+        const bool in = back <= idx;
+        const u32 c = in ? text[idx - back] : 10u;                    // the start of the text acts as a terminator
+        __syncwarp();
+        const u32 m = __ballot_sync(0xffffffffu, c == 10u || c == 13u);
+        if (m) {
+            const u64 b = (u64)it * 32 + (__ffs(m) - 1) + 1;
+            line_start = b > idx ? 0 : idx - b + 1;
+            found = true;
+            break;
+        }
+    }
+    if (!found) { complex = true; return ST_Q; }
+    if (line_start == idx) return ST_S0;
+    return text[line_start] == '>' ? ST_H : ST_Q;
+}
+
+// compress the bits of `field_src` selected by the runs of `mask` (BITS per position)
+template <int BITS>
+__device__ __forceinline__ u32 fn_compress(u32 src, u32 mask) {
+    if (mask == 0xFFFFu) return src;
+    u32 out = 0, o = 0, m = mask;
+    while (m) {
+        const int a = __ffs(m) - 1;
+        const u32 run = m >> a;
+        const int len = __ffs(~run) - 1;
+        const u32 lm = len * BITS >= 32 ? 0xFFFFFFFFu : ((1u << (len * BITS)) - 1u);
+        out |= ((src >> (a * BITS)) & lm) << (o * BITS);
+        o += len;
+        m &= ~(((1u << len) - 1u) << a);
+    }
+    return out;
+}
+
+// ---- K1f: count pass (WRITE = false) and write pass (WRITE = true) --------------------------------------
+template <bool WRITE>
+__global__ void __launch_bounds__(FN_THREADS)
+fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_state, u32* __restrict__ tile_cnt,
+                const u64* __restrict__ tile_off, u32* __restrict__ codes, u32* __restrict__ bad, FnStats* stats) {
+    __shared__ u32 sm[FN_WARPS + 1];
+    __shared__ u32 s_state;
+    __shared__ u32 s_c[WRITE ? 260 : 1], s_b[WRITE ? 132 : 1];
+    const ParseTileView v = make_view(text, len);
+    const u64 tile_v = (u64)blockIdx.x * FN_TILE;
+    const u64 p0 = tile_v + (u64)threadIdx.x * 16;
+    u32 w[4];
+    load16(v, p0, w);
+    const FnMasks m = fn_classify(w);
+    if (!WRITE) {
+        if (threadIdx.x < 32) {
+            bool cx = false;
+            const u32 st = tile_v <= v.lo ? (u32)ST_S0 : fn_tile_state(text, tile_v - v.lo, cx);
+            if (threadIdx.x == 0) {
+                s_state = st;
+                tile_state[blockIdx.x] = (u8)st;
+                if (cx) atomicAdd(&stats->complex, 1ull);
+            }
+        }
+    } else {
+        if (threadIdx.x == 0) s_state = tile_state[blockIdx.x];
+        for (u32 i = threadIdx.x; i < 260; i += FN_THREADS) s_c[i] = 0;
+        for (u32 i = threadIdx.x; i < 132; i += FN_THREADS) s_b[i] = 0;
+    }
+    const u32 pre = block_exclusive_scan<FwdOp, FN_WARPS>(fn_summary(m), sm, nullptr);   // barriers publish s_state
+    const u32 state = FwdOp::apply(pre, s_state);
+    const FnEmit e = fn_emit_masks(m, state);
+    const u32 cnt = __popc(e.emit);
+    u32 total;
+    const u32 off = block_exclusive_scan<OpAdd, FN_WARPS>(cnt, sm, &total);
+    if (!WRITE) {
+        if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+        // statistics: one 64-bit atomic per tile (kept | non-ACGT << 32); `complex` only when it happens
+        const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
+        u32 t_kept, t_slow;
+        block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
+        block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
+        if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed, (ull)t_kept | ((ull)t_slow << 32));
+        if (m.cx) atomicAdd(&stats->complex, 1ull);
+    } else {
+        if (total == 0) return;
+        const u64 s_tile = tile_off[blockIdx.x];            // global symbol index of the tile's first symbol
+        const u64 base_sym = s_tile & ~31ull;
+        const u32 rel0 = (u32)(s_tile - base_sym);
+        if (cnt) {
+            const u32 rel = rel0 + off;
+            const u32 cf = fn_compress<2>(m.codes, e.emit);
+            const u32 bf = fn_compress<1>(e.bad, e.emit);
+            const u64 cv = (u64)(cnt == 16 ? cf : (cf & ((1u << (2 * cnt)) - 1u))) << (2 * (rel & 15));
+            atomicOr(&s_c[rel >> 4], (u32)cv);
+            if (cv >> 32) atomicOr(&s_c[(rel >> 4) + 1], (u32)(cv >> 32));
+            const u64 bv = (u64)(bf & ((1u << cnt) - 1u)) << (rel & 31);
+            atomicOr(&s_b[rel >> 5], (u32)bv);
+            if (bv >> 32) atomicOr(&s_b[(rel >> 5) + 1], (u32)(bv >> 32));
+        }
+        __syncthreads();
+        const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;
+        u32* gc = codes + (base_sym >> 4);
+        for (u32 i = fw + threadIdx.x; i < nw; i += FN_THREADS) {
+            const u32 val = s_c[i];
+            if (i == fw || i == nw - 1) { if (val) atomicOr(&gc[i], val); }
+            else gc[i] = val;
+        }
+        const u32 nbw = (rel0 + total + 31) >> 5;
+        u32* gb = bad + (base_sym >> 5);
+        for (u32 i = threadIdx.x; i < nbw; i += FN_THREADS) {
+            const u32 val = s_b[i];
+            if (i == 0 || i == nbw - 1) { if (val) atomicOr(&gb[i], val); }
+            else gb[i] = val;
+        }
+    }
+}
+
+// ---- packed extraction ---------------------------------------------------------------------------------------
+struct PackedView {
+    const u32* codes;
+    const u32* bad;
+    u64 n;             // symbols
+};
+
+// 16 windows starting in code word g: keys (stream order) and the mask of countable windows
+__device__ __forceinline__ u32 fn_windows(const PackedView& pv, u64 g, int k, u64 mask, u64 keys[16]) {
+    const u64 nwords = (pv.n + 15) >> 4;
+    if (g >= nwords) return 0;
+    const u32 w0 = pv.codes[g];
+    const u32 w1 = g + 1 < nwords ? pv.codes[g + 1] : 0u;
+    const u32 w2 = g + 2 < nwords ? pv.codes[g + 2] : 0u;
+    const u64 nbw = (pv.n + 31) >> 5;
+    const u64 bi = g >> 1;
+    u64 b = (u64)pv.bad[bi] | ((bi + 1 < nbw ? (u64)pv.bad[bi + 1] : 0xFFFFFFFFull) << 32);
+    b >>= (g & 1) * 16;
+    b |= 0xFFFF000000000000ull;                                  // only 48 bits are real
+    const u64 first = g << 4;
+    if (first + 48 > pv.n) b |= ~0ull << (pv.n - first);          // symbols past the end stop every window
+    // OR of the k bad bits of every window: doubling smear
+    u64 x = b;
+    int cur = 1;
+    while (cur * 2 <= k) { x |= x >> cur; cur *= 2; }
+    if (cur < k) x |= x >> (k - cur);
+    const u32 valid = ~(u32)x & 0xFFFFu;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u32 lo = __funnelshift_r(w0, w1, 2 * j);
+        const u32 hi = __funnelshift_r(w1, w2, 2 * j);
+        keys[j] = (((u64)hi << 32) | lo) & mask;
+    }
+    return valid;
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* hist = reinterpret_cast<u32*>(dyn);
+    for (u32 i = threadIdx.x; i < nb; i += EX_THREADS) hist[i] = 0;
+    __syncthreads();
+    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const u64 nwords = (pv.n + 15) >> 4;
+    for (u64 g = (u64)blockIdx.x * EX_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * EX_THREADS) {
+        u64 keys[16];
+        const u32 valid = fn_windows(pv, g, k, mask, keys);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((valid >> j) & 1u) atomicAdd(&hist[hc_bucket(keys[j], nb)], 1u);
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < nb; b += EX_THREADS) {
+        const u32 n = hist[b];
+        if (n) atomicAdd(&ghist[b], n);
+    }
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
+    __shared__ u64 stage[EX_TILE];
+    __shared__ u16 sdig[EX_TILE];
+    __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
+    __shared__ u32 sm[EX_WARPS + 1];
+    for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    u64 mine[16];
+    const u32 valid = fn_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, mask, mine);
+    auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
+    hc_group_and_write(mine, valid, nb1, dig, stage, sdig, cnt, loff, gbase, sm, cur1, keys1);
+}
+
+// stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)
+__global__ void fn_canon_kernel(u64* __restrict__ keys, u64 n, int k) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 x = __brevll(keys[i]);                                    // reverses bits: pairs reversed AND swapped inside
+    x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+    keys[i] = 2 * k >= 64 ? x : (x >> (64 - 2 * k));
+}

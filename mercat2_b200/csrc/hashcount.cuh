@@ -29,7 +29,7 @@
 #define HC_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define HC_NB2_LOG2 7
 #define HC_NB2 (1u << HC_NB2_LOG2)
-#define HC_MAX_NB1 512u
+#define HC_MAX_NB1 400u
 #define HC_TILE 4096u
 
 __device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb) {
@@ -103,24 +103,24 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 }
 
 // ---- shared helper: group up to 16 keys per thread by a small digit and write coalesced runs -----------------
-// cnt / loff / gbase: ND words each.  Every thread calls; `valid` bit i says mine[i] holds a key with digit
-// dig(i).  cursors[d] is advanced atomically by the tile's count for digit d.
-template <int ND_MAX, class DigitFn>
-__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u32* cnt,
-                                                   u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
+// cnt / loff / gbase: nd words each; stage / sdig: one slot per key of the tile.  Every thread calls; bit i of
+// `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.
+template <class DigitFn>
+__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u16* sdig,
+                                                   u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
                                                    u64* __restrict__ out) {
-    // ranks within (tile, digit): shared-memory atomics with return
-    u32 rk[8];
+    u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rk[j] = 0;
+    for (int j = 0; j < 8; ++j) { rk[j] = 0; dg[j] = 0; }
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if ((valid >> i) & 1u) {
-            const u32 r = atomicAdd(&cnt[dig(mine[i])], 1u);
+            const u32 d = dig(mine[i]);
+            const u32 r = atomicAdd(&cnt[d], 1u);
             rk[i >> 1] |= r << (16 * (i & 1));
+            dg[i >> 1] |= d << (16 * (i & 1));
         }
     __syncthreads();
-    // exclusive scan of cnt[0..nd): thread t owns entries [t*per, t*per+per)
     const u32 per = (nd + EX_THREADS - 1) / EX_THREADS;
     u32 acc = 0;
     for (u32 j = 0; j < per; ++j) { const u32 d = threadIdx.x * per + j; if (d < nd) acc += cnt[d]; }
@@ -138,12 +138,16 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        if ((valid >> i) & 1u) stage[loff[dig(mine[i])] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu)] = mine[i];
+        if ((valid >> i) & 1u) {
+            const u32 d = (dg[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            const u32 pos = loff[d] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+            stage[pos] = mine[i];
+            sdig[pos] = (u16)d;
+        }
     __syncthreads();
     for (u32 i = threadIdx.x; i < total; i += EX_THREADS) {
-        const u64 key = stage[i];
-        const u32 d = dig(key);
-        out[gbase[d] + (i - loff[d])] = key;
+        const u32 d = sdig[i];
+        out[gbase[d] + (i - loff[d])] = stage[i];
     }
 }
 
@@ -154,6 +158,7 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
     __shared__ u64 s_code[EX_THREADS + EX_HALO];
     __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     __shared__ u64 stage[EX_TILE];
+    __shared__ u16 sdig[EX_TILE];
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
@@ -170,7 +175,7 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
         if (fast && first + i < s1) valid |= 1u << i;
     });
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };      // nb == nb1 * HC_NB2
-    hc_group_and_write<HC_MAX_NB1>(mine, valid, nb1, dig, stage, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write(mine, valid, nb1, dig, stage, sdig, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(EX_THREADS)
 hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
                    u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
     __shared__ u64 stage[HC_TILE];
+    __shared__ u16 sdig[HC_TILE];
     __shared__ u32 cnt[HC_NB2], loff[HC_NB2], gbase[HC_NB2];
     __shared__ u32 sm[EX_WARPS + 1];
     __shared__ u32 s_b1;
@@ -202,7 +208,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
-    hc_group_and_write<HC_NB2>(mine, valid, nb2, dig, stage, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    hc_group_and_write(mine, valid, nb2, dig, stage, sdig, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
@@ -317,6 +323,166 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                     if (o < out_cap) { out_keys[o] = key; out_cnt[o] = cnt; }
                 }
             }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
+        __syncthreads();
+    }
+}
+
+// ---- hc_count2: bitmap pre-filter (min_count >= 2) --------------------------------------------------------------------
+// Most keys of a metagenome chunk occur once.  Pass 1 sets one bit per key in a 2^19-bit shared bitmap; only a key
+// that finds its bit already set (a repeat, or a ~1 % false positive) is entered into the exact table.  Pass 2
+// re-walks the keys (still in registers) and counts those present in the table.  Every key occurring >= 2 times is
+// in the table (its 2nd occurrence sees the bit), its count is exact (all occurrences are counted in pass 2), keys
+// occurring once can never reach min_count >= 2.  One uniform step per key per pass instead of a divergent probe
+// loop over a half-full table.
+#define HC2_SLOTS 8192u
+#define HC2_LIMIT 6144u
+#define HC2_CLAIM_CAP (HC2_LIMIT + HC_THREADS)
+#define HC2_BM_WORDS 16384u
+#define HC2_SMEM ((size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12 + (size_t)HC2_CLAIM_CAP * 2)
+
+__device__ __forceinline__ u32 hc2_slot(u64 prod) { return (u32)(prod >> 20) & (HC2_SLOTS - 1); }
+
+__device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u16* claimed, u32* s_distinct, u32* s_overflow) {
+    const u64 prod = key * 0xD6E8FEB86659FD93ull;
+    const u32 bi = (u32)(prod >> 45);                       // 19 bits
+    const u32 bit = 1u << (bi & 31);
+    const u32 old = atomicOr(&bm[bi >> 5], bit);
+    if (old & bit) {                                        // repeat (or false positive): make sure the key has a slot
+        u32 p = hc2_slot(prod);
+        while (true) {
+            ull cur = tkeys[p];
+            if (cur == HC_EMPTY) {
+                cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+                if (cur == HC_EMPTY) {
+                    const u32 d = atomicAdd(s_distinct, 1u);
+                    if (d < HC2_CLAIM_CAP) claimed[d] = (u16)p;
+                    if (d >= HC2_LIMIT) *s_overflow = 1;
+                    return;
+                }
+            }
+            if (cur == key) return;
+            p = (p + 1) & (HC2_SLOTS - 1);
+        }
+    }
+}
+__device__ __forceinline__ void hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
+    u32 p = hc2_slot(key * 0xD6E8FEB86659FD93ull);
+    while (true) {
+        const ull cur = tkeys[p];
+        if (cur == key) { atomicAdd(&tcnt[p], 1u); return; }
+        if (cur == HC_EMPTY) return;
+        p = (p + 1) & (HC2_SLOTS - 1);
+    }
+}
+
+__global__ void __launch_bounds__(HC_THREADS, 1)
+hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
+                 u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* bm = reinterpret_cast<u32*>(dyn);                                              // HC2_BM_WORDS
+    ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4);                 // HC2_SLOTS
+    u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 8);
+    u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12);
+    __shared__ u32 s_empty, s_distinct, s_overflow;
+    for (u32 i = threadIdx.x; i < HC2_SLOTS; i += HC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
+    for (u32 i = threadIdx.x; i < HC2_BM_WORDS; i += HC_THREADS) bm[i] = 0;
+    if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
+    const int lane = threadIdx.x & 31;
+    ull knext[HC_PREFETCH];
+    u32 b = blockIdx.x;
+    u32 lo_n = 0, n_n = 0;
+    if (b < nb) {
+        lo_n = sub_base[b];
+        n_n = sub_base[b + 1] - lo_n;
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) {
+            const u32 i = j * HC_THREADS + threadIdx.x;
+            knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+        }
+    }
+    __syncthreads();
+    for (; b < nb; b += gridDim.x) {
+        const u32 lo = lo_n, n = n_n;
+        ull kcur[HC_PREFETCH];
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) kcur[j] = knext[j];
+        const u32 bn = b + gridDim.x;
+        if (bn < nb) {
+            lo_n = sub_base[bn];
+            n_n = sub_base[bn + 1] - lo_n;
+#pragma unroll
+            for (int j = 0; j < HC_PREFETCH; ++j) {
+                const u32 i = j * HC_THREADS + threadIdx.x;
+                knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+            }
+        }
+        // pass 1: bitmap test-and-set, repeats claim a table slot
+#pragma unroll
+        for (int j = 0; j < HC_PREFETCH; ++j) {
+            const u32 i = j * HC_THREADS + threadIdx.x;
+            if (i < n && !*(volatile u32*)&s_overflow) {
+                if (kcur[j] == HC_EMPTY) atomicAdd(&s_empty, 1u);
+                else hc2_pass1(kcur[j], bm, tkeys, claimed, &s_distinct, &s_overflow);
+            }
+        }
+        for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {
+            if (*(volatile u32*)&s_overflow) break;
+            const ull key = keys2[lo + i];
+            if (key == HC_EMPTY) atomicAdd(&s_empty, 1u);
+            else hc2_pass1(key, bm, tkeys, claimed, &s_distinct, &s_overflow);
+        }
+        __syncthreads();
+        const bool ovf = s_overflow != 0;
+        // pass 2: count the keys that have a slot
+        if (!ovf && s_distinct) {
+#pragma unroll
+            for (int j = 0; j < HC_PREFETCH; ++j) {
+                const u32 i = j * HC_THREADS + threadIdx.x;
+                if (i < n && kcur[j] != HC_EMPTY) hc2_pass2(kcur[j], tkeys, tcnt);
+            }
+            for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {
+                const ull key = keys2[lo + i];
+                if (key != HC_EMPTY) hc2_pass2(key, tkeys, tcnt);
+            }
+        }
+        __syncthreads();
+        const u32 nd = min(s_distinct, (u32)HC2_CLAIM_CAP);
+        const u32 n_empty = s_empty;
+        if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
+        for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC_THREADS) {
+            const u32 i = i0 + threadIdx.x;
+            ull key = 0;
+            u32 cnt = 0;
+            if (i < nd) {
+                const u32 p = claimed[i];
+                key = tkeys[p];
+                cnt = tcnt[p];
+                tkeys[p] = HC_EMPTY;
+                tcnt[p] = 0;
+            } else if (i == nd && n_empty) {
+                key = HC_EMPTY;
+                cnt = n_empty;
+            }
+            const bool keep = !ovf && cnt >= c && cnt > 0;
+            __syncwarp();
+            const u32 m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                ull base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(out_n, (ull)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (keep) {
+                    const u64 o = base + __popc(m & ((1u << lane) - 1u));
+                    if (o < out_cap) { out_keys[o] = key; out_cnt[o] = cnt; }
+                }
+            }
+        }
+        {   // clear the bitmap (16 bytes per store)
+            uint4* bm4 = reinterpret_cast<uint4*>(bm);
+            for (u32 i = threadIdx.x; i < HC2_BM_WORDS / 4; i += HC_THREADS) bm4[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
         if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }

@@ -16,6 +16,7 @@
 #include "wide.cuh"
 #include "chunker.cuh"
 #include "hashcount.cuh"
+#include "fastnt.cuh"
 #include "metrics.cuh"
 
 static thread_local std::string g_err;
@@ -34,6 +35,7 @@ struct mc2_engine {
     u64 opt_batch_symbols = 1ull << 28;
     int opt_force_path = 0;
     int opt_force_enc = -1;
+    int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
     u64 opt_hash_bucket_keys = 7000;       // target keys per shared-memory table
     // stats
@@ -486,38 +488,51 @@ static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys
     s->fast.push_back(std::move(part));
 }
 
-// hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch
+// hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch.  Keys come either from
+// the byte symbol stream `v` (encoding ENC) or, when `pv` is given, from the packed nucleotide stream.
 template <int ENC>
-static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v) {
+static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr) {
     const int k = s->k;
     const int kb = k * EncTraits<ENC>::BITS;
-    const u64 cap = v.n;                                       // upper bound on the number of windows
-    const u32 nb1 = (u32)std::min<u64>(400, std::max<u64>(1, div_up(cap, e->opt_hash_bucket_keys * HC_NB2)));
+    const u64 cap = pv ? pv->n : v.n;                           // upper bound on the number of windows
+    const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, e->opt_hash_bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
-    const u64 ntiles = div_up(cap, EX_TILE);
     DBuf<u32> ghist(e, nb), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
     struct Tail { ull total, out_n; u32 ovf_n, pad; };
     DBuf<Tail> tail(e, 1);
     ghist.zero();
     tail.zero();
-    {
+    const size_t hist_smem = (size_t)nb * 4;
+    if (pv) {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            attr_set = true;
+        }
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, EX_THREADS, hist_smem));
+        const u64 nwords = div_up(cap, 16);
+        const u64 grid = std::min<u64>(div_up(nwords, EX_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
+        LAUNCH(e, fn_hist_kernel, (unsigned)grid, EX_THREADS, hist_smem, *pv, k, nb, ghist.p);
+    } else {
         auto kern = hc_hist_kernel<ENC>;
-        const size_t smem = (size_t)nb * 4;
         static thread_local bool attr_set[3] = {false, false, false};
         if (!attr_set[ENC]) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
             attr_set[ENC] = true;
         }
         int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, smem));
-        const u64 grid = std::min<u64>(ntiles, (u64)e->num_sms * std::max(per_sm, 1));
-        LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, smem, v, (u64)0, v.n, k, nb, ghist.p);
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, hist_smem));
+        const u64 grid = std::min<u64>(div_up(cap, EX_TILE), (u64)e->num_sms * std::max(per_sm, 1));
+        LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, hist_smem, v, (u64)0, v.n, k, nb, ghist.p);
     }
     LAUNCH(e, hc_scan_kernel, 1, 1024, 0, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
     DBuf<u64> keys1(e, cap), keys2(e, cap);
-    {
+    if (pv) {
+        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, 0, *pv, k, nb, nb1, cur1.p, keys1.p);
+    } else {
         auto kern = hc_scatter1_kernel<ENC>;
-        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)ntiles, EX_THREADS, 0, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
+        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, 0, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
     }
     LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, 0, (const u64*)keys1.p, (const u32*)sub_base.p,
            (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
@@ -525,19 +540,28 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v) {
     FastPart part;
     part.keys.alloc(e, out_cap);
     part.counts.alloc(e, out_cap);
-    {
+    const unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
+    if (s->c >= 2) {
         static thread_local bool attr_set = false;
-        const size_t smem = HC_COUNT_SMEM;
         if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_count2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC2_SMEM));
             attr_set = true;
         }
-        LAUNCH(e, hc_count_kernel, (unsigned)std::min<u64>(nb, (u64)e->num_sms), HC_THREADS, smem, (const u64*)keys2.p,
-               (const u32*)sub_base.p, nb, s->c, part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
+        LAUNCH(e, hc_count2_kernel, cgrid, HC_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
+               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
+    } else {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(hc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_COUNT_SMEM));
+            attr_set = true;
+        }
+        LAUNCH(e, hc_count_kernel, cgrid, HC_THREADS, HC_COUNT_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
+               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
     }
     const Tail t = read_scalar<Tail>(e, tail.p);
     if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
     if (t.out_n) {
+        if (pv) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(t.out_n, 256), 256, 0, part.keys.p, (u64)t.out_n, k);
         part.n = t.out_n;
         part.sorted = false;
         s->fast.push_back(std::move(part));
@@ -546,14 +570,18 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v) {
         std::vector<u32> ovf(t.ovf_n), base(nb + 1);
         d2h(e, ovf.data(), ovf_list.p, t.ovf_n);
         d2h(e, base.data(), sub_base.p, nb + 1);
-        for (u32 b : ovf) count_key_range_sorted(e, s, keys2.p + base[b], base[b + 1] - base[b], kb);
+        for (u32 b : ovf) {
+            const u64 m = base[b + 1] - base[b];
+            if (pv && m) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, keys2.p + base[b], m, k);
+            count_key_range_sorted(e, s, keys2.p + base[b], m, kb);
+        }
     }
 }
 
 template <int ENC>
 static void sparse_chunk(mc2_engine* e, mc2_sample* s, SymView v) {
     {
-        const u64 hash_max = 400ull * HC_NB2 * e->opt_hash_bucket_keys;
+        const u64 hash_max = (u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys;
         const bool want_hash = e->opt_sparse_algo == 2 || (e->opt_sparse_algo == 0 && s->c >= 2);
         if (want_hash && v.n <= std::min<u64>(hash_max, e->opt_batch_symbols) && v.n < (1ull << 32)) {
             sparse_chunk_hash<ENC>(e, s, v);
@@ -665,9 +693,73 @@ static void adopt_symbols(mc2_engine* e, const u8* dsym, u64 len, Parsed& out) {
         throw Mc2Error(MC2_ERR_NON_ASCII, "sequence contains non-ASCII characters; only 7-bit ASCII is supported");
 }
 
+// The nucleotide fast lane (fastnt.cuh).  Returns false when the chunk must go through the general parser
+// (text not simple, sample is not nucleotide / not on the hash path); *need_exceptions is set when the chunk
+// holds non-ACGT symbols whose windows still have to be counted by the wide path.
+static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, bool* need_exceptions) {
+    *need_exceptions = false;
+    if (!e->opt_fast_nt || e->opt_sparse_algo == 1 || s->c < 2 || s->k > 32 || len == 0) return false;
+    if (s->plan.path != PATH_UNSET && !(s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE)) return false;
+    if (e->opt_force_enc > 0 || (e->opt_force_path != 0 && e->opt_force_path != PATH_SPARSE)) return false;
+    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
+    if (len >= (1ull << 32) || len > hash_max) return false;
+    const u64 mis = (u64)(uintptr_t)dtext & 15ull;
+    const u64 ntiles = div_up(mis + len, FN_TILE);
+    DBuf<u8> tstate(e, ntiles);
+    DBuf<u32> tcnt(e, ntiles);
+    DBuf<u64> toff(e, ntiles);
+    DBuf<FnStats> st(e, 1);
+    st.zero();
+    LAUNCH(e, fn_parse_kernel<false>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
+           (u32*)nullptr, (u32*)nullptr, st.p);
+    dev_exclusive_scan<u32, u64>(e, tcnt.p, toff.p, ntiles, &st.p->n_sym);
+    const FnStats fs = read_scalar<FnStats>(e, st.p);
+    if (getenv("MC2_DEBUG_FAST"))
+        fprintf(stderr, "[fast_nt] len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)len, fs.n_sym,
+                fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
+    if (fs.complex) return false;
+    const u64 n_kept = fs.packed & 0xFFFFFFFFull, n_acgt = n_kept - (fs.packed >> 32);
+    if (s->plan.path == PATH_UNSET) {
+        if (n_kept == 0) return true;                                     // headers only: nothing to count, plan stays open
+        if (n_acgt * 10 < n_kept * 9) return false;                       // not nucleotide-like: let the general path decide
+        ParseStats ps;
+        memset(&ps, 0, sizeof ps);
+        ps.n_acgt = n_acgt;
+        ps.n_upper = n_acgt;
+        ps.n_ascii = n_kept;
+        make_plan(e, ps, s->k, s->plan);
+        if (s->plan.path == PATH_DENSE) {
+            s->dense_sample.alloc(e, s->plan.bins);
+            s->dense_sample.zero();
+            s->dense_chunk.alloc(e, s->plan.bins);
+            s->dense_chunk.zero();
+        }
+        if (!(s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE)) return false;
+    }
+    if (n_kept == 0) return true;
+    const u64 nsym = fs.n_sym;
+    DBuf<u32> codes(e, div_up(nsym, 16) + 4), bad(e, div_up(nsym, 32) + 4);
+    codes.zero();
+    bad.zero();
+    LAUNCH(e, fn_parse_kernel<true>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)toff.p, codes.p,
+           bad.p, st.p);
+    PackedView pv{codes.p, bad.p, nsym};
+    sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
+    *need_exceptions = n_kept > n_acgt;
+    return true;
+}
+
 static void count_chunk(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, bool raw_symbols = false) {
     s->n_chunks++;
     e->chunks++;
+    bool exceptions_only = false;
+    if (!raw_symbols) {
+        bool need_exc = false;
+        if (count_chunk_fast_nt(e, s, dtext, len, &need_exc)) {
+            if (!need_exc) return;
+            exceptions_only = true;            // fast windows are counted; the general parse below feeds the wide path
+        }
+    }
     Parsed ps;
     if (raw_symbols) adopt_symbols(e, dtext, len, ps);
     else parse_text(e, dtext, len, 0, ps);
@@ -690,7 +782,9 @@ static void count_chunk(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, 
         wide_chunk<ENC_BYTE, 1>(e, s, v, ~0ull);
         return;
     }
-    if (plan.path == PATH_DENSE) {
+    if (exceptions_only) {
+        // fast windows were already counted by the packed lane
+    } else if (plan.path == PATH_DENSE) {
         if (plan.enc == ENC_NT2) dense_chunk<ENC_NT2>(e, s, v); else dense_chunk<ENC_AA5>(e, s, v);
     } else {
         if (plan.enc == ENC_NT2) sparse_chunk<ENC_NT2>(e, s, v);
@@ -735,7 +829,7 @@ static const u8* to_device(mc2_engine* e, const void* text, u64 nbytes, int spac
 static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 chunk_bytes) {
     std::vector<u64> bounds(1, 0);
     if (chunk_bytes == 0 || n == 0) return bounds;
-    const u64 ntiles = div_up(n, CH_TILE);
+    const u64 ntiles = div_up(n + ((u64)(uintptr_t)dtext & 15ull), CH_TILE);
     DBuf<u32> tcr(e, ntiles), tca(e, ntiles);
     DBuf<u64> ocr(e, ntiles), oca(e, ntiles);
     LAUNCH(e, chunk_candidates_kernel<false>, (unsigned)ntiles, CH_THREADS, 0, dtext, n, tcr.p, tca.p, (const u64*)nullptr,
@@ -939,6 +1033,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "force_path") e->opt_force_path = (int)value;
     else if (n == "force_encoding") e->opt_force_enc = (int)value;
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
+    else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);

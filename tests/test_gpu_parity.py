@@ -35,6 +35,7 @@ def reset(engine):
     engine.set_option("dense_max_bins", 1 << 24)
     engine.set_option("smem_max_bins", 32768)
     engine.set_option("sparse_algo", 0)
+    engine.set_option("fast_nt", 1)
     engine.set_option("hash_bucket_keys", 7000)
 
 
@@ -70,12 +71,14 @@ def test_edge_cases_forced_paths(engine, edge_cases, path):
         reset(engine)
 
 
-@pytest.mark.parametrize("algo", [1, 2])
-def test_edge_cases_sparse_algorithms(engine, edge_cases, algo):
-    """force the sparse path with the radix-sort (1) and the hash-table (2) counting kernels"""
+@pytest.mark.parametrize("algo,fast_nt", [(1, 0), (2, 0), (2, 1)])
+def test_edge_cases_sparse_algorithms(engine, edge_cases, algo, fast_nt):
+    """force the sparse path with the radix-sort (1) and the hash-table (2) counting kernels, the latter
+    with and without the SWAR/packed nucleotide lane"""
     reset(engine)
     engine.set_option("force_path", 2)
     engine.set_option("sparse_algo", algo)
+    engine.set_option("fast_nt", fast_nt)
     try:
         for case in edge_cases:
             check(engine, case["text"], case["k"], case["min_count"], case["expected"],
@@ -268,13 +271,15 @@ def test_synthetic_reads_vs_oracle(engine, k, c):
             check(engine, text, k, c, want, f"reads batched k={k} c={c}")
         finally:
             reset(engine)
-        for algo, bucket_keys in ((1, 7000), (2, 7000), (2, 64), (2, 1000000)):
+        for algo, bucket_keys, fast_nt in ((1, 7000, 0), (2, 7000, 0), (2, 64, 0), (2, 1000000, 0),
+                                           (2, 7000, 1), (2, 64, 1), (2, 1000000, 1)):
             # 64 keys/bucket: many level-1 buckets; 10^6: every table overflows -> sort fallback
             engine.set_option("force_path", 2)
             engine.set_option("sparse_algo", algo)
             engine.set_option("hash_bucket_keys", bucket_keys)
+            engine.set_option("fast_nt", fast_nt)
             try:
-                check(engine, text, k, c, want, f"reads algo={algo} bucket_keys={bucket_keys} k={k} c={c}")
+                check(engine, text, k, c, want, f"reads algo={algo} bucket_keys={bucket_keys} fast_nt={fast_nt} k={k} c={c}")
             finally:
                 reset(engine)
 
@@ -315,6 +320,38 @@ def test_synthetic_protein_vs_oracle(engine, k, c):
             check(engine, text, k, c, want, f"protein path={path} k={k} c={c}")
         finally:
             reset(engine)
+
+
+@pytest.mark.parametrize("line_end", [b"\n", b"\r\n", b"\r"])
+def test_fast_lane_wrapped_genome(engine, line_end):
+    """multi-line records (windows span line ends), every line-end flavour, odd line widths, long headers,
+    a record whose lines put '>' / 'N' / lower case inside the sequence, through the packed lane"""
+    reset(engine)
+    rng = np.random.default_rng(77)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = []
+    for i, width in enumerate((60, 61, 70, 80, 17, 16, 15, 1, 33, 4096, 5000)):
+        n = int(rng.integers(3000, 9000))
+        seq = bytearray(lut[rng.integers(0, 4, n)].tobytes())
+        if i % 3 == 1:
+            for pos in rng.integers(0, n, 6):
+                seq[pos] = ord("N")
+        if i % 4 == 2:
+            seq[100:130] = seq[100:130].lower()
+        if i == 5:
+            seq[500] = ord(">")
+        body = line_end.join(bytes(seq[j:j + width]) for j in range(0, n, width))
+        recs.append(b">contig_%d some description with > inside" % i + b"x" * (i * 37) + line_end + body + line_end)
+    text = b"".join(recs)
+    for k, c in ((31, 2), (32, 2), (13, 3), (2, 2), (1, 2)):
+        want = orc.find_kmers_text(text.decode(), k, c)
+        for fast in (1, 0):
+            engine.set_option("force_path", 2)
+            engine.set_option("fast_nt", fast)
+            try:
+                check(engine, text, k, c, want, f"genome le={line_end!r} k={k} c={c} fast={fast}")
+            finally:
+                reset(engine)
 
 
 def test_virtual_chunking_vs_oracle(engine, tmp_path):
