@@ -33,6 +33,13 @@ struct Mc2Error : std::runtime_error {
 
 static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 
+// Block barrier that first reconverges the warp.  Measured on B200 / CUDA 12.9: after a data-dependent loop
+// (hash probing, byte compares) the lanes of a warp can reach BAR.SYNC at different times even though ptxas
+// emitted BSSY/BSYNC.RECONVERGENT before it, and the barrier then releases other warps while the late lanes
+// are still inserting -- counts were lost.  __syncwarp() (WARPSYNC.ALL) before the barrier fixes it; every
+// barrier in this code base goes through this macro.
+#define BLOCK_SYNC() do { __syncwarp(); __syncthreads(); } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // Block-wide exclusive scan of a u32 with an arbitrary associative operator.
 // Op::combine(a, b) = "a followed by b".  All threads of the block must call.  NWARPS = blockDim/32.
@@ -57,9 +64,9 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 x, u32* smem /*NWARPS+1 
     }
     u32 excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = Op::identity();
-    __syncthreads();                       // protect smem reuse between consecutive calls
+    BLOCK_SYNC();                       // protect smem reuse between consecutive calls
     if (lane == 31) smem[warp] = incl;
-    __syncthreads();
+    BLOCK_SYNC();
     if (warp == 0) {
         u32 w = lane < NWARPS ? smem[lane] : Op::identity();
         u32 wi = w;
@@ -73,7 +80,7 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 x, u32* smem /*NWARPS+1 
         if (lane < NWARPS) smem[lane] = we;
         if (lane == NWARPS - 1) smem[NWARPS] = wi;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     u32 base = smem[warp];
     if (total) *total = smem[NWARPS];
     return Op::combine(base, excl);
@@ -96,9 +103,9 @@ __device__ __forceinline__ u64 block_exclusive_sum64(u64 x, u64* smem /*NWARPS+1
         if (lane >= d) incl += y;
     }
     u64 excl = incl - x;
-    __syncthreads();
+    BLOCK_SYNC();
     if (lane == 31) smem[warp] = incl;
-    __syncthreads();
+    BLOCK_SYNC();
     if (warp == 0) {
         u64 w = lane < NWARPS ? smem[lane] : 0ull;
         u64 wi = w;
@@ -110,7 +117,7 @@ __device__ __forceinline__ u64 block_exclusive_sum64(u64 x, u64* smem /*NWARPS+1
         if (lane < NWARPS) smem[lane] = wi - w;
         if (lane == NWARPS - 1) smem[NWARPS] = wi;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     u64 base = smem[warp];
     if (total) *total = smem[NWARPS];
     return base + excl;
@@ -122,9 +129,9 @@ __device__ __forceinline__ u32 block_count(bool pred) {
     __syncwarp();
     const u32 b = __ballot_sync(0xffffffffu, pred);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
+    BLOCK_SYNC();
     if (lane == 0) s_block_count[warp] = __popc(b);
-    __syncthreads();
+    BLOCK_SYNC();
     if (warp == 0) {
         const int nw = (blockDim.x + 31) >> 5;
         u32 v = lane < nw ? s_block_count[lane] : 0u;
@@ -132,7 +139,7 @@ __device__ __forceinline__ u32 block_count(bool pred) {
         for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         if (lane == 0) s_block_count[32] = v;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     return s_block_count[32];
 }
 

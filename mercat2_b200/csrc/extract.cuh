@@ -107,7 +107,7 @@ __device__ __forceinline__ void tile_begin(const SymView& v, u64 tile_start, int
         s_code[t] = hc;
         s_meta[t] = hm;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     const u64 c1 = s_code[t + EX_HALO - 1], c2 = s_code[t + EX_HALO - 2];
     ctx.code = (EncTraits<ENC>::BITS == 2) ? ((c2 << 32) | (c1 & 0xFFFFFFFFull)) : c1;
     // run lengths ending just before this thread: walk left while whole 16-symbol groups qualify
@@ -162,7 +162,7 @@ dense_smem_kernel(SymView v, u64 s0, u64 s1, int k, u32 bins, u32 nrep, u32* __r
     __shared__ u64 s_code[EX_THREADS + EX_HALO];
     __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     for (u32 i = threadIdx.x; i < bins * nrep; i += EX_THREADS) hist[i] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const u64 mask = (2 * k >= 64) ? ~0ull : ((1ull << (2 * k)) - 1);
     u32* my = hist + (u32)((threadIdx.x >> 5) % nrep) * bins;
     const u64 ntiles = (s1 - s0 + EX_TILE - 1) / EX_TILE;
@@ -174,9 +174,9 @@ dense_smem_kernel(SymView v, u64 s0, u64 s1, int k, u32 bins, u32 nrep, u32* __r
         tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
             if (fast && first + i < s1) atomicAdd(&my[dense_index<ENC>(code, k, mask)], 1u);
         });
-        __syncthreads();                                     // s_code/s_meta reuse
+        BLOCK_SYNC();                                     // s_code/s_meta reuse
     }
-    __syncthreads();
+    BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < bins; b += EX_THREADS) {
         u32 sum = 0;
         for (u32 r = 0; r < nrep; ++r) sum += hist[r * bins + b];
@@ -259,7 +259,7 @@ extract_keys_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ keys, ul
 #pragma unroll
     for (int i = 0; i < 16; ++i) if ((valid >> i) & 1u) s_keys[off++] = mine[i];
     if (threadIdx.x == 0) s_base = total ? atomicAdd(nkeys, (ull)total) : 0ull;
-    __syncthreads();
+    BLOCK_SYNC();
     const u64 base = s_base;
     for (u32 i = threadIdx.x; i < total; i += EX_THREADS) keys[base + i] = s_keys[i];
 }
@@ -285,7 +285,7 @@ extract_positions_kernel(SymView v, u64 s0, u64 s1, int k, u64* __restrict__ pos
     u32 total;
     u32 off = block_exclusive_scan<OpAdd, EX_WARPS>((u32)__popc(sel), sm, &total);
     if (threadIdx.x == 0) s_base = total ? atomicAdd(npos, (ull)total) : 0ull;
-    __syncthreads();
+    BLOCK_SYNC();
     const u64 base = s_base;
 #pragma unroll
     for (int i = 0; i < 16; ++i)

@@ -192,7 +192,7 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
             atomicOr(&s_b[rel >> 5], (u32)bv);
             if (bv >> 32) atomicOr(&s_b[(rel >> 5) + 1], (u32)(bv >> 32));
         }
-        __syncthreads();
+        BLOCK_SYNC();
         const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;
         u32* gc = codes + (base_sym >> 4);
         for (u32 i = fw + threadIdx.x; i < nw; i += FN_THREADS) {
@@ -246,41 +246,43 @@ __device__ __forceinline__ u32 fn_windows(const PackedView& pv, u64 g, int k, u6
     return valid;
 }
 
-__global__ void __launch_bounds__(EX_THREADS)
+#define FN_HIST_THREADS 1024
+__global__ void __launch_bounds__(FN_HIST_THREADS)
 fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* hist = reinterpret_cast<u32*>(dyn);
-    for (u32 i = threadIdx.x; i < nb; i += EX_THREADS) hist[i] = 0;
-    __syncthreads();
+    for (u32 i = threadIdx.x; i < nb; i += FN_HIST_THREADS) hist[i] = 0;
+    BLOCK_SYNC();
     const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
     const u64 nwords = (pv.n + 15) >> 4;
-    for (u64 g = (u64)blockIdx.x * EX_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * EX_THREADS) {
+    for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
         u64 keys[16];
         const u32 valid = fn_windows(pv, g, k, mask, keys);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if ((valid >> j) & 1u) atomicAdd(&hist[hc_bucket(keys[j], nb)], 1u);
     }
-    __syncthreads();
-    for (u32 b = threadIdx.x; b < nb; b += EX_THREADS) {
+    BLOCK_SYNC();
+    for (u32 b = threadIdx.x; b < nb; b += FN_HIST_THREADS) {
         const u32 n = hist[b];
         if (n) atomicAdd(&ghist[b], n);
     }
 }
 
-__global__ void __launch_bounds__(EX_THREADS)
+__global__ void __launch_bounds__(EX_THREADS, 4)
 fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
-    __shared__ u64 stage[EX_TILE];
-    __shared__ u16 sdig[EX_TILE];
+    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
+    u64* stage = reinterpret_cast<u64*>(dyn_sc);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)EX_TILE * 8);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
     u64 mine[16];
     const u32 valid = fn_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, mask, mine);
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
-    hc_group_and_write(mine, valid, nb1, dig, stage, sdig, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)

@@ -31,9 +31,13 @@
 #define HC_NB2 (1u << HC_NB2_LOG2)
 #define HC_MAX_NB1 400u
 #define HC_TILE 4096u
+#define HC_SCATTER_SMEM ((size_t)HC_TILE * 12)     // staged keys (8 B) + destination indices (4 B)
 
 __device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb) {
-    const u32 h = (u32)((key * 0x9E3779B97F4A7C15ull) >> 32);
+    // two 32-bit multiplies: every key bit reaches the top bits of h, which is what umulhi consumes
+    u32 h = ((u32)key * 0x9E3779B1u) ^ ((u32)(key >> 32) * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
     return __umulhi(h, nb);                               // uniform in [0, nb)
 }
 __device__ __forceinline__ u32 hc_slot(u64 key) {
@@ -49,7 +53,7 @@ hc_hist_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32* __restrict__ ghist
     __shared__ u64 s_code[EX_THREADS + EX_HALO];
     __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     for (u32 i = threadIdx.x; i < nb; i += EX_THREADS) hist[i] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const int kb = k * EncTraits<ENC>::BITS;
     const u64 mask = kb >= 64 ? ~0ull : ((1ull << kb) - 1);
     const u64 ntiles = (s1 - s0 + EX_TILE - 1) / EX_TILE;
@@ -61,9 +65,9 @@ hc_hist_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32* __restrict__ ghist
         tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
             if (fast && first + i < s1) atomicAdd(&hist[hc_bucket(code & mask, nb)], 1u);
         });
-        __syncthreads();
+        BLOCK_SYNC();
     }
-    __syncthreads();
+    BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < nb; b += EX_THREADS) {
         const u32 n = hist[b];
         if (n) atomicAdd(&ghist[b], n);
@@ -92,7 +96,7 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
         base += ghist[t];
     }
     if (threadIdx.x == 0) { sub_base[nb] = (u32)total; s_l1[nb1] = (u32)total; *total_out = total; }
-    __syncthreads();
+    BLOCK_SYNC();
     // tiles per level-1 bucket -> exclusive prefix
     u64 tl = 0;
     if (threadIdx.x < nb1) tl = (s_l1[threadIdx.x + 1] - s_l1[threadIdx.x] + HC_TILE - 1) / HC_TILE;
@@ -103,10 +107,11 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 }
 
 // ---- shared helper: group up to 16 keys per thread by a small digit and write coalesced runs -----------------
-// cnt / loff / gbase: nd words each; stage / sdig: one slot per key of the tile.  Every thread calls; bit i of
-// `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.
+// cnt / loff / gbase: nd words each; stage / sdst: one slot per key of the tile.  Every thread calls; bit i of
+// `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.  Keys are
+// re-ordered through shared memory so that consecutive threads store consecutive addresses of one digit's run.
 template <class DigitFn>
-__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u16* sdig,
+__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                    u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
                                                    u64* __restrict__ out) {
     u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
@@ -120,7 +125,7 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
             rk[i >> 1] |= r << (16 * (i & 1));
             dg[i >> 1] |= d << (16 * (i & 1));
         }
-    __syncthreads();
+    BLOCK_SYNC();
     const u32 per = (nd + EX_THREADS - 1) / EX_THREADS;
     u32 acc = 0;
     for (u32 j = 0; j < per; ++j) { const u32 d = threadIdx.x * per + j; if (d < nd) acc += cnt[d]; }
@@ -135,20 +140,18 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
             run += c;
         }
     }
-    __syncthreads();
+    BLOCK_SYNC();
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if ((valid >> i) & 1u) {
             const u32 d = (dg[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-            const u32 pos = loff[d] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+            const u32 r = (rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            const u32 pos = loff[d] + r;
             stage[pos] = mine[i];
-            sdig[pos] = (u16)d;
+            sdst[pos] = gbase[d] + r;
         }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < total; i += EX_THREADS) {
-        const u32 d = sdig[i];
-        out[gbase[d] + (i - loff[d])] = stage[i];
-    }
+    BLOCK_SYNC();
+    for (u32 i = threadIdx.x; i < total; i += EX_THREADS) out[sdst[i]] = stage[i];
 }
 
 // ---- hc_scatter1: symbols -> level-1 groups ----------------------------------------------------------------
@@ -157,8 +160,9 @@ __global__ void __launch_bounds__(EX_THREADS)
 hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
     __shared__ u64 s_code[EX_THREADS + EX_HALO];
     __shared__ u32 s_meta[EX_THREADS + EX_HALO];
-    __shared__ u64 stage[EX_TILE];
-    __shared__ u16 sdig[EX_TILE];
+    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
+    u64* stage = reinterpret_cast<u64*>(dyn_sc);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)EX_TILE * 8);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
@@ -175,15 +179,16 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
         if (fast && first + i < s1) valid |= 1u << i;
     });
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };      // nb == nb1 * HC_NB2
-    hc_group_and_write(mine, valid, nb1, dig, stage, sdig, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
-__global__ void __launch_bounds__(EX_THREADS)
+__global__ void __launch_bounds__(EX_THREADS, 4)
 hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
                    u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
-    __shared__ u64 stage[HC_TILE];
-    __shared__ u16 sdig[HC_TILE];
+    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
+    u64* stage = reinterpret_cast<u64*>(dyn_sc);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
     __shared__ u32 cnt[HC_NB2], loff[HC_NB2], gbase[HC_NB2];
     __shared__ u32 sm[EX_WARPS + 1];
     __shared__ u32 s_b1;
@@ -194,7 +199,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         s_b1 = lo;
     }
     for (u32 i = threadIdx.x; i < nb2; i += EX_THREADS) cnt[i] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const u32 b1 = s_b1;
     const u32 lo = sub_base[b1 * nb2], hi = sub_base[min(nb, (b1 + 1) * nb2)];
     const u32 t_in = blockIdx.x - tile_pref[b1];
@@ -208,7 +213,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
-    hc_group_and_write(mine, valid, nb2, dig, stage, sdig, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    hc_group_and_write(mine, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
@@ -260,7 +265,7 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
             knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
         }
     }
-    __syncthreads();
+    BLOCK_SYNC();
     for (; b < nb; b += gridDim.x) {
         const u32 lo = lo_n, n = n_n;
         ull kcur[HC_PREFETCH];
@@ -290,7 +295,7 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
             if (key == HC_EMPTY) atomicAdd(&s_empty, 1u);
             else hc_insert(key, tkeys, tcnt, claimed, &s_distinct, &s_overflow);
         }
-        __syncthreads();
+        BLOCK_SYNC();
         const u32 nd = min(s_distinct, (u32)HC_CLAIM_CAP);
         const bool ovf = s_overflow != 0;
         const u32 n_empty = s_empty;
@@ -324,9 +329,9 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                 }
             }
         }
-        __syncthreads();
+        BLOCK_SYNC();
         if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
-        __syncthreads();
+        BLOCK_SYNC();
     }
 }
 
@@ -337,17 +342,20 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
 // in the table (its 2nd occurrence sees the bit), its count is exact (all occurrences are counted in pass 2), keys
 // occurring once can never reach min_count >= 2.  One uniform step per key per pass instead of a divergent probe
 // loop over a half-full table.
-#define HC2_SLOTS 8192u
-#define HC2_LIMIT 6144u
-#define HC2_CLAIM_CAP (HC2_LIMIT + HC_THREADS)
-#define HC2_BM_WORDS 16384u
+#define HC2_THREADS 512
+#define HC2_SLOTS 4096u
+#define HC2_LIMIT 3072u
+#define HC2_CLAIM_CAP (HC2_LIMIT + HC2_THREADS)
+#define HC2_BM_WORDS 8192u                       // 2^18 bits
+#define HC2_BM_BITS_LOG2 18
+#define HC2_PREFETCH 8
 #define HC2_SMEM ((size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12 + (size_t)HC2_CLAIM_CAP * 2)
 
 __device__ __forceinline__ u32 hc2_slot(u64 prod) { return (u32)(prod >> 20) & (HC2_SLOTS - 1); }
 
 __device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u16* claimed, u32* s_distinct, u32* s_overflow) {
     const u64 prod = key * 0xD6E8FEB86659FD93ull;
-    const u32 bi = (u32)(prod >> 45);                       // 19 bits
+    const u32 bi = (u32)(prod >> (64 - HC2_BM_BITS_LOG2));
     const u32 bit = 1u << (bi & 31);
     const u32 old = atomicOr(&bm[bi >> 5], bit);
     if (old & bit) {                                        // repeat (or false positive): make sure the key has a slot
@@ -378,7 +386,8 @@ __device__ __forceinline__ void hc2_pass2(ull key, const ull* tkeys, u32* tcnt) 
     }
 }
 
-__global__ void __launch_bounds__(HC_THREADS, 1)
+// two CTAs per SM (88 KB of shared memory each) so that one CTA's barriers hide behind the other's work
+__global__ void __launch_bounds__(HC2_THREADS, 2)
 hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
                  u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
     extern __shared__ __align__(16) u8 dyn[];
@@ -386,73 +395,77 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
     ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4);                 // HC2_SLOTS
     u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 8);
     u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12);
-    __shared__ u32 s_empty, s_distinct, s_overflow;
-    for (u32 i = threadIdx.x; i < HC2_SLOTS; i += HC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
-    for (u32 i = threadIdx.x; i < HC2_BM_WORDS; i += HC_THREADS) bm[i] = 0;
-    if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
+    __shared__ u32 s_scal[2][4];                            // per parity: empty-key count, distinct, overflow
+    for (u32 i = threadIdx.x; i < HC2_SLOTS; i += HC2_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
+    for (u32 i = threadIdx.x; i < HC2_BM_WORDS; i += HC2_THREADS) bm[i] = 0;
+    if (threadIdx.x < 8) (&s_scal[0][0])[threadIdx.x] = 0;
     const int lane = threadIdx.x & 31;
-    ull knext[HC_PREFETCH];
+    ull knext[HC2_PREFETCH];
     u32 b = blockIdx.x;
     u32 lo_n = 0, n_n = 0;
     if (b < nb) {
         lo_n = sub_base[b];
         n_n = sub_base[b + 1] - lo_n;
 #pragma unroll
-        for (int j = 0; j < HC_PREFETCH; ++j) {
-            const u32 i = j * HC_THREADS + threadIdx.x;
+        for (int j = 0; j < HC2_PREFETCH; ++j) {
+            const u32 i = j * HC2_THREADS + threadIdx.x;
             knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
         }
     }
-    __syncthreads();
-    for (; b < nb; b += gridDim.x) {
+    BLOCK_SYNC();
+    u32 par = 0;
+    for (; b < nb; b += gridDim.x, par ^= 1u) {
+        u32* s_empty = &s_scal[par][0];
+        u32* s_distinct = &s_scal[par][1];
+        u32* s_overflow = &s_scal[par][2];
         const u32 lo = lo_n, n = n_n;
-        ull kcur[HC_PREFETCH];
+        ull kcur[HC2_PREFETCH];
 #pragma unroll
-        for (int j = 0; j < HC_PREFETCH; ++j) kcur[j] = knext[j];
+        for (int j = 0; j < HC2_PREFETCH; ++j) kcur[j] = knext[j];
         const u32 bn = b + gridDim.x;
         if (bn < nb) {
             lo_n = sub_base[bn];
             n_n = sub_base[bn + 1] - lo_n;
 #pragma unroll
-            for (int j = 0; j < HC_PREFETCH; ++j) {
-                const u32 i = j * HC_THREADS + threadIdx.x;
+            for (int j = 0; j < HC2_PREFETCH; ++j) {
+                const u32 i = j * HC2_THREADS + threadIdx.x;
                 knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
             }
         }
         // pass 1: bitmap test-and-set, repeats claim a table slot
 #pragma unroll
-        for (int j = 0; j < HC_PREFETCH; ++j) {
-            const u32 i = j * HC_THREADS + threadIdx.x;
-            if (i < n && !*(volatile u32*)&s_overflow) {
-                if (kcur[j] == HC_EMPTY) atomicAdd(&s_empty, 1u);
-                else hc2_pass1(kcur[j], bm, tkeys, claimed, &s_distinct, &s_overflow);
+        for (int j = 0; j < HC2_PREFETCH; ++j) {
+            const u32 i = j * HC2_THREADS + threadIdx.x;
+            if (i < n && !*(volatile u32*)s_overflow) {
+                if (kcur[j] == HC_EMPTY) atomicAdd(s_empty, 1u);
+                else hc2_pass1(kcur[j], bm, tkeys, claimed, s_distinct, s_overflow);
             }
         }
-        for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {
-            if (*(volatile u32*)&s_overflow) break;
+        for (u32 i = HC2_PREFETCH * HC2_THREADS + threadIdx.x; i < n; i += HC2_THREADS) {
+            if (*(volatile u32*)s_overflow) break;
             const ull key = keys2[lo + i];
-            if (key == HC_EMPTY) atomicAdd(&s_empty, 1u);
-            else hc2_pass1(key, bm, tkeys, claimed, &s_distinct, &s_overflow);
+            if (key == HC_EMPTY) atomicAdd(s_empty, 1u);
+            else hc2_pass1(key, bm, tkeys, claimed, s_distinct, s_overflow);
         }
-        __syncthreads();
-        const bool ovf = s_overflow != 0;
+        BLOCK_SYNC();
+        const bool ovf = *s_overflow != 0;
+        const u32 nd = min(*s_distinct, (u32)HC2_CLAIM_CAP);
+        const u32 n_empty = *s_empty;
         // pass 2: count the keys that have a slot
-        if (!ovf && s_distinct) {
+        if (!ovf && nd) {
 #pragma unroll
-            for (int j = 0; j < HC_PREFETCH; ++j) {
-                const u32 i = j * HC_THREADS + threadIdx.x;
+            for (int j = 0; j < HC2_PREFETCH; ++j) {
+                const u32 i = j * HC2_THREADS + threadIdx.x;
                 if (i < n && kcur[j] != HC_EMPTY) hc2_pass2(kcur[j], tkeys, tcnt);
             }
-            for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {
+            for (u32 i = HC2_PREFETCH * HC2_THREADS + threadIdx.x; i < n; i += HC2_THREADS) {
                 const ull key = keys2[lo + i];
                 if (key != HC_EMPTY) hc2_pass2(key, tkeys, tcnt);
             }
         }
-        __syncthreads();
-        const u32 nd = min(s_distinct, (u32)HC2_CLAIM_CAP);
-        const u32 n_empty = s_empty;
+        BLOCK_SYNC();
         if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
-        for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC_THREADS) {
+        for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC2_THREADS) {
             const u32 i = i0 + threadIdx.x;
             ull key = 0;
             u32 cnt = 0;
@@ -480,12 +493,21 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
                 }
             }
         }
-        {   // clear the bitmap (16 bytes per store)
+        {   // clear the bitmap (16 bytes per store); reset the other parity's scalars for the next bucket
             uint4* bm4 = reinterpret_cast<uint4*>(bm);
-            for (u32 i = threadIdx.x; i < HC2_BM_WORDS / 4; i += HC_THREADS) bm4[i] = make_uint4(0, 0, 0, 0);
+            for (u32 i = threadIdx.x; i < HC2_BM_WORDS / 4; i += HC2_THREADS) bm4[i] = make_uint4(0, 0, 0, 0);
+            if (threadIdx.x < 4) s_scal[par ^ 1u][threadIdx.x] = 0;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_empty = 0; s_distinct = 0; s_overflow = 0; }
-        __syncthreads();
+        BLOCK_SYNC();
     }
+}
+
+// ---- debug: every key of the level-1 / level-2 arrays must sit in the range of its own bucket -------------------
+__global__ void hc_verify_kernel(const u64* __restrict__ keys, const u32* __restrict__ sub_base, u32 nb, u32 step /*1: sub-buckets, HC_NB2: level-1*/,
+                                 u32 total, ull* __restrict__ bad_count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const u32 b = hc_bucket(keys[i], nb);
+    const u32 lo_b = (b / step) * step, hi_b = min(nb, lo_b + step);
+    if (i < sub_base[lo_b] || i >= sub_base[hi_b]) atomicAdd(bad_count, 1ull);
 }

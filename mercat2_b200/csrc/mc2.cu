@@ -37,7 +37,7 @@ struct mc2_engine {
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
-    u64 opt_hash_bucket_keys = 7000;       // target keys per shared-memory table
+    u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
     // stats
     u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0;
     double device_us = 0;
@@ -510,10 +510,10 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             attr_set = true;
         }
         int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, EX_THREADS, hist_smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
         const u64 nwords = div_up(cap, 16);
-        const u64 grid = std::min<u64>(div_up(nwords, EX_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
-        LAUNCH(e, fn_hist_kernel, (unsigned)grid, EX_THREADS, hist_smem, *pv, k, nb, ghist.p);
+        const u64 grid = std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
+        LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, *pv, k, nb, ghist.p);
     } else {
         auto kern = hc_hist_kernel<ENC>;
         static thread_local bool attr_set[3] = {false, false, false};
@@ -528,26 +528,60 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     }
     LAUNCH(e, hc_scan_kernel, 1, 1024, 0, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
     DBuf<u64> keys1(e, cap), keys2(e, cap);
+    const bool dbg = getenv("MC2_DEBUG_HASH") != nullptr;
+    if (dbg) {
+        CUDA_CHECK(cudaMemsetAsync(keys1.p, 0xEE, cap * 8, e->stream));
+        CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
+    }
+    {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_set = true;
+        }
+    }
     if (pv) {
-        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, 0, *pv, k, nb, nb1, cur1.p, keys1.p);
+        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, HC_SCATTER_SMEM, *pv, k, nb, nb1, cur1.p, keys1.p);
     } else {
         auto kern = hc_scatter1_kernel<ENC>;
-        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, 0, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
+        static thread_local bool attr_set[3] = {false, false, false};
+        if (!attr_set[ENC]) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            attr_set[ENC] = true;
+        }
+        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, HC_SCATTER_SMEM, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
     }
-    LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, 0, (const u64*)keys1.p, (const u32*)sub_base.p,
+    LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, HC_SCATTER_SMEM, (const u64*)keys1.p, (const u32*)sub_base.p,
            (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+    if (dbg) {
+        DBuf<ull> badc(e, 2);
+        badc.zero();
+        const u64 total = (u64)read_scalar<ull>(e, &tail.p->total);
+        if (total) {
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys1.p, (const u32*)sub_base.p, nb, (u32)HC_NB2, (u32)total, badc.p);
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys2.p, (const u32*)sub_base.p, nb, 1u, (u32)total, badc.p + 1);
+        }
+        const ull b1 = read_scalar<ull>(e, badc.p), b2 = read_scalar<ull>(e, badc.p + 1);
+        fprintf(stderr, "[hash] cap=%llu total=%llu nb1=%u nb=%u packed=%d misplaced level1=%llu level2=%llu\n", (ull)cap, (ull)total, nb1, nb,
+                pv ? 1 : 0, b1, b2);
+    }
     const u64 out_cap = cap / s->c + 2;
     FastPart part;
     part.keys.alloc(e, out_cap);
     part.counts.alloc(e, out_cap);
-    const unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
+    unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
     if (s->c >= 2) {
+        cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
         static thread_local bool attr_set = false;
         if (!attr_set) {
             CUDA_CHECK(cudaFuncSetAttribute(hc_count2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC2_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_count2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr_set = true;
         }
-        LAUNCH(e, hc_count2_kernel, cgrid, HC_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
+        LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
                part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
     } else {
         static thread_local bool attr_set = false;

@@ -126,9 +126,9 @@ __device__ __forceinline__ u32 block_follow_class(u32 rev, u32* smem) {
     const u32 nn = __ballot_sync(0xffffffffu, rev != R_NONE);
     const u32 first_lane = nn ? (u32)(__ffs(nn) - 1) : 0u;
     const u32 warp_first = __shfl_sync(0xffffffffu, rev, first_lane);
-    __syncthreads();
+    BLOCK_SYNC();
     if (lane == 0) smem[warp] = nn ? warp_first : R_NONE;
-    __syncthreads();
+    BLOCK_SYNC();
     const u32 above = (lane == 31) ? 0u : (nn & (0xFFFFFFFEu << lane));
     const u32 src = above ? (u32)(__ffs(above) - 1) : 0u;
     u32 res = __shfl_sync(0xffffffffu, rev, src);
@@ -196,7 +196,7 @@ parse_scan_tiles_kernel(u8* tile_fwd, u8* tile_rev, u32 ntiles) {
     u32 first = R_NONE;
     for (u32 t = t0; t < t1; ++t) if (tile_rev[t] != R_NONE) { first = tile_rev[t]; break; }
     part[threadIdx.x] = first;
-    __syncthreads();
+    BLOCK_SYNC();
     u32 follow = R_NL;                       // end of text behaves like a terminator for strip()
     for (u32 j = threadIdx.x + 1; j < SCAN1_THREADS; ++j) if (part[j] != R_NONE) { follow = part[j]; break; }
     for (u32 t = t1; t > t0; --t) {
@@ -278,7 +278,7 @@ parse_emit_kernel(const u8* __restrict__ text, u64 len, const u8* __restrict__ t
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if ((u32)i < cnt) stage[off + i] = (u8)((i < 8 ? out_lo >> (8 * i) : out_hi >> (8 * (i - 8))) & 0xFFu);
-        __syncthreads();
+        BLOCK_SYNC();
         u8* dst = sym + tile_off[blockIdx.x];
         for (u32 i = threadIdx.x; i < total; i += PARSE_THREADS) dst[i] = stage[i];
     }

@@ -72,14 +72,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const T* in, O*
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64* __restrict__ keys, u32 n, int shift, u32* __restrict__ hist, u32 ntiles) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const u32 base = blockIdx.x * RS_TILE;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         const u32 i = base + j * RS_THREADS + threadIdx.x;
         if (i < n) atomicAdd(&h[(u32)(keys[i] >> shift) & 255u], 1u);
     }
-    __syncthreads();
+    BLOCK_SYNC();
     hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
@@ -96,7 +96,7 @@ rs_scatter_kernel(const u64* __restrict__ kin, u64* __restrict__ kout, const V* 
     __shared__ u32 gbase[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     const u32 seg = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
     u64 key[RS_ITEMS];
     u32 rank[RS_ITEMS];
@@ -115,7 +115,7 @@ rs_scatter_kernel(const u64* __restrict__ kin, u64* __restrict__ kout, const V* 
         rank[r] = old + __popc(peers & ((1u << lane) - 1u));
         __syncwarp();
     }
-    __syncthreads();
+    BLOCK_SYNC();
     {   // exclusive scan over warps for digit = threadIdx.x; fold in the tile's global base
         const u32 d = threadIdx.x;
         u32 run = 0;
@@ -123,7 +123,7 @@ rs_scatter_kernel(const u64* __restrict__ kin, u64* __restrict__ kout, const V* 
         for (int w2 = 0; w2 < RS_WARPS; ++w2) { const u32 c = wcnt[w2][d]; wcnt[w2][d] = run; run += c; }
         gbase[d] = offs[d * ntiles + blockIdx.x];
     }
-    __syncthreads();
+    BLOCK_SYNC();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const u32 i = seg + r * 32 + lane;

@@ -36,7 +36,7 @@ def reset(engine):
     engine.set_option("smem_max_bins", 32768)
     engine.set_option("sparse_algo", 0)
     engine.set_option("fast_nt", 1)
-    engine.set_option("hash_bucket_keys", 7000)
+    engine.set_option("hash_bucket_keys", 3500)
 
 
 def diff_msg(got, want):
