@@ -97,6 +97,10 @@ def _as_buffer(data):
         t = data.contiguous()
         if t.element_size() != 1:
             raise TypeError("text tensor must be uint8")
+        if t.is_cuda:
+            # the engine works on its own stream: whatever produced this tensor must have finished
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
         return t.data_ptr(), t.numel(), (MC2_DEVICE if t.is_cuda else MC2_HOST), t
     if isinstance(data, np.ndarray):
         a = np.ascontiguousarray(data).view(np.uint8)
@@ -172,6 +176,10 @@ class Engine:
         _check(self._lib, self._lib.mc2_engine_create(device, C.byref(handle)))
         self._h = handle
         self.device = device
+        # tuning / test overrides: MERCAT2_B200_OPTIONS="name=value,name=value"
+        for item in filter(None, os.environ.get("MERCAT2_B200_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            self.set_option(name.strip(), int(value))
 
     def close(self):
         if getattr(self, "_h", None):

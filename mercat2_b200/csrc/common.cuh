@@ -38,7 +38,8 @@ static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 // emitted BSSY/BSYNC.RECONVERGENT before it, and the barrier then releases other warps while the late lanes
 // are still inserting -- counts were lost.  __syncwarp() (WARPSYNC.ALL) before the barrier fixes it; every
 // barrier in this code base goes through this macro.
-#define BLOCK_SYNC() do { __syncwarp(); __syncthreads(); } while (0)
+// (the warp barrier is inline asm so that the compiler cannot drop it as "redundant after BSYNC")
+#define BLOCK_SYNC() do { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); __syncthreads(); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // Block-wide exclusive scan of a u32 with an arbitrary associative operator.

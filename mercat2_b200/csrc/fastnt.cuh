@@ -269,7 +269,8 @@ fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
     }
 }
 
-__global__ void __launch_bounds__(EX_THREADS, 4)
+template <bool USE_DST>
+__global__ void __launch_bounds__(EX_THREADS)
 fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
@@ -282,7 +283,7 @@ fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1
     u64 mine[16];
     const u32 valid = fn_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, mask, mine);
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
-    hc_group_and_write(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write<USE_DST>(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)
@@ -292,4 +293,26 @@ __global__ void fn_canon_kernel(u64* __restrict__ keys, u64 n, int k) {
     u64 x = __brevll(keys[i]);                                    // reverses bits: pairs reversed AND swapped inside
     x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
     keys[i] = 2 * k >= 64 ? x : (x >> (64 - 2 * k));
+}
+
+// debug: order-independent checksum of all countable windows of the packed stream
+__global__ void fn_checksum_kernel(PackedView pv, int k, ull* __restrict__ out /*[0]=sum, [1]=xor, [2]=count*/) {
+    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const u64 nwords = (pv.n + 15) >> 4;
+    ull sum = 0, x = 0, cnt = 0;
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < nwords; g += (u64)gridDim.x * blockDim.x) {
+        u64 keys[16];
+        const u32 valid = fn_windows(pv, g, k, mask, keys);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((valid >> j) & 1u) { sum += keys[j] * 0x9E3779B97F4A7C15ull; x ^= keys[j]; cnt++; }
+    }
+    atomicAdd(&out[0], sum); atomicXor(&out[1], x); atomicAdd(&out[2], cnt);
+}
+__global__ void key_checksum_kernel(const u64* __restrict__ keys, u64 n, ull* __restrict__ out) {
+    ull sum = 0, x = 0, cnt = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        sum += keys[i] * 0x9E3779B97F4A7C15ull; x ^= keys[i]; cnt++;
+    }
+    atomicAdd(&out[0], sum); atomicXor(&out[1], x); atomicAdd(&out[2], cnt);
 }

@@ -34,12 +34,20 @@
 #define HC_SCATTER_SMEM ((size_t)HC_TILE * 12)     // staged keys (8 B) + destination indices (4 B)
 
 __device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb) {
-    // two 32-bit multiplies: every key bit reaches the top bits of h, which is what umulhi consumes
-    u32 h = ((u32)key * 0x9E3779B1u) ^ ((u32)(key >> 32) * 0x85EBCA77u);
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
+    const u32 h = (u32)((key * 0x9E3779B97F4A7C15ull) >> 32);
     return __umulhi(h, nb);                               // uniform in [0, nb)
 }
+// Shared-memory atomics issued from inside divergent probe loops go through inline PTX: the compiler otherwise
+// rewrites atomicAdd(addr, 1) into a warp-aggregated VOTE + leader ATOMS + SHFL sequence.
+__device__ __forceinline__ u32 smem_atom_inc(u32* addr) {
+    u32 old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((u32)__cvta_generic_to_shared(addr)) : "memory");
+    return old;
+}
+__device__ __forceinline__ void smem_red_inc(u32* addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((u32)__cvta_generic_to_shared(addr)) : "memory");
+}
+
 __device__ __forceinline__ u32 hc_slot(u64 key) {
     return (u32)((key * 0xD6E8FEB86659FD93ull) >> 43) & (HC_SLOTS - 1);
 }
@@ -110,7 +118,7 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 // cnt / loff / gbase: nd words each; stage / sdst: one slot per key of the tile.  Every thread calls; bit i of
 // `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.  Keys are
 // re-ordered through shared memory so that consecutive threads store consecutive addresses of one digit's run.
-template <class DigitFn>
+template <bool USE_DST, class DigitFn>
 __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                    u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
                                                    u64* __restrict__ out) {
@@ -148,10 +156,18 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
             const u32 r = (rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
             const u32 pos = loff[d] + r;
             stage[pos] = mine[i];
-            sdst[pos] = gbase[d] + r;
+            if (USE_DST) sdst[pos] = gbase[d] + r;
+            else reinterpret_cast<u16*>(sdst)[pos] = (u16)d;
         }
     BLOCK_SYNC();
-    for (u32 i = threadIdx.x; i < total; i += EX_THREADS) out[sdst[i]] = stage[i];
+    if (USE_DST) {
+        for (u32 i = threadIdx.x; i < total; i += EX_THREADS) out[sdst[i]] = stage[i];
+    } else {
+        for (u32 i = threadIdx.x; i < total; i += EX_THREADS) {
+            const u32 d = reinterpret_cast<u16*>(sdst)[i];
+            out[gbase[d] + (i - loff[d])] = stage[i];
+        }
+    }
 }
 
 // ---- hc_scatter1: symbols -> level-1 groups ----------------------------------------------------------------
@@ -179,11 +195,12 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
         if (fast && first + i < s1) valid |= 1u << i;
     });
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };      // nb == nb1 * HC_NB2
-    hc_group_and_write(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write<true>(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
-__global__ void __launch_bounds__(EX_THREADS, 4)
+template <bool USE_DST>
+__global__ void __launch_bounds__(EX_THREADS)
 hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
                    u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
@@ -213,7 +230,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
-    hc_group_and_write(mine, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    hc_group_and_write<USE_DST>(mine, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
@@ -231,13 +248,13 @@ __device__ __forceinline__ void hc_insert(ull key, ull* tkeys, u32* tcnt, u16* c
         if (cur == HC_EMPTY) {
             cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
             if (cur == HC_EMPTY) {
-                const u32 d = atomicAdd(s_distinct, 1u);
+                const u32 d = smem_atom_inc(s_distinct);
                 if (d < HC_CLAIM_CAP) claimed[d] = (u16)p;
                 if (d >= HC_LIMIT) *s_overflow = 1;
                 cur = key;
             }
         }
-        if (cur == key) { atomicAdd(&tcnt[p], 1u); return; }
+        if (cur == key) { smem_red_inc(&tcnt[p]); return; }
         p = (p + 1) & (HC_SLOTS - 1);
     }
 }
@@ -267,7 +284,7 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
     }
     BLOCK_SYNC();
     for (; b < nb; b += gridDim.x) {
-        const u32 lo = lo_n, n = n_n;
+        const u32 n = n_n;
         ull kcur[HC_PREFETCH];
 #pragma unroll
         for (int j = 0; j < HC_PREFETCH; ++j) kcur[j] = knext[j];
@@ -281,24 +298,19 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                 knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
             }
         }
+        const bool big = n > HC_PREFETCH * HC_THREADS;              // see hc_count2_kernel
 #pragma unroll
         for (int j = 0; j < HC_PREFETCH; ++j) {
             const u32 i = j * HC_THREADS + threadIdx.x;
-            if (i < n && !*(volatile u32*)&s_overflow) {
+            if (!big && i < n && !*(volatile u32*)&s_overflow) {
                 if (kcur[j] == HC_EMPTY) atomicAdd(&s_empty, 1u);      // the all-ones key (T^32) is counted aside
                 else hc_insert(kcur[j], tkeys, tcnt, claimed, &s_distinct, &s_overflow);
             }
         }
-        for (u32 i = HC_PREFETCH * HC_THREADS + threadIdx.x; i < n; i += HC_THREADS) {   // oversized buckets
-            if (*(volatile u32*)&s_overflow) break;
-            const ull key = keys2[lo + i];
-            if (key == HC_EMPTY) atomicAdd(&s_empty, 1u);
-            else hc_insert(key, tkeys, tcnt, claimed, &s_distinct, &s_overflow);
-        }
         BLOCK_SYNC();
         const u32 nd = min(s_distinct, (u32)HC_CLAIM_CAP);
-        const bool ovf = s_overflow != 0;
-        const u32 n_empty = s_empty;
+        const bool ovf = big || s_overflow != 0;
+        const u32 n_empty = big ? 0u : s_empty;
         if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
         // threshold + clean-up over the claimed slots (warp-aggregated output reservation)
         for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC_THREADS) {
@@ -365,7 +377,7 @@ __device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u16* cla
             if (cur == HC_EMPTY) {
                 cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
                 if (cur == HC_EMPTY) {
-                    const u32 d = atomicAdd(s_distinct, 1u);
+                    const u32 d = smem_atom_inc(s_distinct);
                     if (d < HC2_CLAIM_CAP) claimed[d] = (u16)p;
                     if (d >= HC2_LIMIT) *s_overflow = 1;
                     return;
@@ -376,12 +388,12 @@ __device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u16* cla
         }
     }
 }
-__device__ __forceinline__ void hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
+__device__ __forceinline__ u32 hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
     u32 p = hc2_slot(key * 0xD6E8FEB86659FD93ull);
     while (true) {
         const ull cur = tkeys[p];
-        if (cur == key) { atomicAdd(&tcnt[p], 1u); return; }
-        if (cur == HC_EMPTY) return;
+        if (cur == key) { smem_red_inc(&tcnt[p]); return 1u; }
+        if (cur == HC_EMPTY) return 0u;
         p = (p + 1) & (HC2_SLOTS - 1);
     }
 }
@@ -389,7 +401,8 @@ __device__ __forceinline__ void hc2_pass2(ull key, const ull* tkeys, u32* tcnt) 
 // two CTAs per SM (88 KB of shared memory each) so that one CTA's barriers hide behind the other's work
 __global__ void __launch_bounds__(HC2_THREADS, 2)
 hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
-                 u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
+                 u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n,
+                 ull* __restrict__ dbg) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* bm = reinterpret_cast<u32*>(dyn);                                              // HC2_BM_WORDS
     ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4);                 // HC2_SLOTS
@@ -418,7 +431,7 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
         u32* s_empty = &s_scal[par][0];
         u32* s_distinct = &s_scal[par][1];
         u32* s_overflow = &s_scal[par][2];
-        const u32 lo = lo_n, n = n_n;
+        const u32 n = n_n;
         ull kcur[HC2_PREFETCH];
 #pragma unroll
         for (int j = 0; j < HC2_PREFETCH; ++j) kcur[j] = knext[j];
@@ -432,37 +445,35 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
                 knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
             }
         }
+        // A bucket that does not fit the prefetch registers (> 4096 keys: never at the default sizing, which targets
+        // 3500) is handed to the sort fallback like an overflowed table.  [An earlier version walked the tail of such
+        // buckets from global memory in both passes; on B200 that variant lost a few counts per million keys in a
+        // timing-dependent way that neither warp syncs, block fences nor uniform trip counts removed -- see DESIGN.md.]
+        const bool big = n > HC2_PREFETCH * HC2_THREADS;
         // pass 1: bitmap test-and-set, repeats claim a table slot
 #pragma unroll
         for (int j = 0; j < HC2_PREFETCH; ++j) {
             const u32 i = j * HC2_THREADS + threadIdx.x;
-            if (i < n && !*(volatile u32*)s_overflow) {
+            if (!big && i < n && !*(volatile u32*)s_overflow) {
                 if (kcur[j] == HC_EMPTY) atomicAdd(s_empty, 1u);
                 else hc2_pass1(kcur[j], bm, tkeys, claimed, s_distinct, s_overflow);
             }
         }
-        for (u32 i = HC2_PREFETCH * HC2_THREADS + threadIdx.x; i < n; i += HC2_THREADS) {
-            if (*(volatile u32*)s_overflow) break;
-            const ull key = keys2[lo + i];
-            if (key == HC_EMPTY) atomicAdd(s_empty, 1u);
-            else hc2_pass1(key, bm, tkeys, claimed, s_distinct, s_overflow);
-        }
         BLOCK_SYNC();
-        const bool ovf = *s_overflow != 0;
+        const bool ovf = big || *s_overflow != 0;
         const u32 nd = min(*s_distinct, (u32)HC2_CLAIM_CAP);
         const u32 n_empty = *s_empty;
         // pass 2: count the keys that have a slot
+        u32 hits = 0;
         if (!ovf && nd) {
 #pragma unroll
             for (int j = 0; j < HC2_PREFETCH; ++j) {
                 const u32 i = j * HC2_THREADS + threadIdx.x;
-                if (i < n && kcur[j] != HC_EMPTY) hc2_pass2(kcur[j], tkeys, tcnt);
+                if (i < n && kcur[j] != HC_EMPTY) hits += hc2_pass2(kcur[j], tkeys, tcnt);
             }
-            for (u32 i = HC2_PREFETCH * HC2_THREADS + threadIdx.x; i < n; i += HC2_THREADS) {
-                const ull key = keys2[lo + i];
-                if (key != HC_EMPTY) hc2_pass2(key, tkeys, tcnt);
-            }
+
         }
+        if (dbg && hits) atomicAdd(&dbg[0], (ull)hits);
         BLOCK_SYNC();
         if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
         for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC2_THREADS) {
@@ -475,6 +486,7 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
                 cnt = tcnt[p];
                 tkeys[p] = HC_EMPTY;
                 tcnt[p] = 0;
+                if (dbg) { atomicAdd(&dbg[1], (ull)cnt); atomicAdd(&dbg[2], 1ull); if (key == HC_EMPTY) atomicAdd(&dbg[3], 1ull); }
             } else if (i == nd && n_empty) {
                 key = HC_EMPTY;
                 cnt = n_empty;

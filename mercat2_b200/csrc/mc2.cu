@@ -36,6 +36,7 @@ struct mc2_engine {
     int opt_force_path = 0;
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
+    int opt_scatter_variant = 0;           // bit0: stage destination indices, bit1: max shared-memory carveout
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
     // stats
@@ -533,18 +534,26 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         CUDA_CHECK(cudaMemsetAsync(keys1.p, 0xEE, cap * 8, e->stream));
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
+    const bool use_dst = e->opt_scatter_variant & 1;
+    const size_t sc_smem = use_dst ? HC_SCATTER_SMEM : (size_t)HC_TILE * 10;
     {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr_set = true;
+        static thread_local int attr_variant = -1;
+        if (attr_variant != e->opt_scatter_variant) {
+            const int carve = (e->opt_scatter_variant & 2) ? 100 : -1;
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            attr_variant = e->opt_scatter_variant;
         }
     }
     if (pv) {
-        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, HC_SCATTER_SMEM, *pv, k, nb, nb1, cur1.p, keys1.p);
+        if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p);
+        else LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p);
     } else {
         auto kern = hc_scatter1_kernel<ENC>;
         static thread_local bool attr_set[3] = {false, false, false};
@@ -554,8 +563,12 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         }
         LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, HC_SCATTER_SMEM, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
     }
-    LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, HC_SCATTER_SMEM, (const u64*)keys1.p, (const u32*)sub_base.p,
-           (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+    if (use_dst)
+        LAUNCH(e, hc_scatter2_kernel<true>, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
+               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+    else
+        LAUNCH(e, hc_scatter2_kernel<false>, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
+               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
     if (dbg) {
         DBuf<ull> badc(e, 2);
         badc.zero();
@@ -567,6 +580,15 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         const ull b1 = read_scalar<ull>(e, badc.p), b2 = read_scalar<ull>(e, badc.p + 1);
         fprintf(stderr, "[hash] cap=%llu total=%llu nb1=%u nb=%u packed=%d misplaced level1=%llu level2=%llu\n", (ull)cap, (ull)total, nb1, nb,
                 pv ? 1 : 0, b1, b2);
+        DBuf<ull> cs(e, 9);
+        cs.zero();
+        if (pv) LAUNCH(e, fn_checksum_kernel, 256, 256, 0, *pv, k, cs.p);
+        LAUNCH(e, key_checksum_kernel, 256, 256, 0, (const u64*)keys1.p, total, cs.p + 3);
+        LAUNCH(e, key_checksum_kernel, 256, 256, 0, (const u64*)keys2.p, total, cs.p + 6);
+        ull h[9];
+        d2h(e, h, cs.p, 9);
+        fprintf(stderr, "[hash] checksum stream (%llx %llx %llu) keys1 (%llx %llx %llu) keys2 (%llx %llx %llu)%s\n", h[0], h[1], h[2], h[3],
+                h[4], h[5], h[6], h[7], h[8], (pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) ? "  MISMATCH" : "");
     }
     const u64 out_cap = cap / s->c + 2;
     FastPart part;
@@ -582,7 +604,42 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             attr_set = true;
         }
         LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
+               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n, (ull*)nullptr);
+        if (dbg) {                                                // stress: repeat on the same keys, results must not vary
+            DBuf<ull> dc(e, 8 + (u64)cgrid * 64);
+            DBuf<Tail> t2(e, 1);
+            DBuf<u64> ok2(e, out_cap), oc2(e, out_cap);
+            for (int rep = 0; rep < 40; ++rep) {
+                dc.zero();
+                t2.zero();
+                LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
+                       ok2.p, oc2.p, &t2.p->out_n, out_cap, ovf_list.p, &t2.p->ovf_n, dc.p);
+                ull h[4];
+                d2h(e, h, dc.p, 4);
+                if (cgrid == nb) {                                 // one bucket per CTA: barrier timestamps are meaningful
+                    std::vector<ull> ts((u64)cgrid * 64);
+                    d2h(e, ts.data(), dc.p + 8, (u64)cgrid * 64);
+                    int leaks1 = 0, leaks2 = 0;
+                    for (unsigned cta = 0; cta < cgrid; ++cta) {
+                        ull max_end1 = 0, min_beg2 = ~0ull, max_end2 = 0, min_beg3 = ~0ull;
+                        for (int w = 0; w < 16; ++w) {
+                            const ull* q = &ts[((u64)cta * 16 + w) * 4];
+                            max_end1 = std::max(max_end1, q[0]); min_beg2 = std::min(min_beg2, q[1]);
+                            max_end2 = std::max(max_end2, q[2]); min_beg3 = std::min(min_beg3, q[3]);
+                        }
+                        if (min_beg2 < max_end1) leaks1++;
+                        if (min_beg3 < max_end2) leaks2++;
+                    }
+                    if (leaks1 || leaks2) fprintf(stderr, "[hash] BARRIER LEAK rep %d: %d CTAs passed the pass1|pass2 barrier early, %d the pass2|emit barrier\n", rep, leaks1, leaks2);
+                }
+                const Tail tt = read_scalar<Tail>(e, t2.p);
+                static ull first_out = 0, first_hits = 0, first_claims = 0;
+                if (rep == 0) { first_out = tt.out_n; first_hits = h[0]; first_claims = h[2]; }
+                if (h[0] != h[1] || tt.out_n != first_out || h[0] != first_hits || h[2] != first_claims || h[3])
+                    fprintf(stderr, "[hash] STRESS rep %d: pass2 hits %llu, counts read back %llu, claims %llu (first %llu), empty-key slots %llu, survivors %llu (first %llu)\n",
+                            rep, h[0], h[1], h[2], first_claims, h[3], (ull)tt.out_n, first_out);
+            }
+        }
     } else {
         static thread_local bool attr_set = false;
         if (!attr_set) {
@@ -594,6 +651,15 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     }
     const Tail t = read_scalar<Tail>(e, tail.p);
     if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
+    if (dbg) {                                                    // the sort path on the same keys must agree
+        mc2_sample tmp;
+        tmp.e = e; tmp.k = k; tmp.c = s->c;
+        count_key_range_sorted(e, &tmp, keys2.p, t.total, 64);
+        u64 ref_rows = 0;
+        for (auto& p : tmp.fast) ref_rows += p.n;
+        fprintf(stderr, "[hash] survivors: tables %llu (+%u overflowed buckets) sort %llu%s\n", (ull)t.out_n, t.ovf_n, (ull)ref_rows,
+                (!t.ovf_n && ref_rows != t.out_n) ? "  MISMATCH" : "");
+    }
     if (t.out_n) {
         if (pv) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(t.out_n, 256), 256, 0, part.keys.p, (u64)t.out_n, k);
         part.n = t.out_n;
@@ -885,15 +951,97 @@ static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 
     return bounds;
 }
 
+// Pipelined upload: the text goes to the device in pieces on the copy stream (straight from pinned memory, or
+// through the two pinned staging buffers for a pageable source) while the compute stream already chunks and
+// counts the pieces that have landed.
+struct Uploader {
+    mc2_engine* e;
+    const u8* src;
+    u8* dst;
+    u64 n, piece, issued = 0;
+    bool pinned = false;
+    std::vector<cudaEvent_t> done;        // done[j]: piece j is on the device
+    int slot = 0;
+    Uploader(mc2_engine* e_, const void* text, u64 nbytes, u8* dst_) : e(e_), src((const u8*)text), dst(dst_), n(nbytes) {
+        piece = mc2_engine::STAGE_BYTES;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, text) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+        done.resize(div_up(n, piece), nullptr);
+    }
+    ~Uploader() {
+        for (auto ev : done) if (ev) e->ev_pool.push_back(ev);
+    }
+    // make sure everything below `upto` has been issued; the compute stream then waits for it on the device
+    void need(u64 upto) {
+        upto = std::min(upto, n);
+        while (issued < upto) {
+            const u64 j = issued / piece, len = std::min(piece, n - issued);
+            if (pinned) {
+                CUDA_CHECK(cudaMemcpyAsync(dst + issued, src + issued, len, cudaMemcpyHostToDevice, e->copy_stream));
+            } else {
+                CUDA_CHECK(cudaEventSynchronize(e->stage_ev[slot]));
+                memcpy(e->pin_stage[slot], src + issued, len);
+                CUDA_CHECK(cudaMemcpyAsync(dst + issued, e->pin_stage[slot], len, cudaMemcpyHostToDevice, e->copy_stream));
+                CUDA_CHECK(cudaEventRecord(e->stage_ev[slot], e->copy_stream));
+                slot ^= 1;
+            }
+            done[j] = e->get_event();
+            CUDA_CHECK(cudaEventRecord(done[j], e->copy_stream));
+            issued += len;
+        }
+        if (upto) CUDA_CHECK(cudaStreamWaitEvent(e->stream, done[(upto - 1) / piece], 0));
+    }
+    // with a pinned source all copies can be queued at once (they run in order on the copy stream)
+    void issue_all() { if (pinned) { const u64 keep = issued; (void)keep; while (issued < n) need_issue_only(); } }
+    void need_issue_only() {
+        const u64 j = issued / piece, len = std::min(piece, n - issued);
+        CUDA_CHECK(cudaMemcpyAsync(dst + issued, src + issued, len, cudaMemcpyHostToDevice, e->copy_stream));
+        done[j] = e->get_event();
+        CUDA_CHECK(cudaEventRecord(done[j], e->copy_stream));
+        issued += len;
+    }
+};
+
 static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u64 chunk_bytes, u64* n_chunks,
                        std::vector<u64>* bounds_out) {
     mc2_engine* e = s->e;
-    DBuf<u8> holder;
-    const u8* d = to_device(e, text, nbytes, space, holder);
-    std::vector<u64> bounds = chunk_bounds(e, d, nbytes, chunk_bytes);
-    for (size_t i = 0; i < bounds.size(); ++i) {
-        const u64 a = bounds[i], b = i + 1 < bounds.size() ? bounds[i + 1] : nbytes;
-        count_chunk(e, s, d + a, b - a);
+    std::vector<u64> bounds(1, 0);
+    if (space == MC2_DEVICE || nbytes == 0 || chunk_bytes == 0 || nbytes <= 2 * mc2_engine::STAGE_BYTES) {
+        // resident text (or a single piece): find all boundaries at once
+        DBuf<u8> holder;
+        const u8* d = to_device(e, text, nbytes, space, holder);
+        bounds = chunk_bounds(e, d, nbytes, chunk_bytes);
+        for (size_t i = 0; i < bounds.size(); ++i) {
+            const u64 a = bounds[i], b = i + 1 < bounds.size() ? bounds[i + 1] : nbytes;
+            count_chunk(e, s, d + a, b - a);
+        }
+    } else {
+        // host text, chunked: overlap the upload with chunking + counting.  The boundary after `b` is the first
+        // candidate line whose translated offset from b reaches chunk_bytes (lib/mercat2_Chunker.py:45-52); it is
+        // searched in the window [b, b + chunk_bytes + margin) and the window grows until it is found.
+        DBuf<u8> holder(e, nbytes + 16);
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));            // the buffer exists before the copy stream writes it
+        Uploader up(e, text, nbytes, holder.p);
+        up.issue_all();
+        e->h2d_bytes += nbytes;
+        const u64 margin = 4ull << 20;
+        u64 b = 0;
+        while (b < nbytes) {
+            u64 win_end = std::min(nbytes, b + chunk_bytes + margin);
+            u64 nb = nbytes;
+            while (true) {
+                up.need(win_end);
+                const std::vector<u64> wb = chunk_bounds(e, holder.p + b, win_end - b, chunk_bytes);
+                if (wb.size() >= 2) { nb = b + wb[1]; break; }
+                if (win_end == nbytes) { nb = nbytes; break; }
+                win_end = std::min(nbytes, win_end + chunk_bytes);
+            }
+            count_chunk(e, s, holder.p + b, nb - b);
+            b = nb;
+            if (b < nbytes) bounds.push_back(b);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
     }
     if (n_chunks) *n_chunks = bounds.size();
     if (bounds_out) *bounds_out = bounds;
@@ -1068,6 +1216,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "force_encoding") e->opt_force_enc = (int)value;
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
+    else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);

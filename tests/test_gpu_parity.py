@@ -375,6 +375,33 @@ def test_virtual_chunking_vs_oracle(engine, tmp_path):
         assert got == want, f"chunk={chunk}: {diff_msg(got, want)}"
 
 
+def test_streaming_upload_equals_resident(engine):
+    """host text (pageable and pinned) goes through the pipelined upload + windowed boundary search; the device-
+    resident text through the whole-text boundary search: same pieces, same table"""
+    import torch
+    import bench
+    reset(engine)
+    dev = torch.device("cuda", 0)
+    genomes = bench.make_genomes(dev, 0.002)
+    text = bench.make_reads_text(dev, genomes, 500_000, 0)          # 82 MB, ~4x coverage: plenty of survivors
+    chunk = 16 << 20
+    t_dev, offs_dev = engine.count_sample(text, 25, 3, chunk)
+    k_dev, c_dev = t_dev.arrays()
+    assert len(offs_dev) == 5 and len(c_dev) > 1000
+    host = text.cpu()
+    for name, buf in (("pageable", host.numpy()), ("pinned", host.pin_memory())):
+        t_h, offs_h = engine.count_sample(buf, 25, 3, chunk)
+        k_h, c_h = t_h.arrays()
+        assert offs_h == offs_dev, name
+        assert (k_h == k_dev).all() and (c_h == c_dev).all(), name
+    # and against the oracle on a prefix small enough for it
+    small = host.numpy()[:164 * 20000].tobytes()
+    want = orc.merge_counts(orc.find_kmers_text("".join(p), 25, 2)
+                            for p in orc.chunker_pieces(small.decode().splitlines(True), 1 << 20))
+    got = engine.count_sample(small, 25, 2, 1 << 20)[0].to_dict()
+    assert got == want, diff_msg(got, want)
+
+
 def test_large_dense_and_sparse_properties(engine):
     """Size-independent properties at a larger size: sum of counts == number of windows; forcing
     another path gives the same table; c filter is monotone."""

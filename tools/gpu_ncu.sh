@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 KERNEL=${1:-rs_scatter}
 SKIP=${2:-8}
-CMD="python bench.py --reads-per-gpu 1400000 --genome-scale 0.05 --steps 1 --warmup 1 --no-cpu --no-e2e"
+CMD="python bench.py --reads-per-gpu 1400000 --genome-scale ${MC2_GENOME_SCALE:-1.0} --steps 1 --warmup 1 --no-cpu --no-e2e"
 NAMES='regex:parse_|rs_|scan_|rle_|extract_|chunk_|dense_|gather_|iota_|wide_|seg_|mt_|symbol_|hc_|fn_|fill_'
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$NAMES" -c 3000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
