@@ -318,9 +318,10 @@ def main():
         alg = algorithmic_bytes(top[0], windows_per_chunk, nbytes / max(1, n_chunks), args.k)
         avg_us = top[1]["us"] / max(1, top[1]["launches"])
         achieved = alg / (avg_us * 1e-6) / 1e9 if alg else None
-        # the whole extract+count pipeline against SURVEY 8(d)'s sparse-path formula
+        # the whole path against SURVEY 8(d)'s sparse formula: text read once + every key written once and read
+        # once (8 + 8 B per window) + 12 B per row of the emitted table (rows = survivors of the -c filter)
         w_total = bases_per_step * (READ_LEN - args.k + 1) / READ_LEN
-        pipeline_alg = nbytes + 16.0 * w_total + 12.0 * w_total        # D ~= W per chunk at this coverage
+        pipeline_alg = nbytes + 16.0 * w_total + 12.0 * rows
         pipeline_gbs = pipeline_alg * args.steps / (dev_us * 1e-6) / 1e9 if dev_us else None
         out = {
             "metric": "input bases/sec (k-mers counted/sec) per GPU and 8xB200; % of HBM roofline",
@@ -337,6 +338,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "kernel_share_of_step": top[1]["us"] / tot_us,
+                         "algorithmic_bytes_per_launch": alg, "avg_launch_us": avg_us,
+                         "pipeline_bytes_per_base": pipeline_alg / bases_per_step,
                          "pipeline_achieved": pipeline_gbs, "pipeline_frac": (pipeline_gbs / peak) if pipeline_gbs else None},
             "kernels": {k2: {"launches": v["launches"], "ms": round(v["us"] / 1e3, 3)} for k2, v in
                         sorted(profile.items(), key=lambda kv: -kv[1]["us"])[:12]},
@@ -366,18 +369,30 @@ def main():
 
 
 def algorithmic_bytes(kernel, windows, text_bytes, k):
-    """Algorithmic bytes of ONE launch of the named kernel for one chunk."""
+    """Algorithmic bytes of ONE launch of the named kernel for one chunk: what the
+    kernel must read and write once, not what it happens to move."""
     name = kernel.split("<")[0]
-    if name in ("rs_scatter_kernel",):
-        return 16.0 * windows                  # every key read once and written once
-    if name in ("rs_hist_kernel",):
-        return 8.0 * windows
-    if name == "extract_keys_kernel":
-        return text_bytes * (READ_LEN + 1) / REC_BYTES + 8.0 * windows
+    symbols = text_bytes * (READ_LEN + 1) / REC_BYTES            # bases + one separator per read
+    packed = symbols * 0.375                                     # 2-bit codes + 1 validity bit per symbol
+    table = {
+        "fn_parse_kernel": text_bytes + packed if "true" in kernel else text_bytes,
+        "fn_hist_kernel": packed,
+        "fn_scatter1_kernel": packed + 8.0 * windows,            # every key written once
+        "hc_scatter1_kernel": symbols + 8.0 * windows,
+        "hc_scatter2_kernel": 16.0 * windows,                    # every key read once and written once
+        "hc_count2_kernel": 8.0 * windows,                       # every key read once
+        "hc_count_kernel": 8.0 * windows,
+        "rs_scatter_kernel": 16.0 * windows,
+        "rs_hist_kernel": 8.0 * windows,
+        "extract_keys_kernel": symbols + 8.0 * windows,
+        "chunk_candidates_kernel": text_bytes,
+    }
+    if name in table:
+        return table[name]
     if name.startswith("parse_"):
         return text_bytes
     if name.startswith("dense_"):
-        return text_bytes * (READ_LEN + 1) / REC_BYTES
+        return symbols
     return None
 
 

@@ -90,6 +90,10 @@ typedef struct mc2_sample mc2_sample;
 int mc2_sample_begin(mc2_engine* e, int k, int64_t min_count, mc2_sample** out);
 int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes,
                         uint64_t* n_chunks);
+/* Add already counted rows (rows*k bytes of k-mer text + rows counts, host memory) to the sample: the serial dict
+ * merge of bin/mercat2.py:121-127 for tables that were counted elsewhere (another GPU / rank).  Equal k-mers are
+ * summed by mc2_sample_finish on the device. */
+int mc2_sample_add_rows(mc2_sample* s, const char* kmers, const uint64_t* counts, uint64_t rows);
 int mc2_sample_finish(mc2_sample* s, mc2_table** out);   /* consumes s */
 void mc2_sample_abort(mc2_sample* s);
 

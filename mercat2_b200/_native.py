@@ -35,6 +35,7 @@ SYMBOLS = [
     ("mc2_chunk_offsets", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64, _U64, _PU64]),
     ("mc2_sample_begin", _INT, [_VP, _INT, _I64, _PP]),
     ("mc2_sample_add_text", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64]),
+    ("mc2_sample_add_rows", _INT, [_VP, _VP, _VP, _U64]),
     ("mc2_sample_finish", _INT, [_VP, _PP]),
     ("mc2_sample_abort", None, [_VP]),
     ("mc2_table_rows", _U64, [_VP]),
@@ -291,6 +292,13 @@ class Sample:
         lib = self._engine._lib
         _check(lib, lib.mc2_sample_add_text(self._h, addr, n, space, chunk_bytes, C.byref(nchunks)))
         return int(nchunks.value)
+
+    def add_rows(self, kmers, counts):
+        """Add counted rows: kmers uint8[rows, k], counts uint64[rows] (equal k-mers are summed at finish)."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint8)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_sample_add_rows(self._h, kmers.ctypes.data, counts.ctypes.data, len(counts)))
 
     def finish(self) -> Table:
         out = C.c_void_p()

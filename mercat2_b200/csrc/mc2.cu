@@ -197,10 +197,11 @@ struct FastPart {          // unique (key, count) rows in the sample's fast enco
     u64 n = 0;
     bool sorted = true;    // rows ordered by key (the hash path emits unordered rows)
 };
-struct WidePart {          // sorted, unique k-byte rows
+struct WidePart {          // unique k-byte rows
     DBuf<u8> rows;
     DBuf<u64> counts;
     u64 n = 0;
+    bool sorted = true;
 };
 
 enum : int { PATH_UNSET = 0, PATH_DENSE = 1, PATH_SPARSE = 2, PATH_WIDE = 3 };
@@ -431,7 +432,7 @@ static void reduce_wide_parts(mc2_engine* e, std::vector<WidePart>& parts, int k
     for (auto& p : parts) M += p.n;
     out.n = 0;
     if (M == 0) return;
-    if (parts.size() == 1 && c <= 1) { out = std::move(parts[0]); return; }
+    if (parts.size() == 1 && c <= 1 && parts[0].sorted) { out = std::move(parts[0]); return; }
     DBuf<u8> rows(e, M * (u64)k);
     DBuf<u64> w(e, M), pos(e, M);
     u64 at = 0;
@@ -1286,6 +1287,26 @@ int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int sp
     u64 nc = 0;
     sample_add(s, text, nbytes, space, chunk_bytes, &nc, nullptr);
     if (n_chunks) *n_chunks = nc;
+    API_END
+}
+
+int mc2_sample_add_rows(mc2_sample* s, const char* kmers, const uint64_t* counts, uint64_t rows) {
+    API_BEGIN
+    if (!s || (rows && (!kmers || !counts))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    mc2_engine* e = s->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    if (rows) {
+        WidePart part;
+        part.n = rows;
+        part.sorted = false;
+        part.rows.alloc(e, rows * (u64)s->k);
+        part.counts.alloc(e, rows);
+        CUDA_CHECK(cudaMemcpyAsync(part.rows.p, kmers, rows * (u64)s->k, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(part.counts.p, counts, rows * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->h2d_bytes += rows * ((u64)s->k + 8);
+        s->wide.push_back(std::move(part));
+    }
     API_END
 }
 

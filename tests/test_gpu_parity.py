@@ -481,3 +481,48 @@ def test_metrics_scalar_entry_points(engine, capsys):
             want.append((name, name.split()[0], float(len(seq)), orc.predict_isoelectric_point_ProMoST(seq),
                          orc.calculate_MW(seq), orc.calculate_hydro(seq)))
     assert sorted(got) == sorted(want)
+
+
+# ---- 6. the command line and the multi-rank merge ------------------------------------------------------
+def test_cli_end_to_end(golden_configs, reference_results, tmp_path):
+    """bin/mercat2.py -i <5 proteomes> -k 5 -c 10 -s 1 reproduces the reference's committed TSVs; and the
+    nucleotide flow (removeN -> clean/*.fna.gz -> count) reproduces config 1."""
+    import subprocess, sys
+    from conftest import ROOT
+    inputs = []
+    for base in ("RW1_pro", "GIC31_pro"):
+        src = tmp_path / f"{base}.faa"
+        src.write_bytes(read_maybe_gz(GOLDEN / "data/faa_gz" / f"{base}.faa.gz"))
+        inputs.append(str(src))
+    out = tmp_path / "out"
+    proc = subprocess.run([sys.executable, str(ROOT / "bin/mercat2.py"), "-i", *inputs, "-k", "5", "-c", "10", "-s", "1",
+                           "-o", str(out)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert "Significant k-mers:" in proc.stdout
+    for base in ("RW1_pro", "GIC31_pro"):
+        blob = (out / "tsv_protein" / f"{base}_counts.tsv").read_bytes()
+        assert md5(blob) == reference_results["faa-5genomes-1"]["tsv"][base]["tsv_md5"]
+    assert (out / "report" / "metrics-protein.tsv").read_text().count("\n") > 300
+    out2 = tmp_path / "out2"
+    proc = subprocess.run([sys.executable, str(ROOT / "bin/mercat2.py"), "-i", str(GOLDEN / "data/fna_gz/RW1.fna.gz"),
+                           "-k", "3", "-o", str(out2)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert md5((out2 / "tsv_nucleotide" / "RW1_counts.tsv").read_bytes()) == golden_configs["nucleotide_k3_c10"]["RW1"]["tsv_md5"]
+    assert (out2 / "clean" / "RW1_clean.fna.gz").exists()
+
+
+def test_engine_reducer_merges_rank_tables(engine):
+    """two 'ranks' count disjoint sets of pieces; the engine reducer (device sort + reduce-by-key over added
+    rows) must give the reference's merged table"""
+    from mercat2_b200 import distributed as mcd
+    reset(engine)
+    text = synth_reads(4000, 150, seed=9, n_rate=0.003, lower_rate=0.02, genome_len=60000)
+    reads = [b">" + r for r in text.split(b">") if r]
+    halves = [b"".join(reads[0::2]), b"".join(reads[1::2])]
+    for k, c in ((21, 2), (33, 2), (4, 5)):
+        tables = [engine.count_text(h, k, c).arrays() for h in halves]
+        mk, mc = mcd.engine_reducer(engine)([t[0] for t in tables], [t[1] for t in tables], k)
+        got = {bytes(r).decode(): int(n) for r, n in zip(mk, mc)}
+        want = orc.merge_counts(orc.find_kmers_text(h.decode(), k, c) for h in halves)
+        assert got == want, diff_msg(got, want)
+        assert mcd.tsv_bytes("s", mk, mc) == orc.tsv_bytes("s", want)

@@ -89,3 +89,16 @@ def test_chunk_trigger(tmp_path):
     f = tmp_path / "x.fa"
     f.write_bytes(b"A" * (1 << 20))
     assert chunk_trigger(f, 1) == 1 << 20 and chunk_trigger(f, 2) == 0 and chunk_trigger(f, 0) == 0
+
+
+def test_cli_flags_and_classification():
+    from mercat2_b200 import cli
+    args, _ = cli.parseargs(["-i", __file__, "-k", "5"])
+    assert args.c == 10 and args.s == 100 and args.o == "mercat_results" and not args.toupper and not args.skipclean
+    args, _ = cli.parseargs(["-i", __file__, "-k", "31", "-c", "2", "-s", "1", "-toupper", "-skipclean", "-replace"])
+    assert (args.k, args.c, args.s, args.toupper, args.skipclean, args.replace) == (31, 2, 1, True, True, True)
+    assert cli.classify("x/DJ.fna.gz") == ("nucleotide", "DJ")
+    assert cli.classify("x/DJ_pro.faa") == ("protein", "DJ_pro")
+    assert cli.classify("x/Test_R1.fastq") == ("fastq", "Test_R1")
+    assert cli.classify("x/a.b.fasta") == ("nucleotide", "a.b")
+    assert cli.classify("x/readme.txt")[0] is None
