@@ -24,8 +24,9 @@
 
 struct FnStats {
     ull n_sym;      // symbols emitted (kept bytes + one separator per header line)
-    ull packed;     // low 32 bits: kept bytes; high 32 bits: kept bytes outside {A,C,G,T}
+    ull packed;     // low 32 bits: kept bytes; high 32 bits: kept bytes outside {A,C,G,T}   (count pass, MODE 0)
     ull complex;    // != 0: text is not "simple" -> use the general parser
+    ull packed2;    // same fields as `packed`, accumulated by the write pass
 };
 
 __device__ __forceinline__ u32 fn_nz(u32 x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
@@ -39,6 +40,7 @@ struct FnMasks {
     u32 cx;             // != 0: a byte outside the simple subset
 };
 
+template <bool CODES>
 __device__ __forceinline__ FnMasks fn_classify(const u32 w[4]) {
     FnMasks m;
     m.nl = m.gt = m.acgt = m.codes = m.cx = 0;
@@ -50,6 +52,7 @@ __device__ __forceinline__ FnMasks fn_classify(const u32 w[4]) {
         m.cx |= (fn_lt21(x) & ~mnl) | fn_eq(x, 0x2A2A2A2Au) | (x & 0x80808080u);
         m.nl |= fn_movemask(mnl) << (4 * q);
         m.gt |= fn_movemask(mgt) << (4 * q);
+        if (!CODES) continue;
         const u32 t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;            // A,C,G,T -> 0,1,2,3 per byte
         u32 p = t | (t >> 6);
         p = (p | (p >> 12)) & 0xFFu;
@@ -133,10 +136,13 @@ __device__ __forceinline__ u32 fn_compress(u32 src, u32 mask) {
 }
 
 // ---- K1f: count pass (WRITE = false) and write pass (WRITE = true) --------------------------------------
-template <bool WRITE>
+// MODE 0: count pass with alphabet statistics (first piece of a sample); MODE 1: write pass (also counts the kept
+// non-ACGT bytes); MODE 2: light count pass (line structure only).
+template <int MODE>
 __global__ void __launch_bounds__(FN_THREADS)
 fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_state, u32* __restrict__ tile_cnt,
                 const u64* __restrict__ tile_off, u32* __restrict__ codes, u32* __restrict__ bad, FnStats* stats) {
+    constexpr bool WRITE = MODE == 1;
     __shared__ u32 sm[FN_WARPS + 1];
     __shared__ u32 s_state;
     __shared__ u32 s_c[WRITE ? 260 : 1], s_b[WRITE ? 132 : 1];
@@ -145,7 +151,7 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
     const u64 p0 = tile_v + (u64)threadIdx.x * 16;
     u32 w[4];
     load16(v, p0, w);
-    const FnMasks m = fn_classify(w);
+    const FnMasks m = fn_classify<MODE != 2>(w);
     if (!WRITE) {
         if (threadIdx.x < 32) {
             bool cx = false;
@@ -170,13 +176,22 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
     if (!WRITE) {
         if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
         // statistics: one 64-bit atomic per tile (kept | non-ACGT << 32); `complex` only when it happens
-        const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
-        u32 t_kept, t_slow;
-        block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
-        block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
-        if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed, (ull)t_kept | ((ull)t_slow << 32));
+        if (MODE == 0) {
+            const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
+            u32 t_kept, t_slow;
+            block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
+            block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
+            if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed, (ull)t_kept | ((ull)t_slow << 32));
+        }
         if (m.cx) atomicAdd(&stats->complex, 1ull);
     } else {
+        {   // kept bytes outside ACGT (their windows go to the wide path): known only now in the light flow
+            const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
+            u32 t_kept, t_slow;
+            block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
+            block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
+            if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed2, (ull)t_kept | ((ull)t_slow << 32));
+        }
         if (total == 0) return;
         const u64 s_tile = tile_off[blockIdx.x];            // global symbol index of the tile's first symbol
         const u64 base_sym = s_tile & ~31ull;
@@ -216,6 +231,34 @@ struct PackedView {
     const u32* bad;
     u64 n;             // symbols
 };
+
+// the three code words that hold the 16 windows starting in word g, and the mask of countable windows
+struct FnWords { u32 w0, w1, w2; };
+__device__ __forceinline__ u64 fn_key(const FnWords& w, int j, u64 mask) {       // j must be a compile-time constant
+    const u32 lo = __funnelshift_r(w.w0, w.w1, 2 * j);
+    const u32 hi = __funnelshift_r(w.w1, w.w2, 2 * j);
+    return (((u64)hi << 32) | lo) & mask;
+}
+__device__ __forceinline__ u32 fn_load_windows(const PackedView& pv, u64 g, int k, FnWords& w) {
+    const u64 nwords = (pv.n + 15) >> 4;
+    w.w0 = w.w1 = w.w2 = 0;
+    if (g >= nwords) return 0;
+    w.w0 = pv.codes[g];
+    w.w1 = g + 1 < nwords ? pv.codes[g + 1] : 0u;
+    w.w2 = g + 2 < nwords ? pv.codes[g + 2] : 0u;
+    const u64 nbw = (pv.n + 31) >> 5;
+    const u64 bi = g >> 1;
+    u64 b = (u64)pv.bad[bi] | ((bi + 1 < nbw ? (u64)pv.bad[bi + 1] : 0xFFFFFFFFull) << 32);
+    b >>= (g & 1) * 16;
+    b |= 0xFFFF000000000000ull;
+    const u64 first = g << 4;
+    if (first + 48 > pv.n) b |= ~0ull << (pv.n - first);
+    u64 x = b;
+    int cur = 1;
+    while (cur * 2 <= k) { x |= x >> cur; cur *= 2; }
+    if (cur < k) x |= x >> (k - cur);
+    return ~(u32)x & 0xFFFFu;
+}
 
 // 16 windows starting in code word g: keys (stream order) and the mask of countable windows
 __device__ __forceinline__ u32 fn_windows(const PackedView& pv, u64 g, int k, u64 mask, u64 keys[16]) {
@@ -280,10 +323,11 @@ fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
     BLOCK_SYNC();
     const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
-    u64 mine[16];
-    const u32 valid = fn_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, mask, mine);
+    FnWords w;
+    const u32 valid = fn_load_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, w);
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
-    hc_group_and_write<USE_DST>(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    // keys are recomputed (two funnel shifts) wherever they are needed instead of living in 32 registers
+    hc_group_and_write<USE_DST>([&](int i) { return fn_key(w, i, mask); }, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)

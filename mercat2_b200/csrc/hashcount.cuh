@@ -118,8 +118,8 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 // cnt / loff / gbase: nd words each; stage / sdst: one slot per key of the tile.  Every thread calls; bit i of
 // `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.  Keys are
 // re-ordered through shared memory so that consecutive threads store consecutive addresses of one digit's run.
-template <bool USE_DST, class DigitFn>
-__device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
+template <bool USE_DST, class KeyFn, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write(KeyFn mine, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                    u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
                                                    u64* __restrict__ out) {
     u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
@@ -128,7 +128,7 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if ((valid >> i) & 1u) {
-            const u32 d = dig(mine[i]);
+            const u32 d = dig(mine(i));
             const u32 r = atomicAdd(&cnt[d], 1u);
             rk[i >> 1] |= r << (16 * (i & 1));
             dg[i >> 1] |= d << (16 * (i & 1));
@@ -155,7 +155,7 @@ __device__ __forceinline__ void hc_group_and_write(const u64 mine[16], u32 valid
             const u32 d = (dg[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
             const u32 r = (rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
             const u32 pos = loff[d] + r;
-            stage[pos] = mine[i];
+            stage[pos] = mine(i);
             if (USE_DST) sdst[pos] = gbase[d] + r;
             else reinterpret_cast<u16*>(sdst)[pos] = (u16)d;
         }
@@ -195,7 +195,7 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
         if (fast && first + i < s1) valid |= 1u << i;
     });
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };      // nb == nb1 * HC_NB2
-    hc_group_and_write<true>(mine, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    hc_group_and_write<true>([&](int i) { return mine[i]; }, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
@@ -230,7 +230,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
-    hc_group_and_write<USE_DST>(mine, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    hc_group_and_write<USE_DST>([&](int i) { return mine[i]; }, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
@@ -365,27 +365,30 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
 
 __device__ __forceinline__ u32 hc2_slot(u64 prod) { return (u32)(prod >> 20) & (HC2_SLOTS - 1); }
 
-__device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u16* claimed, u32* s_distinct, u32* s_overflow) {
+// Pass 1.  Returns the number of times this key has now been seen with its bitmap bit already set (0 if the bit
+// was clear).  The true multiplicity of a key is that number or that number + 1 (its very first occurrence set
+// the bit itself unless another key's bit collided), so a bucket in which no key reaches min_count - 1 flagged
+// occurrences has no survivor and needs no exact second pass.
+__device__ __forceinline__ u32 hc2_pass1(ull key, u32* bm, ull* tkeys, u32* tcnt, u16* claimed, u32* s_distinct, u32* s_overflow) {
     const u64 prod = key * 0xD6E8FEB86659FD93ull;
     const u32 bi = (u32)(prod >> (64 - HC2_BM_BITS_LOG2));
     const u32 bit = 1u << (bi & 31);
     const u32 old = atomicOr(&bm[bi >> 5], bit);
-    if (old & bit) {                                        // repeat (or false positive): make sure the key has a slot
-        u32 p = hc2_slot(prod);
-        while (true) {
-            ull cur = tkeys[p];
+    if (!(old & bit)) return 0u;
+    u32 p = hc2_slot(prod);                                  // repeat (or false positive): give the key a slot
+    while (true) {
+        ull cur = tkeys[p];
+        if (cur == HC_EMPTY) {
+            cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
             if (cur == HC_EMPTY) {
-                cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
-                if (cur == HC_EMPTY) {
-                    const u32 d = smem_atom_inc(s_distinct);
-                    if (d < HC2_CLAIM_CAP) claimed[d] = (u16)p;
-                    if (d >= HC2_LIMIT) *s_overflow = 1;
-                    return;
-                }
+                const u32 d = smem_atom_inc(s_distinct);
+                if (d < HC2_CLAIM_CAP) claimed[d] = (u16)p;
+                if (d >= HC2_LIMIT) *s_overflow = 1;
+                cur = key;
             }
-            if (cur == key) return;
-            p = (p + 1) & (HC2_SLOTS - 1);
         }
+        if (cur == key) return smem_atom_inc(&tcnt[p]) + 1u;
+        p = (p + 1) & (HC2_SLOTS - 1);
     }
 }
 __device__ __forceinline__ u32 hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
@@ -408,7 +411,7 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
     ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4);                 // HC2_SLOTS
     u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 8);
     u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12);
-    __shared__ u32 s_scal[2][4];                            // per parity: empty-key count, distinct, overflow
+    __shared__ u32 s_scal[2][4];                            // per parity: empty-key count, distinct, overflow, need-pass-2
     for (u32 i = threadIdx.x; i < HC2_SLOTS; i += HC2_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
     for (u32 i = threadIdx.x; i < HC2_BM_WORDS; i += HC2_THREADS) bm[i] = 0;
     if (threadIdx.x < 8) (&s_scal[0][0])[threadIdx.x] = 0;
@@ -431,6 +434,7 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
         u32* s_empty = &s_scal[par][0];
         u32* s_distinct = &s_scal[par][1];
         u32* s_overflow = &s_scal[par][2];
+        u32* s_need = &s_scal[par][3];
         const u32 n = n_n;
         ull kcur[HC2_PREFETCH];
 #pragma unroll
@@ -456,16 +460,21 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
             const u32 i = j * HC2_THREADS + threadIdx.x;
             if (!big && i < n && !*(volatile u32*)s_overflow) {
                 if (kcur[j] == HC_EMPTY) atomicAdd(s_empty, 1u);
-                else hc2_pass1(kcur[j], bm, tkeys, claimed, s_distinct, s_overflow);
+                else if ((u64)hc2_pass1(kcur[j], bm, tkeys, tcnt, claimed, s_distinct, s_overflow) + 1 >= c) *s_need = 1;
             }
         }
         BLOCK_SYNC();
         const bool ovf = big || *s_overflow != 0;
         const u32 nd = min(*s_distinct, (u32)HC2_CLAIM_CAP);
         const u32 n_empty = *s_empty;
-        // pass 2: count the keys that have a slot
+        const bool need2 = !ovf && nd && *s_need;
+        // exact counts are needed only if some key may reach min_count: clear the flagged-occurrence counters ...
+        if (need2)
+            for (u32 i = threadIdx.x; i < nd; i += HC2_THREADS) tcnt[claimed[i]] = 0;
+        if (need2) BLOCK_SYNC();                               // (uniform condition)
+        // ... and pass 2 counts every occurrence of the keys that have a slot
         u32 hits = 0;
-        if (!ovf && nd) {
+        if (need2) {
 #pragma unroll
             for (int j = 0; j < HC2_PREFETCH; ++j) {
                 const u32 i = j * HC2_THREADS + threadIdx.x;
@@ -486,12 +495,13 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
                 cnt = tcnt[p];
                 tkeys[p] = HC_EMPTY;
                 tcnt[p] = 0;
-                if (dbg) { atomicAdd(&dbg[1], (ull)cnt); atomicAdd(&dbg[2], 1ull); if (key == HC_EMPTY) atomicAdd(&dbg[3], 1ull); }
+                if (dbg && need2) { atomicAdd(&dbg[1], (ull)cnt); atomicAdd(&dbg[2], 1ull); if (key == HC_EMPTY) atomicAdd(&dbg[3], 1ull); }
             } else if (i == nd && n_empty) {
                 key = HC_EMPTY;
                 cnt = n_empty;
             }
-            const bool keep = !ovf && cnt >= c && cnt > 0;
+            // (without pass 2 the counters hold flagged occurrences < min_count - 1: nothing survives, only clean-up)
+            const bool keep = !ovf && (need2 || i >= nd) && cnt >= c && cnt > 0;
             __syncwarp();
             const u32 m = __ballot_sync(0xffffffffu, keep);
             if (m) {

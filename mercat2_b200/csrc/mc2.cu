@@ -545,8 +545,9 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
             CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
             CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            const int carve1 = (e->opt_scatter_variant & 4) ? 85 : carve;
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
             CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             attr_variant = e->opt_scatter_variant;
@@ -811,15 +812,23 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     DBuf<u64> toff(e, ntiles);
     DBuf<FnStats> st(e, 1);
     st.zero();
-    LAUNCH(e, fn_parse_kernel<false>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
-           (u32*)nullptr, (u32*)nullptr, st.p);
+    const bool plan_known = s->plan.path != PATH_UNSET;
+    if (plan_known)
+        LAUNCH(e, fn_parse_kernel<2>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
+               (u32*)nullptr, (u32*)nullptr, st.p);
+    else
+        LAUNCH(e, fn_parse_kernel<0>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
+               (u32*)nullptr, (u32*)nullptr, st.p);
     dev_exclusive_scan<u32, u64>(e, tcnt.p, toff.p, ntiles, &st.p->n_sym);
     const FnStats fs = read_scalar<FnStats>(e, st.p);
     if (getenv("MC2_DEBUG_FAST"))
         fprintf(stderr, "[fast_nt] len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)len, fs.n_sym,
                 fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
     if (fs.complex) return false;
-    const u64 n_kept = fs.packed & 0xFFFFFFFFull, n_acgt = n_kept - (fs.packed >> 32);
+    // kept / ACGT counts: exact from the statistics pass (first piece); for later pieces "kept" is a bound from the
+    // symbol count and the non-ACGT count arrives with the write pass
+    const u64 n_kept = plan_known ? fs.n_sym : (fs.packed & 0xFFFFFFFFull);
+    const u64 n_acgt = plan_known ? fs.n_sym : n_kept - (fs.packed >> 32);
     if (s->plan.path == PATH_UNSET) {
         if (n_kept == 0) return true;                                     // headers only: nothing to count, plan stays open
         if (n_acgt * 10 < n_kept * 9) return false;                       // not nucleotide-like: let the general path decide
@@ -842,11 +851,12 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     DBuf<u32> codes(e, div_up(nsym, 16) + 4), bad(e, div_up(nsym, 32) + 4);
     codes.zero();
     bad.zero();
-    LAUNCH(e, fn_parse_kernel<true>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)toff.p, codes.p,
+    LAUNCH(e, fn_parse_kernel<1>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)toff.p, codes.p,
            bad.p, st.p);
     PackedView pv{codes.p, bad.p, nsym};
-    sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
-    *need_exceptions = n_kept > n_acgt;
+    sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);          // (synchronises: the statistics below are final)
+    const FnStats fs2 = read_scalar<FnStats>(e, st.p);
+    *need_exceptions = (fs2.packed2 >> 32) != 0;
     return true;
 }
 

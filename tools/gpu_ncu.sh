@@ -9,7 +9,7 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$NAMES" -c 3000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KERNEL -s $SKIP -c 3 -f -o gpurun_out/prof_$KERNEL $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:$KERNEL -s $SKIP -c ${MC2_NCU_COUNT:-3} -f -o gpurun_out/prof_$KERNEL $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
 tail -3 gpurun_out/plain.log
 ls -la gpurun_out/
