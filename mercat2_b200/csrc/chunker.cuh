@@ -128,3 +128,99 @@ __global__ void chunk_select_kernel(const u64* __restrict__ cand_ls, const u64* 
     }
     *nbounds = nb;
 }
+
+// ---- fast path for text without '\r' ---------------------------------------------------------------------------
+// Without "\r\n" pairs the translated offset of the reference (text-mode read) equals the raw offset, so the
+// boundary after b is simply the first line that starts at or after b + chunk_bytes and contains '>'.  One kernel
+// checks that no '\r' exists; one CTA then walks the whole boundary chain with block-parallel searches (a few
+// hundred bytes per boundary for read files) instead of classifying every byte of the text twice.
+__global__ void __launch_bounds__(256) chunk_has_cr_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ flag) {
+    const u64 mis = (16 - ((u64)(uintptr_t)text & 15ull)) & 15ull;          // bytes before the first aligned 16
+    bool hit = false;
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x, gsz = (u64)gridDim.x * blockDim.x;
+    if (gid < mis && gid < n) hit |= text[gid] == 13u;
+    const u64 nvec = n > mis ? (n - mis) / 16 : 0;
+    const uint4* v = reinterpret_cast<const uint4*>(text + mis);
+    for (u64 i = gid; i < nvec; i += gsz) {
+        const uint4 q = v[i];
+        hit |= (ch_eq(q.x, 0x0D0D0D0Du) | ch_eq(q.y, 0x0D0D0D0Du) | ch_eq(q.z, 0x0D0D0D0Du) | ch_eq(q.w, 0x0D0D0D0Du)) != 0;
+    }
+    const u64 tail = mis + nvec * 16;
+    if (tail + gid < n) hit |= text[tail + gid] == 13u;                      // fewer than 16 tail bytes
+    if (hit) atomicOr(flag, 1u);
+}
+
+#define CH_NONE 0xFFFFFFFFFFFFFFFFull
+// first position in [start, n) whose byte satisfies MODE (0: terminator, 1: '>'); all threads call
+template <int MODE>
+__device__ __forceinline__ u64 ch_find_first(const u8* __restrict__ text, u64 start, u64 n, ull* s_pos) {
+    for (u64 base = start; base < n; base += 256 * 8) {
+        if (threadIdx.x == 0) *s_pos = CH_NONE;
+        BLOCK_SYNC();
+        const u64 a = base + (u64)threadIdx.x * 8;
+        u64 found = CH_NONE;
+        for (int j = 7; j >= 0; --j) {
+            const u64 p = a + j;
+            if (p < n) {
+                const u32 c = text[p];
+                if (MODE == 0 ? ch_is_nl(c) : c == '>') found = p;
+            }
+        }
+        if (found != CH_NONE) atomicMin(s_pos, (ull)found);
+        BLOCK_SYNC();
+        const u64 r = *s_pos;
+        BLOCK_SYNC();
+        if (r != CH_NONE) return r;
+    }
+    return CH_NONE;
+}
+// last terminator in [lo, hi), CH_NONE if there is none; all threads call
+__device__ __forceinline__ u64 ch_find_last_nl(const u8* __restrict__ text, u64 lo, u64 hi, ull* s_pos) {
+    u64 top = hi;
+    while (top > lo) {
+        const u64 base = top - lo >= 256 * 8 ? top - 256 * 8 : lo;
+        if (threadIdx.x == 0) *s_pos = 0;
+        BLOCK_SYNC();
+        const u64 a = base + (u64)threadIdx.x * 8;
+        u64 found = 0;                                   // position + 1, 0 = none
+        for (int j = 0; j < 8; ++j) {
+            const u64 p = a + j;
+            if (p < top && ch_is_nl(text[p])) found = p + 1;
+        }
+        if (found) atomicMax(s_pos, (ull)found);
+        BLOCK_SYNC();
+        const u64 r = *s_pos;
+        BLOCK_SYNC();
+        if (r) return r - 1;
+        top = base;
+    }
+    return CH_NONE;
+}
+
+__global__ void __launch_bounds__(256)
+chunk_chain_kernel(const u8* __restrict__ text, u64 n, u64 chunk_bytes, const u32* __restrict__ has_cr, u64* __restrict__ bounds,
+                   u64 max_bounds, ull* __restrict__ nbounds) {
+    __shared__ ull s_pos;
+    if (*has_cr) { if (threadIdx.x == 0) *nbounds = CH_NONE; return; }      // "\r" present: use the exact kernels
+    u64 nb = 1, b = 0;
+    if (threadIdx.x == 0) bounds[0] = 0;
+    while (true) {
+        const u64 p = b + chunk_bytes;
+        if (p >= n) break;
+        u64 ls = p;
+        if (!ch_is_nl(text[p - 1])) {                                       // p is inside a line: go to the next line
+            const u64 q = ch_find_first<0>(text, p, n, &s_pos);
+            if (q == CH_NONE) break;
+            ls = q + 1;
+        }
+        if (ls >= n) break;
+        const u64 g = ch_find_first<1>(text, ls, n, &s_pos);                 // first '>' in an eligible line
+        if (g == CH_NONE) break;
+        const u64 r = ch_find_last_nl(text, ls, g, &s_pos);                  // start of the line that holds it
+        const u64 bs = r == CH_NONE ? ls : r + 1;
+        if (threadIdx.x == 0 && nb < max_bounds) bounds[nb] = bs;
+        nb++;
+        b = bs;
+    }
+    if (threadIdx.x == 0) *nbounds = nb;
+}

@@ -185,12 +185,15 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
         }
         if (m.cx) atomicAdd(&stats->complex, 1ull);
     } else {
-        {   // kept bytes outside ACGT (their windows go to the wide path): known only now in the light flow
-            const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
-            u32 t_kept, t_slow;
-            block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
-            block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
-            if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed2, (ull)t_kept | ((ull)t_slow << 32));
+        {   // kept bytes outside ACGT (their windows go to the wide path): rare, so only warps that see one report
+            const u32 slow = __popc(e.keep & ~m.acgt);
+            __syncwarp();
+            if (__ballot_sync(0xffffffffu, slow != 0)) {
+                u32 t = slow;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&stats->packed2, (ull)t << 32);
+            }
         }
         if (total == 0) return;
         const u64 s_tile = tile_off[blockIdx.x];            // global symbol index of the tile's first symbol

@@ -533,3 +533,155 @@ __global__ void hc_verify_kernel(const u64* __restrict__ keys, const u32* __rest
     const u32 lo_b = (b / step) * step, hi_b = min(nb, lo_b + step);
     if (i < sub_base[lo_b] || i >= sub_base[hi_b]) atomicAdd(bad_count, 1ull);
 }
+
+// ---- hc_count3: 16-bit counter pre-filter, no returning atomics on the common path (min_count >= 2) --------------
+// Measured: shared-memory atomics that RETURN a value (test-and-set on the bitmap of hc_count2, rank counters) run
+// at ~1-2 cycles per lane, ~10x slower than reductions without return (~5 per clock and SM).  Here every key first
+// adds 1 to a 16-bit hashed counter with RED (no return); after a barrier it reads the counter back with a plain
+// load.  A key occurring m >= 2 times reads >= m >= 2 at EVERY occurrence, so all its occurrences enter the exact
+// table and the table count is exact without a second pass; a key occurring once enters only on a counter collision
+// (~5 %) and is dropped by the threshold.  Counters cannot wrap: a bucket holds at most 4096 keys.
+#define HC3_THREADS 1024
+#define HC3_PREFETCH 4
+#define HC3_CNT_LOG2 16                                   // 2^16 counters of 16 bits = 128 KB
+#define HC3_CNT_WORDS (1u << (HC3_CNT_LOG2 - 1))
+#define HC3_SLOTS 4096u
+#define HC3_LIMIT 3072u
+#define HC3_CLAIM_CAP (HC3_LIMIT + HC3_THREADS)
+#define HC3_SMEM ((size_t)HC3_CNT_WORDS * 4 + (size_t)HC3_SLOTS * 12 + (size_t)HC3_CLAIM_CAP * 2)
+
+__device__ __forceinline__ void smem_red_add(u32* addr, u32 v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"((u32)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(HC3_THREADS, 1)
+hc_count3_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
+                 u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* cnt16 = reinterpret_cast<u32*>(dyn);                                                  // HC3_CNT_WORDS
+    ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC3_CNT_WORDS * 4);                       // HC3_SLOTS
+    u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC3_CNT_WORDS * 4 + (size_t)HC3_SLOTS * 8);
+    u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC3_CNT_WORDS * 4 + (size_t)HC3_SLOTS * 12);
+    __shared__ u32 s_scal[2][4];                              // per parity: all-ones-key count, distinct, overflow
+    for (u32 i = threadIdx.x; i < HC3_SLOTS; i += HC3_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
+    for (u32 i = threadIdx.x; i < HC3_CNT_WORDS; i += HC3_THREADS) cnt16[i] = 0;
+    if (threadIdx.x < 8) (&s_scal[0][0])[threadIdx.x] = 0;
+    const int lane = threadIdx.x & 31;
+    ull knext[HC3_PREFETCH];
+    u32 b = blockIdx.x;
+    u32 n_n = 0;
+    if (b < nb) {
+        const u32 lo_n = sub_base[b];
+        n_n = sub_base[b + 1] - lo_n;
+#pragma unroll
+        for (int j = 0; j < HC3_PREFETCH; ++j) {
+            const u32 i = j * HC3_THREADS + threadIdx.x;
+            knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+        }
+    }
+    BLOCK_SYNC();
+    u32 par = 0;
+    for (; b < nb; b += gridDim.x, par ^= 1u) {
+        u32* s_empty = &s_scal[par][0];
+        u32* s_distinct = &s_scal[par][1];
+        u32* s_overflow = &s_scal[par][2];
+        const u32 n = n_n;
+        const bool big = n > HC3_PREFETCH * HC3_THREADS;      // handed to the sort fallback (see hc_count2_kernel)
+        ull kcur[HC3_PREFETCH];
+#pragma unroll
+        for (int j = 0; j < HC3_PREFETCH; ++j) kcur[j] = knext[j];
+        const u32 bn = b + gridDim.x;
+        if (bn < nb) {
+            const u32 lo_n = sub_base[bn];
+            n_n = sub_base[bn + 1] - lo_n;
+#pragma unroll
+            for (int j = 0; j < HC3_PREFETCH; ++j) {
+                const u32 i = j * HC3_THREADS + threadIdx.x;
+                knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+            }
+        }
+        // pass A: hashed 16-bit counters += 1 (reduction, nothing returned)
+        u32 hh[HC3_PREFETCH];
+        u32 live = 0;                                         // bit j: kcur[j] is a key of this bucket
+#pragma unroll
+        for (int j = 0; j < HC3_PREFETCH; ++j) {
+            const u32 i = j * HC3_THREADS + threadIdx.x;
+            hh[j] = 0;
+            if (!big && i < n) {
+                if (kcur[j] == HC_EMPTY) atomicAdd(s_empty, 1u);
+                else {
+                    const u64 prod = kcur[j] * 0xD6E8FEB86659FD93ull;
+                    hh[j] = (u32)(prod >> 32);                  // top 16 bits: counter, bits 4..15: table slot
+                    live |= 1u << j;
+                    const u32 h = hh[j] >> 16;
+                    smem_red_add(&cnt16[h >> 1], 1u << (16 * (h & 1)));
+                }
+            }
+        }
+        BLOCK_SYNC();
+        // pass B: keys whose counter reached 2 are counted exactly in the table
+#pragma unroll
+        for (int j = 0; j < HC3_PREFETCH; ++j) {
+            if (!((live >> j) & 1u)) continue;
+            const u32 h = hh[j] >> 16;
+            const u32 seen = (cnt16[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
+            if (seen >= 2 && !*(volatile u32*)s_overflow) {
+                const ull key = kcur[j];
+                u32 p = (hh[j] >> 4) & (HC3_SLOTS - 1);
+                while (true) {
+                    ull cur = tkeys[p];
+                    if (cur == HC_EMPTY) {
+                        cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+                        if (cur == HC_EMPTY) {
+                            const u32 d = smem_atom_inc(s_distinct);
+                            if (d < HC3_CLAIM_CAP) claimed[d] = (u16)p;
+                            if (d >= HC3_LIMIT) *s_overflow = 1;
+                            cur = key;
+                        }
+                    }
+                    if (cur == key) { smem_red_inc(&tcnt[p]); break; }
+                    p = (p + 1) & (HC3_SLOTS - 1);
+                }
+            }
+        }
+        BLOCK_SYNC();
+        const bool ovf = big || *s_overflow != 0;
+        const u32 nd = min(*s_distinct, (u32)HC3_CLAIM_CAP);
+        const u32 n_empty = big ? 0u : *s_empty;
+        if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
+        for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC3_THREADS) {
+            const u32 i = i0 + threadIdx.x;
+            ull key = 0;
+            u32 cnt = 0;
+            if (i < nd) {
+                const u32 p = claimed[i];
+                key = tkeys[p];
+                cnt = tcnt[p];
+                tkeys[p] = HC_EMPTY;
+                tcnt[p] = 0;
+            } else if (i == nd && n_empty) {
+                key = HC_EMPTY;
+                cnt = n_empty;
+            }
+            const bool keep = !ovf && cnt >= c && cnt > 0;
+            __syncwarp();
+            const u32 m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                ull base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(out_n, (ull)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (keep) {
+                    const u64 o = base + __popc(m & ((1u << lane) - 1u));
+                    if (o < out_cap) { out_keys[o] = key; out_cnt[o] = cnt; }
+                }
+            }
+        }
+        // undo the counters this thread touched; reset the other parity's scalars for the next bucket
+#pragma unroll
+        for (int j = 0; j < HC3_PREFETCH; ++j)
+            if ((live >> j) & 1u) cnt16[hh[j] >> 17] = 0;
+        if (threadIdx.x < 4) s_scal[par ^ 1u][threadIdx.x] = 0;
+        BLOCK_SYNC();
+    }
+}

@@ -36,6 +36,7 @@ struct mc2_engine {
     int opt_force_path = 0;
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
+    int opt_count_variant = 2;             // min_count >= 2: 2 = bitmap pre-filter (faster as measured), 3 = 16-bit counter pre-filter
     int opt_scatter_variant = 0;           // bit0: stage destination indices, bit1: max shared-memory carveout
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
@@ -597,7 +598,15 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     part.keys.alloc(e, out_cap);
     part.counts.alloc(e, out_cap);
     unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
-    if (s->c >= 2) {
+    if (s->c >= 2 && e->opt_count_variant == 3) {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(hc_count3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC3_SMEM));
+            attr_set = true;
+        }
+        LAUNCH(e, hc_count3_kernel, cgrid, HC3_THREADS, HC3_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
+               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
+    } else if (s->c >= 2) {
         cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
         static thread_local bool attr_set = false;
         if (!attr_set) {
@@ -940,6 +949,22 @@ static const u8* to_device(mc2_engine* e, const void* text, u64 nbytes, int spac
 static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 chunk_bytes) {
     std::vector<u64> bounds(1, 0);
     if (chunk_bytes == 0 || n == 0) return bounds;
+    {   // fast path: no '\r' anywhere -> raw offsets are the reference's translated offsets
+        const u64 max_bounds = n / chunk_bytes + 2;
+        DBuf<u64> db(e, max_bounds);
+        DBuf<ull> nbd(e, 1);
+        DBuf<u32> flag(e, 1);
+        flag.zero();
+        LAUNCH(e, chunk_has_cr_kernel, (unsigned)std::min<u64>(div_up(n, 256 * 16 * 4), (u64)e->num_sms * 8), 256, 0, dtext, n, flag.p);
+        LAUNCH(e, chunk_chain_kernel, 1, 256, 0, dtext, n, chunk_bytes, (const u32*)flag.p, db.p, max_bounds, nbd.p);
+        const u64 nbounds = (u64)read_scalar<ull>(e, nbd.p);
+        if (nbounds != ~0ull) {
+            if (nbounds > max_bounds) throw Mc2Error(MC2_ERR_LIMIT, "chunker: boundary buffer overflow");
+            bounds.resize(nbounds);
+            d2h(e, bounds.data(), db.p, nbounds);
+            return bounds;
+        }
+    }
     const u64 ntiles = div_up(n + ((u64)(uintptr_t)dtext & 15ull), CH_TILE);
     DBuf<u32> tcr(e, ntiles), tca(e, ntiles);
     DBuf<u64> ocr(e, ntiles), oca(e, ntiles);
@@ -1228,6 +1253,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
+    else if (n == "count_variant") e->opt_count_variant = (int)value;
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);
