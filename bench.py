@@ -28,6 +28,7 @@ import tempfile
 import threading
 import time
 from pathlib import Path
+from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -323,6 +324,13 @@ def main():
         w_total = bases_per_step * (READ_LEN - args.k + 1) / READ_LEN
         pipeline_alg = nbytes + 16.0 * w_total + 12.0 * rows
         pipeline_gbs = pipeline_alg * args.steps / (dev_us * 1e-6) / 1e9 if dev_us else None
+        traffic, traffic_src = None, None
+        try:                                        # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+            tj = json.loads((Path(__file__).parent / "profiles" / "traffic.json").read_text())
+            if top[0] in tj["kernels"] and n_chunks >= 2:
+                traffic, traffic_src = tj["kernels"][top[0]]["dram_bytes_per_launch"], tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         out = {
             "metric": "input bases/sec (k-mers counted/sec) per GPU and 8xB200; % of HBM roofline",
             "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,7 +344,8 @@ def main():
             "gpu_launches": launches,
             "device_ms_per_step": dev_us / args.steps / 1e3,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel_share_of_step": top[1]["us"] / tot_us,
                          "algorithmic_bytes_per_launch": alg, "avg_launch_us": avg_us,
                          "pipeline_bytes_per_base": pipeline_alg / bases_per_step,

@@ -118,10 +118,12 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 // cnt / loff / gbase: nd words each; stage / sdst: one slot per key of the tile.  Every thread calls; bit i of
 // `valid` says mine[i] holds a key.  cursors[d] is advanced atomically by the tile's count for digit d.  Keys are
 // re-ordered through shared memory so that consecutive threads store consecutive addresses of one digit's run.
-template <bool USE_DST, class KeyFn, class DigitFn>
-__device__ __forceinline__ void hc_group_and_write(KeyFn mine, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
-                                                   u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
-                                                   u64* __restrict__ out) {
+// `mine` yields key i in the ranking phase, `again` in the staging phase: the same registers, or a re-load that
+// lets the keys die in between (fewer live registers, more resident CTAs).
+template <bool USE_DST, class KeyFn, class KeyFn2, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
+                                                    u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
+                                                    u64* __restrict__ out) {
     u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rk[j] = 0; dg[j] = 0; }
@@ -155,7 +157,7 @@ __device__ __forceinline__ void hc_group_and_write(KeyFn mine, u32 valid, u32 nd
             const u32 d = (dg[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
             const u32 r = (rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
             const u32 pos = loff[d] + r;
-            stage[pos] = mine(i);
+            stage[pos] = again(i);
             if (USE_DST) sdst[pos] = gbase[d] + r;
             else reinterpret_cast<u16*>(sdst)[pos] = (u16)d;
         }
@@ -168,6 +170,13 @@ __device__ __forceinline__ void hc_group_and_write(KeyFn mine, u32 valid, u32 nd
             out[gbase[d] + (i - loff[d])] = stage[i];
         }
     }
+}
+
+template <bool USE_DST, class KeyFn, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write(KeyFn mine, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
+                                                   u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
+                                                   u64* __restrict__ out) {
+    hc_group_and_write2<USE_DST>(mine, mine, valid, nd, dig, stage, sdst, cnt, loff, gbase, sm, cursors, out);
 }
 
 // ---- hc_scatter1: symbols -> level-1 groups ----------------------------------------------------------------
@@ -199,8 +208,8 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------
-template <bool USE_DST>
-__global__ void __launch_bounds__(EX_THREADS)
+template <bool USE_DST, bool RELOAD>
+__global__ void __launch_bounds__(EX_THREADS, RELOAD ? 5 : 3)
 hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
                    u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
@@ -230,7 +239,18 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
-    hc_group_and_write<USE_DST>([&](int i) { return mine[i]; }, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    if (RELOAD) {
+        // the staging phase reads the keys again (an L2 hit: the tile was read a few microseconds ago) instead of
+        // carrying 32 registers across two barriers
+        auto again = [&](int j) {
+            u64 x;
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x) : "l"(keys1 + base + j * EX_THREADS + threadIdx.x));
+            return x;
+        };
+        hc_group_and_write2<USE_DST>([&](int i) { return mine[i]; }, again, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    } else {
+        hc_group_and_write<USE_DST>([&](int i) { return mine[i]; }, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+    }
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------

@@ -15,6 +15,50 @@ __global__ void k_smem_add(u32* out, int iters, u32 bins) {
     __syncthreads();
     if (threadIdx.x == 0) out[blockIdx.x] = h[0];
 }
+__global__ void k_smem_add_ret(u32* out, int iters, u32 bins) {
+    extern __shared__ u32 h[];
+    for (u32 i = threadIdx.x; i < bins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    u64 s = mix(blockIdx.x * 1024 + threadIdx.x + 1);
+    u32 acc = 0;
+    for (int i = 0; i < iters; ++i) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; acc += atomicAdd(&h[(u32)(s >> 40) & (bins - 1)], 1u); }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = h[0] + acc;
+    if (acc == 0xFFFFFFFF) out[1] = acc;
+}
+__global__ void k_smem_or_ret(u32* out, int iters, u32 words) {
+    extern __shared__ u32 h[];
+    for (u32 i = threadIdx.x; i < words; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    u64 s = mix(blockIdx.x * 1024 + threadIdx.x + 1);
+    u32 acc = 0;
+    for (int i = 0; i < iters; ++i) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; acc += atomicOr(&h[(u32)(s >> 40) & (words - 1)], 1u << ((u32)(s >> 35) & 31)) & 1; }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = h[0] + acc;
+}
+__global__ void k_smem_add_noret_pow2(u32* out, int iters, u32 bins) {
+    extern __shared__ u32 h[];
+    for (u32 i = threadIdx.x; i < bins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    u64 s = mix(blockIdx.x * 1024 + threadIdx.x + 1);
+    for (int i = 0; i < iters; ++i) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; atomicAdd(&h[(u32)(s >> 40) & (bins - 1)], 1u); }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = h[0];
+}
+__global__ void k_ballot_split(u32* out, int iters) {       // 7-bit multisplit rank by ballots
+    u64 s = mix((u64)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    u32 acc = 0;
+    const u32 lt = (1u << (threadIdx.x & 31)) - 1u;
+    for (int i = 0; i < iters; ++i) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        const u32 d = (u32)(s >> 57);
+        u32 peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 7; ++b) { const u32 m = __ballot_sync(0xffffffffu, (d >> b) & 1u); peers &= ((d >> b) & 1u) ? m : ~m; }
+        acc += __popc(peers & lt);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 __global__ void k_smem_cas(u32* out, int iters, u32 slots /*pow2*/) {
     extern __shared__ ull t[];
     u32* cnt = (u32*)(t + slots);
@@ -102,6 +146,19 @@ int main() {
         if (bins * 4 > 48 * 1024) cudaFuncSetAttribute(k_smem_add, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         float ms = timeit([&] { k_smem_add<<<grid, threads, bins * 4>>>(out, iters, bins); });
         printf("smem atomicAdd bins=%u threads=%d grid=%d: %.1f Gop/s\n", bins, threads, grid, (double)grid * threads * iters / ms / 1e6);
+    }
+    for (u32 bins : {128u, 4096u, 16384u}) for (int threads : {256, 1024}) {
+        int grid = sms * (threads == 256 ? 4 : 1);
+        float ms = timeit([&] { k_smem_add_ret<<<grid, threads, bins * 4>>>(out, iters, bins); });
+        float ms2 = timeit([&] { k_smem_add_noret_pow2<<<grid, threads, bins * 4>>>(out, iters, bins); });
+        float ms3 = timeit([&] { k_smem_or_ret<<<grid, threads, bins * 4>>>(out, iters, bins); });
+        printf("smem atomics bins=%u threads=%d: add+return %.1f Gop/s, add no return %.1f Gop/s, or+return %.1f Gop/s\n", bins, threads,
+               (double)grid * threads * iters / ms / 1e6, (double)grid * threads * iters / ms2 / 1e6, (double)grid * threads * iters / ms3 / 1e6);
+    }
+    {
+        int grid = sms * 8, threads = 256;
+        float ms = timeit([&] { k_ballot_split<<<grid, threads>>>(out, 1000); });
+        printf("7-ballot multisplit rank: %.1f G lane-ops/s\n", (double)grid * threads * 1000 / ms / 1e6);
     }
     CK(cudaGetLastError());
     for (u32 slots : {4096u, 16384u}) for (int threads : {256, 1024}) {
