@@ -28,7 +28,6 @@ import tempfile
 import threading
 import time
 from pathlib import Path
-from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
