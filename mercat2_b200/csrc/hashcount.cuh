@@ -381,29 +381,34 @@ hc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
 #define HC2_BM_WORDS 8192u                       // 2^18 bits
 #define HC2_BM_BITS_LOG2 18
 #define HC2_PREFETCH 8
-#define HC2_SMEM ((size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12 + (size_t)HC2_CLAIM_CAP * 2)
+#define HC2_FLIST 1024u                          // flagged keys queued per bucket before the dense insert step
+#define HC2_SMEM ((size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12 + (size_t)HC2_CLAIM_CAP * 2 + (size_t)HC2_FLIST * 8)
 
-__device__ __forceinline__ u32 hc2_slot(u64 prod) { return (u32)(prod >> 20) & (HC2_SLOTS - 1); }
+// One 32-bit multiply-add hash per key: its top 18 bits address the bitmap; the table slot comes from a second
+// multiply that only the (rare) repeat path pays for.  (The bucket index used the high bits of a different, 64-bit
+// product, so these bits are independent of the bucket the key sits in.)
+__device__ __forceinline__ u32 hc2_hash(ull key) { return (u32)key * 0x9E3779B1u + (u32)(key >> 32) * 0x85EBCA77u; }
+__device__ __forceinline__ u32 hc2_slot(u32 h) { return (h * 0xC2B2AE3Du) >> (32 - 12); }
+static_assert(HC2_SLOTS == 4096u, "hc2_slot yields 12 bits");
+static_assert((HC2_CLAIM_CAP * 2) % 8 == 0, "the flagged-key queue follows the claim log and holds 8-byte keys");
 
-// Pass 1.  Returns the number of times this key has now been seen with its bitmap bit already set (0 if the bit
-// was clear).  The true multiplicity of a key is that number or that number + 1 (its very first occurrence set
-// the bit itself unless another key's bit collided), so a bucket in which no key reaches min_count - 1 flagged
-// occurrences has no survivor and needs no exact second pass.
-__device__ __forceinline__ u32 hc2_pass1(ull key, u32* bm, ull* tkeys, u32* tcnt, u16* claimed, u32* s_distinct, u32* s_overflow) {
-    const u64 prod = key * 0xD6E8FEB86659FD93ull;
-    const u32 bi = (u32)(prod >> (64 - HC2_BM_BITS_LOG2));
-    const u32 bit = 1u << (bi & 31);
-    const u32 old = atomicOr(&bm[bi >> 5], bit);
-    if (!(old & bit)) return 0u;
-    u32 p = hc2_slot(prod);                                  // repeat (or false positive): give the key a slot
+// Pass 1, repeat path: the key found its bitmap bit already set (a repeat, or a ~1 % false positive) and is given a
+// table slot.  Returns the number of times this key has now been seen with its bit set.  The true multiplicity of
+// a key is that number or that number + 1 (its very first occurrence set the bit itself unless another key's bit
+// collided), so a bucket in which no key reaches min_count - 1 flagged occurrences has no survivor and needs no
+// exact second pass.  The all-ones key (T^32) doubles as the empty-slot marker and is counted aside.
+__device__ __noinline__ u32 hc2_flagged(ull key, u32 h, ull* tkeys, u32* tcnt, u16* claimed, u32* scal) {
+    if (*(volatile u32*)&scal[2]) return 0u;                 // table already overflowed: the bucket is redone by sorting
+    if (key == HC_EMPTY) return smem_atom_inc(&scal[0]) + 1u;
+    u32 p = hc2_slot(h);
     while (true) {
         ull cur = tkeys[p];
         if (cur == HC_EMPTY) {
             cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
             if (cur == HC_EMPTY) {
-                const u32 d = smem_atom_inc(s_distinct);
+                const u32 d = smem_atom_inc(&scal[1]);
                 if (d < HC2_CLAIM_CAP) claimed[d] = (u16)p;
-                if (d >= HC2_LIMIT) *s_overflow = 1;
+                if (d >= HC2_LIMIT) scal[2] = 1;
                 cur = key;
             }
         }
@@ -411,8 +416,22 @@ __device__ __forceinline__ u32 hc2_pass1(ull key, u32* bm, ull* tkeys, u32* tcnt
         p = (p + 1) & (HC2_SLOTS - 1);
     }
 }
-__device__ __forceinline__ u32 hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
-    u32 p = hc2_slot(key * 0xD6E8FEB86659FD93ull);
+// Pass 1a: bitmap test-and-set.  A flagged key is queued (scal[5] = queue length) so that the probe loops run
+// afterwards with one key per lane instead of one or two active lanes per warp; if the queue is full (heavily
+// duplicated data) the key is inserted on the spot.
+__device__ __forceinline__ void hc2_pass1(ull key, u32* bm, ull* tkeys, u32* tcnt, u16* claimed, ull* flist, u32* scal, u32 need_at) {
+    const u32 h = hc2_hash(key);
+    const u32 bit = 1u << ((h >> 14) & 31u);
+    const u32 old = atomicOr(&bm[h >> 19], bit);
+    if (old & bit) {
+        const u32 q = smem_atom_inc(&scal[5]);
+        if (q < HC2_FLIST) flist[q] = key;
+        else if (hc2_flagged(key, h, tkeys, tcnt, claimed, scal) >= need_at) scal[3] = 1;
+    }
+}
+__device__ __forceinline__ u32 hc2_pass2(ull key, const ull* tkeys, u32* tcnt, u32* scal) {
+    if (key == HC_EMPTY) { smem_red_inc(&scal[4]); return 1u; }
+    u32 p = hc2_slot(hc2_hash(key));
     while (true) {
         const ull cur = tkeys[p];
         if (cur == key) { smem_red_inc(&tcnt[p]); return 1u; }
@@ -425,17 +444,20 @@ __device__ __forceinline__ u32 hc2_pass2(ull key, const ull* tkeys, u32* tcnt) {
 __global__ void __launch_bounds__(HC2_THREADS, 2)
 hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u64 c, u64* __restrict__ out_keys,
                  u64* __restrict__ out_cnt, ull* __restrict__ out_n, u64 out_cap, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n,
-                 ull* __restrict__ dbg) {
+                 ull* __restrict__ dbg, u32 exp_flags) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* bm = reinterpret_cast<u32*>(dyn);                                              // HC2_BM_WORDS
     ull* tkeys = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4);                 // HC2_SLOTS
     u32* tcnt = reinterpret_cast<u32*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 8);
     u16* claimed = reinterpret_cast<u16*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12);
-    __shared__ u32 s_scal[2][4];                            // per parity: empty-key count, distinct, overflow, need-pass-2
+    ull* flist = reinterpret_cast<ull*>(dyn + (size_t)HC2_BM_WORDS * 4 + (size_t)HC2_SLOTS * 12 + (size_t)HC2_CLAIM_CAP * 2);
+    // per parity: flagged empty-key occurrences, distinct, overflow, need-pass-2, exact empty-key count, queue length
+    __shared__ u32 s_scal[2][8];
     for (u32 i = threadIdx.x; i < HC2_SLOTS; i += HC2_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
     for (u32 i = threadIdx.x; i < HC2_BM_WORDS; i += HC2_THREADS) bm[i] = 0;
-    if (threadIdx.x < 8) (&s_scal[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x < 16) (&s_scal[0][0])[threadIdx.x] = 0;
     const int lane = threadIdx.x & 31;
+    const u32 need_at = (u32)min(c - 1, (u64)0xFFFFFFFFu);     // flagged occurrences at which a key may reach min_count
     ull knext[HC2_PREFETCH];
     u32 b = blockIdx.x;
     u32 lo_n = 0, n_n = 0;
@@ -451,16 +473,13 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
     BLOCK_SYNC();
     u32 par = 0;
     for (; b < nb; b += gridDim.x, par ^= 1u) {
-        u32* s_empty = &s_scal[par][0];
-        u32* s_distinct = &s_scal[par][1];
-        u32* s_overflow = &s_scal[par][2];
-        u32* s_need = &s_scal[par][3];
+        u32* scal = s_scal[par];
         const u32 n = n_n;
         ull kcur[HC2_PREFETCH];
 #pragma unroll
         for (int j = 0; j < HC2_PREFETCH; ++j) kcur[j] = knext[j];
         const u32 bn = b + gridDim.x;
-        if (bn < nb) {
+        if (bn < nb && !(exp_flags & 1u)) {
             lo_n = sub_base[bn];
             n_n = sub_base[bn + 1] - lo_n;
 #pragma unroll
@@ -474,20 +493,24 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
         // buckets from global memory in both passes; on B200 that variant lost a few counts per million keys in a
         // timing-dependent way that neither warp syncs, block fences nor uniform trip counts removed -- see DESIGN.md.]
         const bool big = n > HC2_PREFETCH * HC2_THREADS;
-        // pass 1: bitmap test-and-set, repeats claim a table slot
+        const u32 n1 = big ? 0u : n;
+        // pass 1: bitmap test-and-set (ten instructions per key); repeats claim a table slot
 #pragma unroll
-        for (int j = 0; j < HC2_PREFETCH; ++j) {
-            const u32 i = j * HC2_THREADS + threadIdx.x;
-            if (!big && i < n && !*(volatile u32*)s_overflow) {
-                if (kcur[j] == HC_EMPTY) atomicAdd(s_empty, 1u);
-                else if ((u64)hc2_pass1(kcur[j], bm, tkeys, tcnt, claimed, s_distinct, s_overflow) + 1 >= c) *s_need = 1;
+        for (int j = 0; j < HC2_PREFETCH; ++j)
+            if (j * HC2_THREADS + threadIdx.x < n1) hc2_pass1(kcur[j], bm, tkeys, tcnt, claimed, flist, scal, need_at);
+        BLOCK_SYNC();
+        // pass 1b: the queued keys claim / bump their table slots, one key per lane
+        {
+            const u32 nq = min(scal[5], HC2_FLIST);
+            for (u32 i = threadIdx.x; i < nq; i += HC2_THREADS) {
+                const ull key = flist[i];
+                if (hc2_flagged(key, hc2_hash(key), tkeys, tcnt, claimed, scal) >= need_at) scal[3] = 1;
             }
         }
         BLOCK_SYNC();
-        const bool ovf = big || *s_overflow != 0;
-        const u32 nd = min(*s_distinct, (u32)HC2_CLAIM_CAP);
-        const u32 n_empty = *s_empty;
-        const bool need2 = !ovf && nd && *s_need;
+        const bool ovf = big || scal[2] != 0;
+        const u32 nd = min(scal[1], (u32)HC2_CLAIM_CAP);
+        const bool need2 = !ovf && scal[3];
         // exact counts are needed only if some key may reach min_count: clear the flagged-occurrence counters ...
         if (need2)
             for (u32 i = threadIdx.x; i < nd; i += HC2_THREADS) tcnt[claimed[i]] = 0;
@@ -498,12 +521,13 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
 #pragma unroll
             for (int j = 0; j < HC2_PREFETCH; ++j) {
                 const u32 i = j * HC2_THREADS + threadIdx.x;
-                if (i < n && kcur[j] != HC_EMPTY) hits += hc2_pass2(kcur[j], tkeys, tcnt);
+                if (i < n) hits += hc2_pass2(kcur[j], tkeys, tcnt, scal);
             }
 
         }
         if (dbg && hits) atomicAdd(&dbg[0], (ull)hits);
         BLOCK_SYNC();
+        const u32 n_empty = need2 ? scal[4] : 0u;
         if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
         for (u32 i0 = 0; i0 < nd + (n_empty ? 1u : 0u); i0 += HC2_THREADS) {
             const u32 i = i0 + threadIdx.x;
@@ -538,7 +562,7 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
         {   // clear the bitmap (16 bytes per store); reset the other parity's scalars for the next bucket
             uint4* bm4 = reinterpret_cast<uint4*>(bm);
             for (u32 i = threadIdx.x; i < HC2_BM_WORDS / 4; i += HC2_THREADS) bm4[i] = make_uint4(0, 0, 0, 0);
-            if (threadIdx.x < 4) s_scal[par ^ 1u][threadIdx.x] = 0;
+            if (threadIdx.x < 8) s_scal[par ^ 1u][threadIdx.x] = 0;
         }
         BLOCK_SYNC();
     }

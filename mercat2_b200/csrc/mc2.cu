@@ -611,7 +611,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     part.keys.alloc(e, out_cap);
     part.counts.alloc(e, out_cap);
     unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
-    if (s->c >= 2 && e->opt_count_variant == 3) {
+    if (s->c >= 2 && (e->opt_count_variant & 15) == 3) {
         static thread_local bool attr_set = false;
         if (!attr_set) {
             CUDA_CHECK(cudaFuncSetAttribute(hc_count3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC3_SMEM));
@@ -619,7 +619,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         }
         LAUNCH(e, hc_count3_kernel, cgrid, HC3_THREADS, HC3_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
                part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
-    } else if (s->c >= 2) {
+    } else if (s->c >= 2) {                                        // (count_variant bits >= 4: timing experiments)
         cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
         static thread_local bool attr_set = false;
         if (!attr_set) {
@@ -628,7 +628,8 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             attr_set = true;
         }
         LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n, (ull*)nullptr);
+               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n, (ull*)nullptr,
+               (u32)(e->opt_count_variant >> 4));
         if (dbg) {                                                // stress: repeat on the same keys, results must not vary
             DBuf<ull> dc(e, 8 + (u64)cgrid * 64);
             DBuf<Tail> t2(e, 1);
@@ -637,7 +638,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
                 dc.zero();
                 t2.zero();
                 LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-                       ok2.p, oc2.p, &t2.p->out_n, out_cap, ovf_list.p, &t2.p->ovf_n, dc.p);
+                       ok2.p, oc2.p, &t2.p->out_n, out_cap, ovf_list.p, &t2.p->ovf_n, dc.p, 0u);
                 ull h[4];
                 d2h(e, h, dc.p, 4);
                 if (cgrid == nb) {                                 // one bucket per CTA: barrier timestamps are meaningful
