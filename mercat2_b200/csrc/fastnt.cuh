@@ -1,8 +1,9 @@
 // K1f + packed extraction -- the nucleotide fast lane.
 //
 // Same semantics as parse.cuh (reference parser lib/mercat2_kmers.py:47-63) restricted to "simple" FASTA
-// text: line ends '\n', '\r\n' or '\r', no other whitespace/control byte, no '*', 7-bit ASCII.  Any
-// other byte raises the `complex` flag and the chunk is redone by the general parser, so results never
+// text: line ends '\n', '\r\n' or '\r', 7-bit ASCII, and outside header lines no other whitespace/control
+// byte and no '*' (header lines may say anything: their bytes are dropped).  Any other
+// byte raises the `complex` flag and the chunk is redone by the general parser, so results never
 // depend on this lane.  What it buys: the byte-granular work is done once, with SWAR on 32-bit words
 // (about 11 ALU ops per text byte instead of ~55), and everything downstream works on 2-bit packed
 // symbols: a k-mer is two funnel shifts instead of a 16-step rolling loop.
@@ -37,19 +38,21 @@ __device__ __forceinline__ u32 fn_movemask(u32 m) { return (((m >> 7) * 0x002040
 struct FnMasks {
     u32 nl, gt, acgt;   // 16-bit masks over the thread's 16 bytes
     u32 codes;          // 2-bit code of every byte (garbage where the byte is not ACGT)
-    u32 cx;             // != 0: a byte outside the simple subset
+    u32 cx;             // 16-bit mask: whitespace/control bytes and '*' (not simple unless inside a header line)
+    u32 hi;             // != 0: a byte >= 0x80 (never simple: the reference decodes text)
 };
 
 template <bool CODES>
 __device__ __forceinline__ FnMasks fn_classify(const u32 w[4]) {
     FnMasks m;
-    m.nl = m.gt = m.acgt = m.codes = m.cx = 0;
+    m.nl = m.gt = m.acgt = m.codes = m.cx = m.hi = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const u32 x = w[q];
         const u32 mnl = fn_eq(x, 0x0A0A0A0Au) | fn_eq(x, 0x0D0D0D0Du);
         const u32 mgt = fn_eq(x, 0x3E3E3E3Eu);
-        m.cx |= (fn_lt21(x) & ~mnl) | fn_eq(x, 0x2A2A2A2Au) | (x & 0x80808080u);
+        m.cx |= fn_movemask((fn_lt21(x) & ~mnl) | fn_eq(x, 0x2A2A2A2Au)) << (4 * q);
+        m.hi |= x & 0x80808080u;
         m.nl |= fn_movemask(mnl) << (4 * q);
         m.gt |= fn_movemask(mgt) << (4 * q);
         if (!CODES) continue;
@@ -78,6 +81,7 @@ struct FnEmit {
     u32 bad;       // symbols that stop a fast window (header start, or kept byte outside ACGT)
     u32 hs;        // header starts
     u32 keep;
+    u32 cx;        // != 0: a byte the simple rules do not cover
 };
 
 __device__ __forceinline__ FnEmit fn_emit_masks(const FnMasks& m, u32 state) {
@@ -91,6 +95,7 @@ __device__ __forceinline__ FnEmit fn_emit_masks(const FnMasks& m, u32 state) {
     e.hs = hs;
     e.emit = e.keep | hs;
     e.bad = hs | (e.keep & ~m.acgt);
+    e.cx = (m.cx & ~hdr) | m.hi;
     return e;
 }
 
@@ -183,7 +188,7 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
             block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
             if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed, (ull)t_kept | ((ull)t_slow << 32));
         }
-        if (m.cx) atomicAdd(&stats->complex, 1ull);
+        if (e.cx) atomicAdd(&stats->complex, 1ull);
     } else {
         {   // kept bytes outside ACGT (their windows go to the wide path): rare, so only warps that see one report
             const u32 slow = __popc(e.keep & ~m.acgt);
@@ -312,6 +317,45 @@ fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
     for (u32 b = threadIdx.x; b < nb; b += FN_HIST_THREADS) {
         const u32 n = hist[b];
         if (n) atomicAdd(&ghist[b], n);
+    }
+}
+
+// ---- dense tables straight from the packed stream (4^k bins, k <= 15) -----------------------------------------
+// Index = the window's code with its first symbol most significant (the layout of the sample table), obtained from
+// the stream-order key by one bit reversal.  SMEM: per-CTA histogram replicated per warp group, flushed once;
+// otherwise reduction atomics on the L2-resident global table.
+__device__ __forceinline__ u32 fn_dense_index(u32 key, int k) {
+    u32 x = __brev(key);                                          // pairs reversed and swapped inside
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    return x >> (32 - 2 * k);
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(FN_HIST_THREADS)
+fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ table) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* hist = reinterpret_cast<u32*>(dyn);                      // [nrep][bins] (SMEM only)
+    if (SMEM) {
+        for (u32 i = threadIdx.x; i < bins * nrep; i += FN_HIST_THREADS) hist[i] = 0;
+        BLOCK_SYNC();
+    }
+    u32* my = SMEM ? hist + (u32)((threadIdx.x >> 5) % nrep) * bins : table;
+    const u64 mask = (1ull << (2 * k)) - 1;
+    const u64 nwords = (pv.n + 15) >> 4;
+    for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
+        u64 keys[16];
+        const u32 valid = fn_windows(pv, g, k, mask, keys);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((valid >> j) & 1u) atomicAdd(&my[fn_dense_index((u32)keys[j], k)], 1u);
+    }
+    if (SMEM) {
+        BLOCK_SYNC();
+        for (u32 b = threadIdx.x; b < bins; b += FN_HIST_THREADS) {
+            u32 sum = 0;
+            for (u32 r = 0; r < nrep; ++r) sum += hist[r * bins + b];
+            if (sum) atomicAdd(&table[b], sum);
+        }
     }
 }
 

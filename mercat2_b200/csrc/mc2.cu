@@ -18,6 +18,7 @@
 #include "hashcount.cuh"
 #include "fastnt.cuh"
 #include "metrics.cuh"
+#include "tsv.cuh"
 
 static thread_local std::string g_err;
 
@@ -823,11 +824,17 @@ static void adopt_symbols(mc2_engine* e, const u8* dsym, u64 len, Parsed& out) {
 // holds non-ACGT symbols whose windows still have to be counted by the wide path.
 static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, bool* need_exceptions) {
     *need_exceptions = false;
-    if (!e->opt_fast_nt || e->opt_sparse_algo == 1 || s->c < 2 || s->k > 32 || len == 0) return false;
-    if (s->plan.path != PATH_UNSET && !(s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE)) return false;
-    if (e->opt_force_enc > 0 || (e->opt_force_path != 0 && e->opt_force_path != PATH_SPARSE)) return false;
-    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
-    if (len >= (1ull << 32) || len > hash_max) return false;
+    if (!e->opt_fast_nt || s->k > 32 || len == 0 || len >= (1ull << 32)) return false;
+    if (e->opt_force_enc > 0 || e->opt_force_path == PATH_WIDE) return false;
+    // which plans the packed lane serves: 2-bit sparse keys through the hash tables (min_count >= 2), and dense 4^k tables
+    auto served = [&](const Plan& pl) {
+        if (pl.enc != ENC_NT2) return false;
+        if (pl.path == PATH_DENSE) return s->k <= 15;
+        if (pl.path != PATH_SPARSE || s->c < 2 || e->opt_sparse_algo == 1) return false;
+        const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
+        return len <= hash_max;
+    };
+    if (s->plan.path != PATH_UNSET && !served(s->plan)) return false;
     const u64 mis = (u64)(uintptr_t)dtext & 15ull;
     const u64 ntiles = div_up(mis + len, FN_TILE);
     DBuf<u8> tstate(e, ntiles);
@@ -867,7 +874,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
             s->dense_chunk.alloc(e, s->plan.bins);
             s->dense_chunk.zero();
         }
-        if (!(s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE)) return false;
+        if (!served(s->plan)) return false;
     }
     if (n_kept == 0) return true;
     const u64 nsym = fs.n_sym;
@@ -877,6 +884,27 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     LAUNCH(e, fn_parse_kernel<1>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)toff.p, codes.p,
            bad.p, st.p);
     PackedView pv{codes.p, bad.p, nsym};
+    if (s->plan.path == PATH_DENSE) {
+        const Plan& plan = s->plan;
+        const u64 nwords = div_up(nsym, 16);
+        if (plan.smem) {
+            const size_t smem = (size_t)plan.bins * plan.nrep * 4;
+            static thread_local bool attr_set = false;
+            if (!attr_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * (smem <= 96 * 1024 ? 2 : 1));
+            LAUNCHN(e, "fn_dense_kernel<smem>", fn_dense_kernel<true>, grid, FN_HIST_THREADS, smem, pv, s->k, plan.bins, plan.nrep, s->dense_chunk.p);
+        } else {
+            const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * 2);
+            LAUNCHN(e, "fn_dense_kernel<global>", fn_dense_kernel<false>, grid, FN_HIST_THREADS, 0, pv, s->k, plan.bins, 1u, s->dense_chunk.p);
+        }
+        LAUNCH(e, dense_fold_kernel, (unsigned)div_up(plan.bins, 256), 256, 0, s->dense_chunk.p, s->dense_sample.p, plan.bins, s->c);
+        const FnStats fsd = read_scalar<FnStats>(e, st.p);
+        *need_exceptions = (fsd.packed2 >> 32) != 0;
+        return true;
+    }
     // the write pass's statistics come back with the hash path's own final readback (one sync fewer per chunk)
     e->ride_dev = st.p;
     e->ride_len = sizeof(FnStats);
@@ -1182,24 +1210,28 @@ static void ensure_host(mc2_table* t) {
     t->on_host = true;
 }
 
-static std::string tsv_of(mc2_table* t, const char* basename) {
-    ensure_host(t);
-    const u64 rows = t->counts.size(), k = t->k;
-    std::string s;
-    s.reserve(32 + strlen(basename) + rows * (k + 12));
-    s += "k-mer\t";
-    s += basename;
-    s += "_Count\n";
-    char num[32];
-    for (u64 r = 0; r < rows; ++r) {
-        s.append(&t->kmers[r * k], k);
-        s += '\t';
-        int len = snprintf(num, sizeof num, "%llu", (ull)t->counts[r]);
-        s.append(num, len);
-        s += '\n';
-    }
-    return s;
+// TSV body (every row, no header line) formatted on the device; returns its size in bytes.
+static u64 tsv_body_device(mc2_table* t, DBuf<u8>& body) {
+    mc2_engine* e = t->e;
+    const u64 nf = t->fast.n, nw = t->wide.n, rows = nf + nw;
+    if (!rows) return 0;
+    if (nf && t->k > 32) throw Mc2Error(MC2_ERR_INVALID, "tsv: packed rows with k > 32 (internal error)");
+    const int kind = t->key_kind == KEY_DENSE_AA ? TSV_DENSE_AA : t->enc == ENC_NT2 ? TSV_NT2 : t->enc == ENC_AA5 ? TSV_AA5 : TSV_BYTE;
+    DBuf<u64> pos(e, rows), off(e, rows);
+    DBuf<u32> len(e, rows);
+    DBuf<ull> total(e, 1);
+    const unsigned grid = (unsigned)div_up(rows, 256);
+    LAUNCH(e, tsv_place_kernel, grid, 256, 0, (const u64*)t->fast.keys.p, (const u64*)t->fast.counts.p, nf, (const u8*)t->wide.rows.p,
+           (const u64*)t->wide.counts.p, nw, t->k, kind, pos.p, len.p);
+    dev_exclusive_scan<u32, u64>(e, len.p, off.p, rows, total.p);
+    const u64 nbytes = (u64)read_scalar<ull>(e, total.p);
+    body.alloc(e, nbytes);
+    LAUNCH(e, tsv_write_kernel, grid, 256, 0, (const u64*)t->fast.keys.p, (const u64*)t->fast.counts.p, nf, (const u8*)t->wide.rows.p,
+           (const u64*)t->wide.counts.p, nw, t->k, kind, (const u64*)pos.p, (const u64*)off.p, body.p);
+    return nbytes;
 }
+
+static std::string tsv_header(const char* basename) { return std::string("k-mer\t") + basename + "_Count\n"; }
 
 // =====================================================================================================
 // C ABI
@@ -1472,26 +1504,37 @@ int mc2_table_tsv(mc2_table* t, const char* basename, char* buf, uint64_t cap, u
     API_BEGIN
     if (!t || !basename) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
     CUDA_CHECK(cudaSetDevice(t->e->device));
-    const std::string s = tsv_of(t, basename);
-    if (size) *size = s.size();
+    const std::string head = tsv_header(basename);
+    DBuf<u8> body;
+    const u64 nbytes = tsv_body_device(t, body);
+    if (size) *size = head.size() + nbytes;
     if (buf) {
-        if (cap < s.size()) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
-        memcpy(buf, s.data(), s.size());
+        if (cap < head.size() + nbytes) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+        memcpy(buf, head.data(), head.size());
+        d2h(t->e, (u8*)buf + head.size(), (const u8*)body.p, nbytes);
     }
     API_END
 }
-
 int mc2_table_write_tsv(mc2_table* t, const char* path, const char* basename) {
     try {
         if (!t || !path || !basename) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
         if (mc2_table_rows(t) == 0) return 1;
         CUDA_CHECK(cudaSetDevice(t->e->device));
-        const std::string s = tsv_of(t, basename);
+        const std::string head = tsv_header(basename);
+        DBuf<u8> body;
+        const u64 nbytes = tsv_body_device(t, body);
         FILE* f = fopen(path, "wb");
         if (!f) throw Mc2Error(MC2_ERR_IO, std::string("cannot open ") + path);
-        const size_t w = fwrite(s.data(), 1, s.size(), f);
-        fclose(f);
-        if (w != s.size()) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
+        bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+        const u64 piece = 64ull << 20;                              // the body streams through a bounded host buffer
+        std::vector<u8> host(std::min(piece, nbytes));
+        for (u64 o = 0; ok && o < nbytes; o += piece) {
+            const u64 m = std::min(piece, nbytes - o);
+            d2h(t->e, host.data(), (const u8*)body.p + o, m);
+            ok = fwrite(host.data(), 1, m, f) == m;
+        }
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
     } catch (const Mc2Error& err) { g_err = err.what(); return err.code; }
     catch (const std::exception& err) { g_err = err.what(); return MC2_ERR_INVALID; }
     return MC2_OK;
