@@ -245,6 +245,10 @@ struct mc2_table {
     int key_kind = KEY_CODE;
     FastPart fast;
     WidePart wide;
+    // formatted TSV body kept between the size query and the copy-out of mc2_table_tsv
+    DBuf<u8> tsv_body;
+    u64 tsv_bytes = 0;
+    bool tsv_ready = false;
     // host side (filled by ensure_host)
     bool on_host = false;
     std::vector<char> kmers;
@@ -1231,6 +1235,31 @@ static u64 tsv_body_device(mc2_table* t, DBuf<u8>& body) {
     return nbytes;
 }
 
+// Device -> host in 32 MiB pieces through the engine's two pinned buffers: while piece j is handed to `sink`
+// (memcpy or fwrite), piece j+1 is already crossing PCIe on the copy stream.
+template <class Sink>
+static void download_pipelined(mc2_engine* e, const u8* dev, u64 nbytes, Sink sink) {
+    if (!nbytes) return;
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));                 // the producer kernels ran on the compute stream
+    const u64 piece = mc2_engine::STAGE_BYTES;
+    const u64 np = div_up(nbytes, piece);
+    auto issue = [&](u64 j) {
+        const u64 o = j * piece, m = std::min(piece, nbytes - o);
+        CUDA_CHECK(cudaMemcpyAsync(e->pin_stage[j & 1], dev + o, m, cudaMemcpyDeviceToHost, e->copy_stream));
+        CUDA_CHECK(cudaEventRecord(e->stage_ev[j & 1], e->copy_stream));
+    };
+    CUDA_CHECK(cudaEventSynchronize(e->stage_ev[0]));
+    CUDA_CHECK(cudaEventSynchronize(e->stage_ev[1]));
+    issue(0);
+    for (u64 j = 0; j < np; ++j) {
+        if (j + 1 < np) issue(j + 1);
+        CUDA_CHECK(cudaEventSynchronize(e->stage_ev[j & 1]));
+        const u64 o = j * piece, m = std::min(piece, nbytes - o);
+        sink(e->pin_stage[j & 1], o, m);
+    }
+    e->d2h_bytes += nbytes;
+}
+
 static std::string tsv_header(const char* basename) { return std::string("k-mer\t") + basename + "_Count\n"; }
 
 // =====================================================================================================
@@ -1505,13 +1534,19 @@ int mc2_table_tsv(mc2_table* t, const char* basename, char* buf, uint64_t cap, u
     if (!t || !basename) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
     CUDA_CHECK(cudaSetDevice(t->e->device));
     const std::string head = tsv_header(basename);
-    DBuf<u8> body;
-    const u64 nbytes = tsv_body_device(t, body);
+    if (!t->tsv_ready) {                                  // (a size query followed by the copy-out formats once)
+        t->tsv_bytes = tsv_body_device(t, t->tsv_body);
+        t->tsv_ready = true;
+    }
+    const u64 nbytes = t->tsv_bytes;
     if (size) *size = head.size() + nbytes;
     if (buf) {
         if (cap < head.size() + nbytes) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
         memcpy(buf, head.data(), head.size());
-        d2h(t->e, (u8*)buf + head.size(), (const u8*)body.p, nbytes);
+        u8* dst = (u8*)buf + head.size();
+        download_pipelined(t->e, (const u8*)t->tsv_body.p, nbytes, [&](const u8* src, u64 o, u64 m) { memcpy(dst + o, src, m); });
+        t->tsv_body.release();
+        t->tsv_ready = false;
     }
     API_END
 }
@@ -1526,13 +1561,7 @@ int mc2_table_write_tsv(mc2_table* t, const char* path, const char* basename) {
         FILE* f = fopen(path, "wb");
         if (!f) throw Mc2Error(MC2_ERR_IO, std::string("cannot open ") + path);
         bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
-        const u64 piece = 64ull << 20;                              // the body streams through a bounded host buffer
-        std::vector<u8> host(std::min(piece, nbytes));
-        for (u64 o = 0; ok && o < nbytes; o += piece) {
-            const u64 m = std::min(piece, nbytes - o);
-            d2h(t->e, host.data(), (const u8*)body.p + o, m);
-            ok = fwrite(host.data(), 1, m, f) == m;
-        }
+        download_pipelined(t->e, (const u8*)body.p, nbytes, [&](const u8* src, u64, u64 m) { ok = ok && fwrite(src, 1, m, f) == m; });
         ok = (fclose(f) == 0) && ok;
         if (!ok) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
     } catch (const Mc2Error& err) { g_err = err.what(); return err.code; }
