@@ -240,8 +240,19 @@ def main():
 
     engine = mercat2_b200.Engine(local)
 
+    def merged(table):
+        """N > 1: the ranks hold pieces of ONE sample -- sum their filtered tables on the devices (key-range
+        all-to-all over NCCL); every rank keeps the rows of its own key range."""
+        if world == 1:
+            return table
+        from mercat2_b200 import distributed as mcd
+        part = mcd.merge_table_device(engine, table, dist, device)
+        table.close()
+        return part
+
     def step_resident():
         table, offsets = engine.count_sample(text, args.k, args.c, chunk_bytes)
+        table = merged(table)
         rows = table.rows
         table.close()
         return rows, len(offsets)
@@ -278,6 +289,7 @@ def main():
 
             def step_e2e():
                 table, _ = engine.count_sample(host, args.k, args.c, chunk_bytes)
+                table = merged(table)
                 kmers, counts = table.arrays()
                 table.close()
                 return kmers.nbytes + counts.nbytes
@@ -337,7 +349,7 @@ def main():
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"cfg4 shard: synthetic 150-bp metagenome reads, nucleotide k={args.k} -c {args.c} -s {args.s}",
                        "reads_per_gpu": n_reads, "bases_per_gpu_per_step": bases_per_step, "text_bytes_per_gpu": nbytes,
-                       "chunks_per_gpu": n_chunks, "surviving_rows": rows, "parallelism": f"chunk-sharded x{world}",
+                       "chunks_per_gpu": n_chunks, "surviving_rows": rows, "parallelism": f"chunk-sharded x{world}" + (" + NCCL key-range all-to-all of the filtered tables" if world > 1 else ""),
                        "l2_policy": "input per step (>= 1 GB) is larger than L2; no flush needed"},
             "clocks": clocks,
             "gpu_launches": launches,

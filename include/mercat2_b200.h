@@ -112,6 +112,37 @@ int mc2_table_write_tsv(mc2_table* t, const char* path, const char* basename);
 int mc2_table_tsv(mc2_table* t, const char* basename, char* buf, uint64_t cap, uint64_t* size);
 void mc2_table_free(mc2_table* t);
 
+/* ---- device-resident exchange between ranks ------------------------------------------------------
+ * When several GPUs hold parts of the SAME sample (whole pieces per rank), their already filtered tables are
+ * summed like the dict merge of bin/mercat2.py:121-127.  These calls let the host layer do that with NCCL on
+ * device memory: the packed rows of a table (64-bit order-preserving codes + counts) are exposed as device
+ * pointers, cut at splitter keys, exchanged all-to-all by the caller and rebuilt into a table on the receiving
+ * GPU; dense per-sample tables are exposed for an in-place NCCL (all-)reduce. */
+/* encoding (0 = 2-bit ACGT, 1 = 5-bit A-Z, 2 = byte), key kind (0 = bit-packed code, 1 = base-26 index of a dense
+ * protein table), number of packed rows and of literal-byte ("wide") rows */
+int mc2_table_info(const mc2_table* t, int* encoding, int* key_kind, uint64_t* packed_rows, uint64_t* wide_rows);
+/* device pointers to the packed rows (sorted by key; valid until the table is freed) */
+int mc2_table_device_rows(mc2_table* t, const uint64_t** keys, const uint64_t** counts, uint64_t* rows);
+/* cuts[i] = number of packed rows with key < splitters[i] (host arrays) */
+int mc2_table_lower_bound(mc2_table* t, const uint64_t* splitters, uint64_t m, uint64_t* cuts);
+/* the literal-byte rows (host copies): kmers wide_rows*k bytes, counts wide_rows entries */
+int mc2_table_export_wide(mc2_table* t, char* kmers, uint64_t* counts);
+/* Build a table from packed rows (device or host memory; unsorted, equal keys are summed) plus literal-byte rows
+ * (host memory, may be NULL/0). */
+int mc2_table_from_rows(mc2_engine* e, int k, int encoding, int key_kind, const uint64_t* keys, const uint64_t* counts,
+                        uint64_t rows, int space, const char* wide_kmers, const uint64_t* wide_counts, uint64_t wide_rows,
+                        mc2_table** out);
+/* The TSV body (rows only, no header line) of a table into host memory: call with buf = NULL for the size. */
+int mc2_table_tsv_body(mc2_table* t, char* buf, uint64_t cap, uint64_t* size);
+/* Device pointer to the per-sample dense table (uint64[bins], bins = 4^k or 26^k) of a sample whose plan is the
+ * dense path, for an in-place NCCL reduce; *bins = 0 when the sample is not on the dense path (or has seen no
+ * text yet).  mc2_sample_dense_plan forces that plan on a sample that has not seen text (a rank without pieces). */
+int mc2_sample_dense(mc2_sample* s, uint64_t** table, uint64_t* bins, int* encoding);
+int mc2_sample_dense_plan(mc2_sample* s, int encoding);
+/* Device-to-device copy on the engine's stream, complete at return (moves a reduced table between engine memory and
+ * a buffer owned by the communication library). */
+int mc2_device_copy(mc2_engine* e, void* dst, const void* src, uint64_t nbytes);
+
 /* ---- protein metrics ----------------------------------------------------------------------------
  * Replaces the numeric part of plot_sample_metrics (lib/mercat2_figures.py:157-183) and
  * predict_isoelectric_point_ProMoST / calculate_MW / calculate_hydro (lib/mercat2_metrics.py:57-170)

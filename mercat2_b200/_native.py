@@ -45,6 +45,15 @@ SYMBOLS = [
     ("mc2_table_write_tsv", _INT, [_VP, C.c_char_p, C.c_char_p]),
     ("mc2_table_tsv", _INT, [_VP, C.c_char_p, _VP, _U64, _PU64]),
     ("mc2_table_free", None, [_VP]),
+    ("mc2_table_info", _INT, [_VP, C.POINTER(_INT), C.POINTER(_INT), _PU64, _PU64]),
+    ("mc2_table_device_rows", _INT, [_VP, _PP, _PP, _PU64]),
+    ("mc2_table_lower_bound", _INT, [_VP, _VP, _U64, _VP]),
+    ("mc2_table_export_wide", _INT, [_VP, _VP, _VP]),
+    ("mc2_table_from_rows", _INT, [_VP, _INT, _INT, _INT, _VP, _VP, _U64, _INT, _VP, _VP, _U64, _PP]),
+    ("mc2_table_tsv_body", _INT, [_VP, _VP, _U64, _PU64]),
+    ("mc2_sample_dense", _INT, [_VP, _PP, _PU64, C.POINTER(_INT)]),
+    ("mc2_sample_dense_plan", _INT, [_VP, _INT]),
+    ("mc2_device_copy", _INT, [_VP, _VP, _VP, _U64]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -167,6 +176,48 @@ class Table:
         lib = self._engine._lib
         return _check(lib, lib.mc2_table_write_tsv(self._h, os.fsencode(str(path)), basename.encode())) == 0
 
+    # ---- device-resident exchange (mercat2_b200.distributed) --------------------------------------
+    def info(self) -> dict:
+        enc, kind, nf, nw = C.c_int(0), C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_info(self._h, C.byref(enc), C.byref(kind), C.byref(nf), C.byref(nw)))
+        return {"encoding": enc.value, "key_kind": kind.value, "packed_rows": int(nf.value), "wide_rows": int(nw.value)}
+
+    def device_rows(self):
+        """(keys_ptr, counts_ptr, rows): device addresses of the packed rows, sorted by key; valid while the table lives."""
+        keys, counts, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_device_rows(self._h, C.byref(keys), C.byref(counts), C.byref(n)))
+        return keys.value or 0, counts.value or 0, int(n.value)
+
+    def lower_bound(self, splitters) -> list:
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        cuts = np.zeros(len(sp), dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_lower_bound(self._h, sp.ctypes.data, len(sp), cuts.ctypes.data))
+        return [int(x) for x in cuts]
+
+    def wide_arrays(self):
+        """The literal-byte rows: (kmers uint8[rows, k], counts uint64[rows])."""
+        nw, k = self.info()["wide_rows"], self.k
+        kmers = np.empty((nw, k), dtype=np.uint8)
+        counts = np.empty(nw, dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_export_wide(self._h, kmers.ctypes.data, counts.ctypes.data))
+        return kmers, counts
+
+    def tsv_body(self) -> bytes:
+        """The TSV rows without the header line."""
+        lib = self._engine._lib
+        size = C.c_uint64(0)
+        _check(lib, lib.mc2_table_tsv_body(self._h, None, 0, C.byref(size)))
+        buf = bytearray(size.value)
+        if size.value:
+            ref = (C.c_char * size.value).from_buffer(buf)
+            _check(lib, lib.mc2_table_tsv_body(self._h, ref, size.value, C.byref(size)))
+            del ref
+        return bytes(buf)
+
 
 class Engine:
     """One CUDA device + stream.  Not thread-safe: one host thread per engine."""
@@ -240,6 +291,21 @@ class Engine:
         _check(self._lib, self._lib.mc2_chunk_offsets(self._h, addr, n, space, chunk_bytes, offs, cap, C.byref(npieces)))
         return [int(offs[i]) for i in range(min(cap, npieces.value))]
 
+    def table_from_rows(self, k: int, encoding: int, key_kind: int, keys_ptr: int, counts_ptr: int, rows: int, on_device: bool,
+                        wide_kmers=None, wide_counts=None) -> Table:
+        """Table from packed rows at raw addresses (equal keys are summed) plus optional literal-byte rows (numpy)."""
+        out = C.c_void_p()
+        nw = 0 if wide_counts is None else len(wide_counts)
+        wk = np.ascontiguousarray(wide_kmers, dtype=np.uint8) if nw else None
+        wc = np.ascontiguousarray(wide_counts, dtype=np.uint64) if nw else None
+        _check(self._lib, self._lib.mc2_table_from_rows(self._h, k, encoding, key_kind, keys_ptr or None, counts_ptr or None, rows,
+                                                        MC2_DEVICE if on_device else MC2_HOST, wk.ctypes.data if nw else None,
+                                                        wc.ctypes.data if nw else None, nw, C.byref(out)))
+        return Table(self, out)
+
+    def device_copy(self, dst_ptr: int, src_ptr: int, nbytes: int):
+        _check(self._lib, self._lib.mc2_device_copy(self._h, dst_ptr, src_ptr, nbytes))
+
     def sample(self, k: int, min_count: int) -> "Sample":
         return Sample(self, k, min_count)
 
@@ -299,6 +365,17 @@ class Sample:
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
         lib = self._engine._lib
         _check(lib, lib.mc2_sample_add_rows(self._h, kmers.ctypes.data, counts.ctypes.data, len(counts)))
+
+    def dense(self):
+        """(device address, bins, encoding) of the per-sample dense table; bins == 0 if the sample is not on the dense path."""
+        ptr, bins, enc = C.c_void_p(), C.c_uint64(0), C.c_int(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_sample_dense(self._h, C.byref(ptr), C.byref(bins), C.byref(enc)))
+        return ptr.value or 0, int(bins.value), enc.value
+
+    def dense_plan(self, encoding: int):
+        lib = self._engine._lib
+        _check(lib, lib.mc2_sample_dense_plan(self._h, encoding))
 
     def finish(self) -> Table:
         out = C.c_void_p()

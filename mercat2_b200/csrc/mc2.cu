@@ -1432,6 +1432,157 @@ int mc2_sample_add_rows(mc2_sample* s, const char* kmers, const uint64_t* counts
     API_END
 }
 
+int mc2_table_info(const mc2_table* t, int* encoding, int* key_kind, uint64_t* packed_rows, uint64_t* wide_rows) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (encoding) *encoding = t->enc;
+    if (key_kind) *key_kind = t->key_kind;
+    if (packed_rows) *packed_rows = t->fast.n;
+    if (wide_rows) *wide_rows = t->wide.n;
+    API_END
+}
+
+int mc2_table_device_rows(mc2_table* t, const uint64_t** keys, const uint64_t** counts, uint64_t* rows) {
+    API_BEGIN
+    if (!t || !keys || !counts || !rows) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    *keys = (const uint64_t*)t->fast.keys.p;
+    *counts = (const uint64_t*)t->fast.counts.p;
+    *rows = t->fast.n;
+    API_END
+}
+
+int mc2_table_lower_bound(mc2_table* t, const uint64_t* splitters, uint64_t m, uint64_t* cuts) {
+    API_BEGIN
+    if (!t || (m && (!splitters || !cuts))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (!m) return MC2_OK;
+    mc2_engine* e = t->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    DBuf<u64> sp(e, m), out(e, m);
+    CUDA_CHECK(cudaMemcpyAsync(sp.p, splitters, m * 8, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, lower_bound_kernel, (unsigned)div_up(m, 128), 128, 0, (const u64*)t->fast.keys.p, (u64)t->fast.n, (const u64*)sp.p, m, out.p);
+    d2h(e, (u64*)cuts, (const u64*)out.p, m);
+    API_END
+}
+
+int mc2_table_export_wide(mc2_table* t, char* kmers, uint64_t* counts) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (t->wide.n && (!kmers || !counts)) throw Mc2Error(MC2_ERR_INVALID, "NULL buffer");
+    CUDA_CHECK(cudaSetDevice(t->e->device));
+    d2h(t->e, (u8*)kmers, (const u8*)t->wide.rows.p, t->wide.n * (u64)t->k);
+    d2h(t->e, (u64*)counts, (const u64*)t->wide.counts.p, t->wide.n);
+    API_END
+}
+
+int mc2_table_from_rows(mc2_engine* e, int k, int encoding, int key_kind, const uint64_t* keys, const uint64_t* counts,
+                        uint64_t rows, int space, const char* wide_kmers, const uint64_t* wide_counts, uint64_t wide_rows,
+                        mc2_table** out) {
+    API_BEGIN
+    if (!e || !out) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (k < 1 || k > 128) throw Mc2Error(MC2_ERR_INVALID, "k out of range");
+    if (encoding < ENC_NT2 || encoding > ENC_BYTE) throw Mc2Error(MC2_ERR_INVALID, "unknown encoding");
+    if ((rows && (!keys || !counts)) || (wide_rows && (!wide_kmers || !wide_counts))) throw Mc2Error(MC2_ERR_INVALID, "NULL rows");
+    if (rows && k * enc_bits(encoding) > 64) throw Mc2Error(MC2_ERR_INVALID, "packed rows need k * bits <= 64");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    mc2_sample s;
+    s.e = e;
+    s.k = k;
+    s.c = 1;
+    s.plan.enc = encoding;
+    s.plan.path = PATH_SPARSE;
+    if (rows) {
+        FastPart part;
+        part.n = rows;
+        part.sorted = false;
+        part.keys.alloc(e, rows);
+        part.counts.alloc(e, rows);
+        const cudaMemcpyKind kind = space == MC2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_CHECK(cudaMemcpyAsync(part.keys.p, keys, rows * 8, kind, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(part.counts.p, counts, rows * 8, kind, e->stream));
+        if (space != MC2_DEVICE) e->h2d_bytes += rows * 16;
+        s.fast.push_back(std::move(part));
+    }
+    if (wide_rows) {
+        WidePart part;
+        part.n = wide_rows;
+        part.sorted = false;
+        part.rows.alloc(e, wide_rows * (u64)k);
+        part.counts.alloc(e, wide_rows);
+        CUDA_CHECK(cudaMemcpyAsync(part.rows.p, wide_kmers, wide_rows * (u64)k, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(part.counts.p, wide_counts, wide_rows * 8, cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += wide_rows * ((u64)k + 8);
+        s.wide.push_back(std::move(part));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));                 // the source buffers may be released by the caller
+    mc2_table* t = sample_finish(&s);
+    t->key_kind = key_kind == KEY_DENSE_AA ? KEY_DENSE_AA : KEY_CODE;
+    *out = t;
+    API_END
+}
+
+int mc2_table_tsv_body(mc2_table* t, char* buf, uint64_t cap, uint64_t* size) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(t->e->device));
+    if (!t->tsv_ready) {
+        t->tsv_bytes = tsv_body_device(t, t->tsv_body);
+        t->tsv_ready = true;
+    }
+    if (size) *size = t->tsv_bytes;
+    if (buf) {
+        if (cap < t->tsv_bytes) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+        download_pipelined(t->e, (const u8*)t->tsv_body.p, t->tsv_bytes, [&](const u8* src, u64 o, u64 m) { memcpy(buf + o, src, m); });
+        t->tsv_body.release();
+        t->tsv_ready = false;
+    }
+    API_END
+}
+
+int mc2_sample_dense(mc2_sample* s, uint64_t** table, uint64_t* bins, int* encoding) {
+    API_BEGIN
+    if (!s || !table || !bins) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(s->e->device));
+    CUDA_CHECK(cudaStreamSynchronize(s->e->stream));
+    const bool dense = s->plan.path == PATH_DENSE;
+    *table = dense ? (uint64_t*)s->dense_sample.p : nullptr;
+    *bins = dense ? s->plan.bins : 0;
+    if (encoding) *encoding = s->plan.enc;
+    API_END
+}
+
+int mc2_device_copy(mc2_engine* e, void* dst, const void* src, uint64_t nbytes) {
+    API_BEGIN
+    if (!e || (nbytes && (!dst || !src))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    if (nbytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    API_END
+}
+
+int mc2_sample_dense_plan(mc2_sample* s, int encoding) {
+    API_BEGIN
+    if (!s) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (s->plan.path != PATH_UNSET) throw Mc2Error(MC2_ERR_INVALID, "the sample already has a plan");
+    if (encoding != ENC_NT2 && encoding != ENC_AA5) throw Mc2Error(MC2_ERR_INVALID, "dense tables exist for encodings 0 and 1");
+    mc2_engine* e = s->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    ParseStats ps;
+    memset(&ps, 0, sizeof ps);
+    ps.n_ascii = ps.n_upper = 1;                                 // shape the statistics so that make_plan picks `encoding`
+    ps.n_acgt = encoding == ENC_NT2 ? 1 : 0;
+    make_plan(e, ps, s->k, s->plan);
+    if (s->plan.path != PATH_DENSE || s->plan.enc != encoding) {
+        s->plan = Plan();
+        throw Mc2Error(MC2_ERR_INVALID, "k too large for a dense table of this encoding");
+    }
+    s->dense_sample.alloc(e, s->plan.bins);
+    s->dense_sample.zero();
+    s->dense_chunk.alloc(e, s->plan.bins);
+    s->dense_chunk.zero();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    API_END
+}
+
 int mc2_sample_finish(mc2_sample* s, mc2_table** out) {
     API_BEGIN
     if (!s || !out) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");

@@ -264,3 +264,16 @@ __global__ void fill_u64_kernel(u64* dst, u64 n, u64 v) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
 }
+
+// out[i] = number of keys (sorted ascending) smaller than q[i]
+__global__ void lower_bound_kernel(const u64* __restrict__ keys, u64 n, const u64* __restrict__ q, u64 m, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const u64 x = q[i];
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (keys[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    out[i] = lo;
+}

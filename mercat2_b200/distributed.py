@@ -135,3 +135,198 @@ def tsv_bytes(basename: str, kmers: np.ndarray, counts: np.ndarray) -> bytes:
     rows = ["k-mer\t%s_Count\n" % basename]
     rows += ["%s\t%d\n" % (text[i * k:(i + 1) * k], int(c)) for i, c in enumerate(counts.tolist())]
     return "".join(rows).encode()
+
+
+# =====================================================================================================
+# Device-resident exchange (NCCL on engine memory)
+# =====================================================================================================
+# The functions above bounce tables through numpy (they also serve the gloo CPU tests).  Below, rows never leave
+# the GPUs: packed (key, count) rows are cut at splitter keys on the device, exchanged with one NCCL all-to-all per
+# array and re-reduced by the engine on the receiving GPU, so each rank ends up owning a disjoint, sorted key range
+# (BASELINE north_star item 5: "hash-partitioned by k-mer code with an NCCL all-to-all"); dense small-k tables are
+# summed in place with an NCCL reduce.  Rank order = key order, so the per-sample TSV is the concatenation of the
+# ranks' parts and every rank writes its own byte range of the file.
+
+ENC_NT2, ENC_AA5, ENC_BYTE = 0, 1, 2
+KEY_CODE, KEY_DENSE_AA = 0, 1
+
+
+def _to_tensor(engine, ptr: int, n: int, device):
+    """n int64 words of engine memory as a tensor the communication library owns (one device-to-device copy)."""
+    import torch
+    t = torch.empty(n, dtype=torch.int64, device=device)
+    if n and ptr:
+        torch.cuda.synchronize(device)
+        engine.device_copy(t.data_ptr(), ptr, n * 8)
+    return t
+
+
+def decode_key(key: int, k: int, encoding: int, key_kind: int) -> bytes:
+    """Text of a packed key (same layouts as csrc/tsv.cuh::tsv_decode)."""
+    out = bytearray(k)
+    for j in range(k - 1, -1, -1):
+        if key_kind == KEY_DENSE_AA:
+            out[j] = 65 + key % 26
+            key //= 26
+        elif encoding == ENC_NT2:
+            out[j] = b"ACGT"[key & 3]
+            key >>= 2
+        elif encoding == ENC_AA5:
+            out[j] = 65 + (key & 31)
+            key >>= 5
+        else:
+            out[j] = key & 255
+            key >>= 8
+    return bytes(out)
+
+
+def _agree(dist, mine):
+    world = dist.get_world_size()
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+    return got
+
+
+def merge_table_device(engine, table, dist, device):
+    """Every rank passes its (already -c filtered) table of ONE sample.  Returns, on every rank, a new table holding
+    the merged rows of the key range that rank owns (ranges are disjoint and ascending with the rank).  Packed rows
+    travel GPU-to-GPU over NCCL; literal-byte rows (rare) go through the object collectives."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    k = table.k
+    info = table.info()
+    metas = _agree(dist, (k, info["encoding"], info["key_kind"], info["packed_rows"], info["wide_rows"]))
+    with_packed = [m for m in metas if m[3] > 0]
+    if any(m[0] != k for m in metas):
+        raise ValueError("ranks disagree on k")
+    if len({(m[1], m[2]) for m in with_packed}) > 1:
+        raise ValueError("ranks counted the same sample under different encodings; merge with merge_tables() instead")
+    enc, kind = (with_packed[0][1], with_packed[0][2]) if with_packed else (info["encoding"], info["key_kind"])
+    keys_ptr, counts_ptr, n = table.device_rows()
+    keys = _to_tensor(engine, keys_ptr, n, device)
+    counts = _to_tensor(engine, counts_ptr, n, device)
+    # splitters from an evenly spaced sample of every rank's sorted keys
+    if n:
+        m = min(n, 256)
+        idx = (torch.arange(m, device=device, dtype=torch.int64) * (n - 1)) // max(m - 1, 1)
+        mine = keys[idx].cpu().numpy().view(np.uint64)
+    else:
+        mine = np.zeros(0, dtype=np.uint64)
+    pool = np.sort(np.concatenate(_agree(dist, mine)))
+    splitters = np.array([pool[(i * len(pool)) // world] for i in range(1, world)], dtype=np.uint64) if len(pool) else np.zeros(0, np.uint64)
+    cuts = [0] + (table.lower_bound(splitters) if len(splitters) else []) + [n]
+    cuts += [n] * (world + 1 - len(cuts))
+    send = [cuts[d + 1] - cuts[d] for d in range(world)]
+    matrix = _agree(dist, send)
+    recv = [matrix[src][rank] for src in range(world)]
+    rk = torch.empty(sum(recv), dtype=torch.int64, device=device)
+    rc = torch.empty(sum(recv), dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_to_all_single(rk, keys, recv, send)
+        dist.all_to_all_single(rc, counts, recv, send)
+    else:
+        rk.copy_(keys)
+        rc.copy_(counts)
+    # literal-byte rows: destination = number of splitter texts <= row text (consistent with the packed cuts)
+    wk = wc = None
+    if any(m[4] > 0 for m in metas):
+        sp_text = np.array([decode_key(int(x), k, enc, kind) for x in splitters], dtype=f"S{k}")
+        my_wk, my_wc = table.wide_arrays() if info["wide_rows"] else (np.zeros((0, k), np.uint8), np.zeros(0, np.uint64))
+        dest = np.searchsorted(sp_text, _as_keys(my_wk, k), side="right") if len(sp_text) else np.zeros(len(my_wc), np.int64)
+        outgoing = [(my_wk[dest == d], my_wc[dest == d]) for d in range(world)]
+        incoming = [x[rank] for x in _agree(dist, outgoing)]
+        wk = np.concatenate([x[0].reshape(-1, k) for x in incoming])
+        wc = np.concatenate([x[1] for x in incoming])
+    torch.cuda.synchronize(device)
+    return engine.table_from_rows(k, enc, kind, rk.data_ptr(), rc.data_ptr(), int(rk.numel()), True, wk, wc)
+
+
+def reduce_dense_sample(engine, sample, dist, device, root: int = 0) -> bool:
+    """If the sample is on the dense path on the ranks that saw text, sum the per-sample tables onto `root` with one
+    NCCL reduce (in place) and return True; return False (nothing done) when the sample is not dense everywhere."""
+    import torch
+    ptr, bins, enc = sample.dense()
+    metas = _agree(dist, (bins, enc))
+    dense = [m for m in metas if m[0] > 0]
+    if not dense or len({(m[0], m[1]) for m in dense}) > 1:
+        return False
+    if any(m[0] == 0 and m[1] >= 0 for m in metas):          # some rank counted its pieces on a non-dense path
+        return False
+    if bins == 0:                                   # this rank saw no text: contribute zeros
+        sample.dense_plan(dense[0][1])
+        ptr, bins, enc = sample.dense()
+        if bins != dense[0][0]:
+            raise RuntimeError("dense plan mismatch between ranks")
+    if dist.get_world_size() > 1:
+        t = _to_tensor(engine, ptr, bins, device)
+        dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize(device)
+        if dist.get_rank() == root:
+            engine.device_copy(ptr, t.data_ptr(), bins * 8)
+    return True
+
+
+def write_tsv_sharded(part, path, basename: str, dist) -> bool:
+    """Write the per-sample TSV (bin/mercat2.py:130-133) from the per-rank key ranges of merge_table_device: every
+    rank formats its rows on its GPU and writes them at its own offset.  No file when no rank has a row."""
+    import os
+    rank = dist.get_rank()
+    body = part.tsv_body() if part.rows else b""
+    sizes = _agree(dist, len(body))
+    if sum(sizes) == 0:
+        return False
+    head = ("k-mer\t%s_Count\n" % basename).encode()
+    if rank == 0:
+        with open(path, "wb") as f:
+            f.write(head)
+            f.truncate(len(head) + sum(sizes))
+    dist.barrier()
+    if body:
+        fd = os.open(path, os.O_WRONLY)
+        try:
+            os.pwrite(fd, body, len(head) + sum(sizes[:rank]))
+        finally:
+            os.close(fd)
+    dist.barrier()
+    return True
+
+
+def count_sample_sharded(engine, pieces, k: int, min_count: int, dist, device, out_path=None, basename: str = "sample",
+                         chunk_bytes: int = 0):
+    """One sample whose pieces (FASTA texts, each filtered on its own like a chunk file) are spread over the ranks:
+    count the local pieces, merge across GPUs on the device, optionally write the TSV.  Returns the rank's table part
+    (sparse: its key range; dense: the full table on rank 0, None elsewhere)."""
+    sample = engine.sample(k, min_count)
+    for text in pieces:
+        sample.add_text(text, chunk_bytes)
+    if reduce_dense_sample(engine, sample, dist, device):
+        # rank 0 now holds the summed dense table; the literal-byte rows (windows outside the alphabet) of the other
+        # ranks are few and follow through the object collective
+        rank = dist.get_rank()
+        table = sample.finish()
+        info = table.info()
+        wide = table.wide_arrays() if info["wide_rows"] else None
+        gathered = _agree(dist, wide if rank != 0 else None)
+        if rank == 0:
+            extra = [g for g in gathered if g is not None and len(g[1])]
+            if extra:
+                own = [wide] if wide is not None else []
+                wk = np.concatenate([x[0].reshape(-1, k) for x in own + extra])
+                wc = np.concatenate([x[1] for x in own + extra])
+                kp, cp, n = table.device_rows()
+                merged = engine.table_from_rows(k, info["encoding"], info["key_kind"], kp, cp, n, True, wk, wc)
+                table.close()
+                table = merged
+            if out_path:
+                table.write_tsv(out_path, basename)
+        else:
+            table.close()
+            table = None
+        dist.barrier()
+        return table
+    table = sample.finish()
+    part = merge_table_device(engine, table, dist, device)
+    table.close()
+    if out_path:
+        write_tsv_sharded(part, out_path, basename, dist)
+    return part

@@ -526,3 +526,36 @@ def test_engine_reducer_merges_rank_tables(engine):
         want = orc.merge_counts(orc.find_kmers_text(h.decode(), k, c) for h in halves)
         assert got == want, diff_msg(got, want)
         assert mcd.tsv_bytes("s", mk, mc) == orc.tsv_bytes("s", want)
+
+
+# ---- device-resident exchange: NCCL process group of size 1 on this GPU (the 2-GPU run is tools/sharded_check.py) ----
+def test_sharded_sample_device_exchange(engine, tmp_path):
+    """count_sample_sharded: local pieces -> per-sample merge on the device -> TSV written by byte ranges.  With one
+    rank the all-to-all is a self copy, but every device call of the exchange (row pointers, splitter cuts, rebuild
+    from packed + literal rows, TSV body, dense reduce) runs."""
+    import torch
+    import torch.distributed as dist
+    from mercat2_b200 import distributed as mcd
+    reset(engine)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29500 + os.getpid() % 2000))
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        dev = torch.device("cuda", 0)
+        text = synth_reads(3000, 150, seed=21, n_rate=0.003, lower_rate=0.02, genome_len=50000)
+        reads = [b">" + r for r in text.split(b">") if r]
+        pieces = [b"".join(reads[i::3]) for i in range(3)]
+        for k, c in ((21, 2), (4, 5), (33, 2), (12, 1)):
+            out = tmp_path / f"s_{k}_{c}.tsv"
+            part = mcd.count_sample_sharded(engine, pieces, k, c, dist, dev, out_path=out, basename="s")
+            want = orc.merge_counts(orc.find_kmers_text(p.decode(), k, c) for p in pieces)
+            assert part is not None and part.to_dict() == want, diff_msg(part.to_dict(), want)
+            if want:
+                assert out.read_bytes() == orc.tsv_bytes("s", want)
+            else:
+                assert not out.exists()
+    finally:
+        if created:
+            dist.destroy_process_group()
