@@ -361,7 +361,8 @@ fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ tabl
 
 template <bool USE_DST>
 __global__ void __launch_bounds__(EX_THREADS)
-fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1) {
+fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1,
+                   const u64* __restrict__ base64) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
     u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)EX_TILE * 8);
@@ -374,7 +375,8 @@ fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1
     const u32 valid = fn_load_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, w);
     auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
     // keys are recomputed (two funnel shifts) wherever they are needed instead of living in 32 registers
-    hc_group_and_write<USE_DST>([&](int i) { return fn_key(w, i, mask); }, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    auto key = [&](int i) { return fn_key(w, i, mask); };
+    hc_group_and_write2<USE_DST>(key, key, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1, base64);
 }
 
 // stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)

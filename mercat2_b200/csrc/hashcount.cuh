@@ -33,8 +33,10 @@
 #define HC_TILE 4096u
 #define HC_SCATTER_SMEM ((size_t)HC_TILE * 12)     // staged keys (8 B) + destination indices (4 B)
 
-__device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb) {
-    const u32 h = (u32)((key * 0x9E3779B97F4A7C15ull) >> 32);
+#define HC_MULT1 0x9E3779B97F4A7C15ull           // bucket hash of a chunk's keys
+#define HC_MULT2 0xC2B2AE3D27D4EB4Full           // independent bucket hash inside a level-0 group (very large chunks)
+__device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb, u64 mult = HC_MULT1) {
+    const u32 h = (u32)((key * mult) >> 32);
     return __umulhi(h, nb);                               // uniform in [0, nb)
 }
 // Shared-memory atomics issued from inside divergent probe loops go through inline PTX: the compiler otherwise
@@ -120,10 +122,12 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 // re-ordered through shared memory so that consecutive threads store consecutive addresses of one digit's run.
 // `mine` yields key i in the ranking phase, `again` in the staging phase: the same registers, or a re-load that
 // lets the keys die in between (fewer live registers, more resident CTAs).
+// `base64` (may be NULL): 64-bit start of every digit's region; the cursors are then relative to it (level-0 groups of
+// chunks with more than 2^32 windows).
 template <bool USE_DST, class KeyFn, class KeyFn2, class DigitFn>
 __device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                     u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
-                                                    u64* __restrict__ out) {
+                                                    u64* __restrict__ out, const u64* __restrict__ base64 = nullptr) {
     u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rk[j] = 0; dg[j] = 0; }
@@ -167,7 +171,8 @@ __device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u3
     } else {
         for (u32 i = threadIdx.x; i < total; i += EX_THREADS) {
             const u32 d = reinterpret_cast<u16*>(sdst)[i];
-            out[gbase[d] + (i - loff[d])] = stage[i];
+            const u64 at = (base64 ? base64[d] : 0ull) + gbase[d] + (i - loff[d]);
+            out[at] = stage[i];
         }
     }
 }
@@ -211,7 +216,7 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
 template <bool USE_DST, bool RELOAD>
 __global__ void __launch_bounds__(EX_THREADS, RELOAD ? 5 : 3)
 hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_base, const u32* __restrict__ tile_pref,
-                   u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2) {
+                   u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2, u64 mult) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
     u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
@@ -238,7 +243,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         mine[j] = 0;
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
-    auto dig = [nb, nb2](u64 key) { return hc_bucket(key, nb) & (nb2 - 1); };
+    auto dig = [nb, nb2, mult](u64 key) { return hc_bucket(key, nb, mult) & (nb2 - 1); };
     if (RELOAD) {
         // the staging phase reads the keys again (an L2 hit: the tile was read a few microseconds ago) instead of
         // carrying 32 registers across two barriers
@@ -251,6 +256,45 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
     } else {
         hc_group_and_write<USE_DST>([&](int i) { return mine[i]; }, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
     }
+}
+
+// ---- key-array sources (level-0 groups of very large chunks): histogram and level-1 scatter over 64-bit keys ----
+#define HK_HIST_THREADS 1024
+__global__ void __launch_bounds__(HK_HIST_THREADS)
+hk_hist_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u64 mult, u32* __restrict__ ghist) {
+    extern __shared__ __align__(16) u8 dyn[];
+    u32* hist = reinterpret_cast<u32*>(dyn);
+    for (u32 i = threadIdx.x; i < nb; i += HK_HIST_THREADS) hist[i] = 0;
+    BLOCK_SYNC();
+    for (u64 i = (u64)blockIdx.x * HK_HIST_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * HK_HIST_THREADS)
+        atomicAdd(&hist[hc_bucket(keys[i], nb, mult)], 1u);
+    BLOCK_SYNC();
+    for (u32 b = threadIdx.x; b < nb; b += HK_HIST_THREADS) {
+        const u32 c = hist[b];
+        if (c) atomicAdd(&ghist[b], c);
+    }
+}
+
+__global__ void __launch_bounds__(EX_THREADS, 3)
+hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u32 nb1, u64 mult, u32* __restrict__ cur1, u64* __restrict__ keys1) {
+    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_TILE * 10 bytes
+    u64* stage = reinterpret_cast<u64*>(dyn_sc);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
+    __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
+    __shared__ u32 sm[EX_WARPS + 1];
+    for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
+    BLOCK_SYNC();
+    const u64 base = (u64)blockIdx.x * HC_TILE;
+    u64 mine[16];
+    u32 valid = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u64 i = base + (u64)j * EX_THREADS + threadIdx.x;
+        mine[j] = 0;
+        if (i < n) { mine[j] = keys[i]; valid |= 1u << j; }
+    }
+    auto dig = [nb, mult](u64 key) { return hc_bucket(key, nb, mult) >> HC_NB2_LOG2; };
+    hc_group_and_write<false>([&](int i) { return mine[i]; }, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------
@@ -570,10 +614,10 @@ hc_count2_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base
 
 // ---- debug: every key of the level-1 / level-2 arrays must sit in the range of its own bucket -------------------
 __global__ void hc_verify_kernel(const u64* __restrict__ keys, const u32* __restrict__ sub_base, u32 nb, u32 step /*1: sub-buckets, HC_NB2: level-1*/,
-                                 u32 total, ull* __restrict__ bad_count) {
+                                 u32 total, ull* __restrict__ bad_count, u64 mult) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const u32 b = hc_bucket(keys[i], nb);
+    const u32 b = hc_bucket(keys[i], nb, mult);
     const u32 lo_b = (b / step) * step, hi_b = min(nb, lo_b + step);
     if (i < sub_base[lo_b] || i >= sub_base[hi_b]) atomicAdd(bad_count, 1ull);
 }

@@ -37,6 +37,8 @@ struct mc2_engine {
     int opt_force_path = 0;
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
+    int opt_big_chunks = 1;                // chunks beyond one hash batch: level-0 key partition in HBM (0 = sort fallback)
+    u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
     int opt_count_variant = 2;             // min_count >= 2: 2 = bitmap pre-filter (faster as measured), 3 = 16-bit counter pre-filter
     int opt_scatter_variant = 0;           // bit0: stage destination indices, bit1: max shared-memory carveout
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
@@ -506,11 +508,19 @@ static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys
 
 // hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch.  Keys come either from
 // the byte symbol stream `v` (encoding ENC) or, when `pv` is given, from the packed nucleotide stream.
+struct KeySpan {               // keys already extracted (one level-0 group of a very large chunk)
+    const u64* keys;
+    u64 n;
+    bool stream_order;         // keys come from the packed lane (first symbol in the low bits)
+};
+
 template <int ENC>
-static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr) {
+static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr) {
     const int k = s->k;
     const int kb = k * EncTraits<ENC>::BITS;
-    const u64 cap = pv ? pv->n : v.n;                           // upper bound on the number of windows
+    const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
+    const u64 mult = ks ? HC_MULT2 : HC_MULT1;
+    const bool stream_order = pv || (ks && ks->stream_order);
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, e->opt_hash_bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
     DBuf<u32> ghist(e, nb), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
@@ -519,7 +529,18 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     ghist.zero();
     tail.zero();
     const size_t hist_smem = (size_t)nb * 4;
-    if (pv) {
+    if (ks) {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(hk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            attr_set = true;
+        }
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hk_hist_kernel, HK_HIST_THREADS, hist_smem));
+        const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms * std::max(per_sm, 1));
+        LAUNCH(e, hk_hist_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, nb, mult, ghist.p);
+    } else if (pv) {
         static thread_local bool attr_set = false;
         if (!attr_set) {
             CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
@@ -549,7 +570,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         CUDA_CHECK(cudaMemsetAsync(keys1.p, 0xEE, cap * 8, e->stream));
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
-    const bool use_dst = e->opt_scatter_variant & 1;
+    const bool use_dst = (e->opt_scatter_variant & 1) && !ks;
     const size_t sc_smem = use_dst ? HC_SCATTER_SMEM : (size_t)HC_TILE * 10;
     {
         static thread_local int attr_variant = -1;
@@ -569,9 +590,11 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             attr_variant = e->opt_scatter_variant;
         }
     }
-    if (pv) {
-        if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p);
-        else LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p);
+    if (ks) {
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p);
+    } else if (pv) {
+        if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
+        else LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
     } else {
         auto kern = hc_scatter1_kernel<ENC>;
         static thread_local bool attr_set[3] = {false, false, false};
@@ -583,20 +606,20 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     }
     if (use_dst)
         LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<true, false>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
     else if (e->opt_scatter_variant & 8)
         LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<false, true>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
     else
         LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<false, false>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p);
+               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
     if (dbg) {
         DBuf<ull> badc(e, 2);
         badc.zero();
         const u64 total = (u64)read_scalar<ull>(e, &tail.p->total);
         if (total) {
-            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys1.p, (const u32*)sub_base.p, nb, (u32)HC_NB2, (u32)total, badc.p);
-            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys2.p, (const u32*)sub_base.p, nb, 1u, (u32)total, badc.p + 1);
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys1.p, (const u32*)sub_base.p, nb, (u32)HC_NB2, (u32)total, badc.p, mult);
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys2.p, (const u32*)sub_base.p, nb, 1u, (u32)total, badc.p + 1, mult);
         }
         const ull b1 = read_scalar<ull>(e, badc.p), b2 = read_scalar<ull>(e, badc.p + 1);
         fprintf(stderr, "[hash] cap=%llu total=%llu nb1=%u nb=%u packed=%d misplaced level1=%llu level2=%llu\n", (ull)cap, (ull)total, nb1, nb,
@@ -691,7 +714,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
                 (!t.ovf_n && ref_rows != t.out_n) ? "  MISMATCH" : "");
     }
     if (t.out_n) {
-        if (pv) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(t.out_n, 256), 256, 0, part.keys.p, (u64)t.out_n, k);
+        if (stream_order) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(t.out_n, 256), 256, 0, part.keys.p, (u64)t.out_n, k);
         part.n = t.out_n;
         part.sorted = false;
         s->fast.push_back(std::move(part));
@@ -702,7 +725,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         d2h(e, base.data(), sub_base.p, nb + 1);
         for (u32 b : ovf) {
             const u64 m = base[b + 1] - base[b];
-            if (pv && m) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, keys2.p + base[b], m, k);
+            if (stream_order && m) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, keys2.p + base[b], m, k);
             count_key_range_sorted(e, s, keys2.p + base[b], m, kb);
         }
     }
@@ -826,103 +849,258 @@ static void adopt_symbols(mc2_engine* e, const u8* dsym, u64 len, Parsed& out) {
 // The nucleotide fast lane (fastnt.cuh).  Returns false when the chunk must go through the general parser
 // (text not simple, sample is not nucleotide / not on the hash path); *need_exceptions is set when the chunk
 // holds non-ACGT symbols whose windows still have to be counted by the wide path.
+static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 chunk_bytes);
+
+// One span (< 4 GiB, starting at a line start) of simple FASTA text on its way to packed symbols.
+struct FnSpan {
+    const u8* text = nullptr;
+    u64 len = 0, ntiles = 0, nsym = 0;
+    DBuf<u8> tstate;
+    DBuf<u32> tcnt;
+    DBuf<u64> toff;
+    DBuf<u32> codes, bad;
+};
+
+// count pass: tile line states + symbols per tile (+ alphabet statistics on the first piece of a sample)
+static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
+    const u64 mis = (u64)(uintptr_t)sp.text & 15ull;
+    sp.ntiles = div_up(mis + sp.len, FN_TILE);
+    sp.tstate.alloc(e, sp.ntiles);
+    sp.tcnt.alloc(e, sp.ntiles);
+    sp.toff.alloc(e, sp.ntiles);
+    if (with_stats)
+        LAUNCH(e, fn_parse_kernel<0>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len, sp.tstate.p, sp.tcnt.p, (const u64*)nullptr,
+               (u32*)nullptr, (u32*)nullptr, st.p);
+    else
+        LAUNCH(e, fn_parse_kernel<2>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len, sp.tstate.p, sp.tcnt.p, (const u64*)nullptr,
+               (u32*)nullptr, (u32*)nullptr, st.p);
+    dev_exclusive_scan<u32, u64>(e, sp.tcnt.p, sp.toff.p, sp.ntiles, &st.p->n_sym);
+    const FnStats fs = read_scalar<FnStats>(e, st.p);
+    sp.nsym = fs.n_sym;
+    if (getenv("MC2_DEBUG_FAST"))
+        fprintf(stderr, "[fast_nt] len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)sp.len, fs.n_sym,
+                fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
+    return fs;
+}
+
+// write pass: 2-bit codes + bad bits (also counts the kept non-ACGT bytes into st->packed2)
+static void fn_write_pass(mc2_engine* e, FnSpan& sp, DBuf<FnStats>& st) {
+    sp.codes.alloc(e, div_up(sp.nsym, 16) + 4);
+    sp.bad.alloc(e, div_up(sp.nsym, 32) + 4);
+    sp.codes.zero();
+    sp.bad.zero();
+    LAUNCH(e, fn_parse_kernel<1>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len, sp.tstate.p, sp.tcnt.p, (const u64*)sp.toff.p,
+           sp.codes.p, sp.bad.p, st.p);
+    sp.tstate.release();
+    sp.tcnt.release();
+    sp.toff.release();
+}
+
+static void fn_dense_span(mc2_engine* e, mc2_sample* s, const PackedView& pv) {
+    const Plan& plan = s->plan;
+    const u64 nwords = div_up(pv.n, 16);
+    if (plan.smem) {
+        const size_t smem = (size_t)plan.bins * plan.nrep * 4;
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * (smem <= 96 * 1024 ? 2 : 1));
+        LAUNCHN(e, "fn_dense_kernel<smem>", fn_dense_kernel<true>, grid, FN_HIST_THREADS, smem, pv, s->k, plan.bins, plan.nrep, s->dense_chunk.p);
+    } else {
+        const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * 2);
+        LAUNCHN(e, "fn_dense_kernel<global>", fn_dense_kernel<false>, grid, FN_HIST_THREADS, 0, pv, s->k, plan.bins, 1u, s->dense_chunk.p);
+    }
+}
+
+// A chunk with more windows than one hash batch holds (-s 0 on a large file): a level-0 partition of ALL its keys by an
+// independent hash into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then
+// the usual two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact
+// for the whole chunk.  Returns false (nothing counted) when the keys do not fit in free device memory.
+static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, u64 hash_max) {
+    const int k = s->k;
+    u64 cap = 0;
+    for (auto& pv : pvs) cap += pv.n;
+    const u32 g0 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(2, div_up(cap, std::max<u64>(1, hash_max / 2))));
+    if (div_up(cap, g0) > hash_max) return false;
+    const u32 nb0 = g0 * HC_NB2;
+    DBuf<u32> ghist(e, nb0);
+    ghist.zero();
+    {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            attr_set = true;
+        }
+    }
+    const size_t hist_smem = (size_t)nb0 * 4;
+    int per_sm = 1;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
+    for (auto& pv : pvs) {
+        const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
+        if (grid) LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, nb0, ghist.p);
+    }
+    std::vector<u32> h(nb0);
+    d2h(e, h.data(), (const u32*)ghist.p, nb0);
+    std::vector<u64> gbase(g0 + 1, 0);
+    u64 gmax = 0;
+    for (u32 g = 0; g < g0; ++g) {
+        u64 n = 0;
+        for (u32 j = 0; j < HC_NB2; ++j) n += h[(u64)g * HC_NB2 + j];
+        gbase[g + 1] = gbase[g] + n;
+        gmax = std::max(gmax, n);
+    }
+    const u64 total = gbase[g0];
+    if (total == 0) return true;
+    if (gmax > hash_max || gmax >= (1ull << 32)) return false;
+    {   // the level-0 array plus one group's working set must fit (free memory + what the pool holds unused)
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, e->device));
+        unsigned long long reserved = 0, used = 0;
+        CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+        CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+        const u64 avail = (u64)free_b + (reserved > used ? (u64)(reserved - used) : 0);
+        const u64 need = total * 8 + gmax * 8 * 3 + (1ull << 30);
+        if (need > avail) return false;
+    }
+    DBuf<u64> keys0(e, total), gbase_dev(e, g0 + 1);
+    DBuf<u32> cur0(e, g0);
+    cur0.zero();
+    CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+            attr_set = true;
+        }
+    }
+    for (auto& pv : pvs) {
+        const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
+        if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, (size_t)HC_TILE * 10, pv, k, nb0, g0, cur0.p, keys0.p,
+                         (const u64*)gbase_dev.p);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // gbase (host vector) was the source of an async copy
+    for (u32 g = 0; g < g0; ++g) {
+        const u64 n = gbase[g + 1] - gbase[g];
+        if (!n) continue;
+        KeySpan ks{keys0.p + gbase[g], n, true};
+        sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &ks);
+    }
+    return true;
+}
+
 static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u64 len, bool* need_exceptions) {
     *need_exceptions = false;
-    if (!e->opt_fast_nt || s->k > 32 || len == 0 || len >= (1ull << 32)) return false;
+    if (!e->opt_fast_nt || s->k > 32 || len == 0) return false;
     if (e->opt_force_enc > 0 || e->opt_force_path == PATH_WIDE) return false;
+    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
     // which plans the packed lane serves: 2-bit sparse keys through the hash tables (min_count >= 2), and dense 4^k tables
     auto served = [&](const Plan& pl) {
         if (pl.enc != ENC_NT2) return false;
         if (pl.path == PATH_DENSE) return s->k <= 15;
         if (pl.path != PATH_SPARSE || s->c < 2 || e->opt_sparse_algo == 1) return false;
-        const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
-        return len <= hash_max;
+        return len <= hash_max || e->opt_big_chunks != 0;
     };
     if (s->plan.path != PATH_UNSET && !served(s->plan)) return false;
-    const u64 mis = (u64)(uintptr_t)dtext & 15ull;
-    const u64 ntiles = div_up(mis + len, FN_TILE);
-    DBuf<u8> tstate(e, ntiles);
-    DBuf<u32> tcnt(e, ntiles);
-    DBuf<u64> toff(e, ntiles);
+    // spans of at most ~span_bytes, cut where the Chunker would cut (at a line containing '>'): no window crosses a cut
+    std::vector<u64> cuts{0};
+    if (len > e->opt_span_bytes) {
+        cuts = chunk_bounds(e, dtext, len, e->opt_span_bytes);
+        if (cuts.empty() || cuts[0] != 0) return false;
+    }
+    for (size_t i = 1; i < cuts.size(); ++i) {                         // the Chunker also cuts at a '>' inside a sequence line:
+        u8 first = 0;                                                  // only real header lines may separate spans
+        CUDA_CHECK(cudaMemcpyAsync(&first, dtext + cuts[i], 1, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (first != '>') return false;
+    }
+    cuts.push_back(len);
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+        if (cuts[i + 1] - cuts[i] >= (1ull << 32)) return false;      // one record of 4 GiB: general path
+    const size_t nspans = cuts.size() - 1;
     DBuf<FnStats> st(e, 1);
     st.zero();
-    const bool plan_known = s->plan.path != PATH_UNSET;
-    if (plan_known)
-        LAUNCH(e, fn_parse_kernel<2>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
-               (u32*)nullptr, (u32*)nullptr, st.p);
-    else
-        LAUNCH(e, fn_parse_kernel<0>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)nullptr,
-               (u32*)nullptr, (u32*)nullptr, st.p);
-    dev_exclusive_scan<u32, u64>(e, tcnt.p, toff.p, ntiles, &st.p->n_sym);
-    const FnStats fs = read_scalar<FnStats>(e, st.p);
-    if (getenv("MC2_DEBUG_FAST"))
-        fprintf(stderr, "[fast_nt] len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)len, fs.n_sym,
-                fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
-    if (fs.complex) return false;
-    // kept / ACGT counts: exact from the statistics pass (first piece); for later pieces "kept" is a bound from the
-    // symbol count and the non-ACGT count arrives with the write pass
-    const u64 n_kept = plan_known ? fs.n_sym : (fs.packed & 0xFFFFFFFFull);
-    const u64 n_acgt = plan_known ? fs.n_sym : n_kept - (fs.packed >> 32);
-    if (s->plan.path == PATH_UNSET) {
-        if (n_kept == 0) return true;                                     // headers only: nothing to count, plan stays open
-        if (n_acgt * 10 < n_kept * 9) return false;                       // not nucleotide-like: let the general path decide
-        ParseStats ps;
-        memset(&ps, 0, sizeof ps);
-        ps.n_acgt = n_acgt;
-        ps.n_upper = n_acgt;
-        ps.n_ascii = n_kept;
-        make_plan(e, ps, s->k, s->plan);
-        if (s->plan.path == PATH_DENSE) {
-            s->dense_sample.alloc(e, s->plan.bins);
-            s->dense_sample.zero();
-            s->dense_chunk.alloc(e, s->plan.bins);
-            s->dense_chunk.zero();
+    std::vector<FnSpan> spans(nspans);
+    u64 nsym_total = 0;
+    for (size_t i = 0; i < nspans; ++i) {
+        FnSpan& sp = spans[i];
+        sp.text = dtext + cuts[i];
+        sp.len = cuts[i + 1] - cuts[i];
+        const bool plan_known = s->plan.path != PATH_UNSET;
+        const FnStats fs = fn_count_pass(e, sp, !plan_known, st);
+        if (fs.complex) return false;
+        if (!plan_known) {
+            // kept / ACGT counts are exact from the statistics pass; later spans learn their non-ACGT count in the write pass
+            const u64 n_kept = fs.packed & 0xFFFFFFFFull, n_acgt = n_kept - (fs.packed >> 32);
+            if (n_kept == 0) {
+                if (nspans == 1) return true;                              // headers only: nothing to count, plan stays open
+                return false;
+            }
+            if (n_acgt * 10 < n_kept * 9) return false;                   // not nucleotide-like: let the general path decide
+            ParseStats ps;
+            memset(&ps, 0, sizeof ps);
+            ps.n_acgt = n_acgt;
+            ps.n_upper = n_acgt;
+            ps.n_ascii = n_kept;
+            make_plan(e, ps, s->k, s->plan);
+            if (s->plan.path == PATH_DENSE) {
+                s->dense_sample.alloc(e, s->plan.bins);
+                s->dense_sample.zero();
+                s->dense_chunk.alloc(e, s->plan.bins);
+                s->dense_chunk.zero();
+            }
+            if (!served(s->plan)) return false;
         }
-        if (!served(s->plan)) return false;
+        if (sp.nsym) fn_write_pass(e, sp, st);
+        nsym_total += sp.nsym;
     }
-    if (n_kept == 0) return true;
-    const u64 nsym = fs.n_sym;
-    DBuf<u32> codes(e, div_up(nsym, 16) + 4), bad(e, div_up(nsym, 32) + 4);
-    codes.zero();
-    bad.zero();
-    LAUNCH(e, fn_parse_kernel<1>, (unsigned)ntiles, FN_THREADS, 0, dtext, len, tstate.p, tcnt.p, (const u64*)toff.p, codes.p,
-           bad.p, st.p);
-    PackedView pv{codes.p, bad.p, nsym};
+    if (nsym_total == 0) return true;
     if (s->plan.path == PATH_DENSE) {
         const Plan& plan = s->plan;
-        const u64 nwords = div_up(nsym, 16);
-        if (plan.smem) {
-            const size_t smem = (size_t)plan.bins * plan.nrep * 4;
-            static thread_local bool attr_set = false;
-            if (!attr_set) {
-                CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_set = true;
+        const unsigned fgrid = (unsigned)div_up(plan.bins, 256);
+        const bool wide_counts = nsym_total >= (1ull << 32);              // a u32 bin could wrap: fold span by span into 64 bits
+        for (auto& sp : spans) {
+            if (!sp.nsym) continue;
+            fn_dense_span(e, s, PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+            if (wide_counts) {
+                if (!s->dense_chunk64.p) { s->dense_chunk64.alloc(e, plan.bins); s->dense_chunk64.zero(); }
+                LAUNCH(e, dense_fold_batch_kernel, fgrid, 256, 0, s->dense_chunk.p, s->dense_chunk64.p, plan.bins);
             }
-            const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * (smem <= 96 * 1024 ? 2 : 1));
-            LAUNCHN(e, "fn_dense_kernel<smem>", fn_dense_kernel<true>, grid, FN_HIST_THREADS, smem, pv, s->k, plan.bins, plan.nrep, s->dense_chunk.p);
-        } else {
-            const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * 2);
-            LAUNCHN(e, "fn_dense_kernel<global>", fn_dense_kernel<false>, grid, FN_HIST_THREADS, 0, pv, s->k, plan.bins, 1u, s->dense_chunk.p);
         }
-        LAUNCH(e, dense_fold_kernel, (unsigned)div_up(plan.bins, 256), 256, 0, s->dense_chunk.p, s->dense_sample.p, plan.bins, s->c);
+        if (wide_counts) LAUNCH(e, dense_fold64_kernel, fgrid, 256, 0, s->dense_chunk64.p, s->dense_sample.p, plan.bins, s->c);
+        else LAUNCH(e, dense_fold_kernel, fgrid, 256, 0, s->dense_chunk.p, s->dense_sample.p, plan.bins, s->c);
         const FnStats fsd = read_scalar<FnStats>(e, st.p);
         *need_exceptions = (fsd.packed2 >> 32) != 0;
         return true;
     }
-    // the write pass's statistics come back with the hash path's own final readback (one sync fewer per chunk)
-    e->ride_dev = st.p;
-    e->ride_len = sizeof(FnStats);
-    e->ride_done = false;
-    try {
-        sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
-    } catch (...) {
-        e->ride_dev = nullptr;
-        throw;
+    if (nspans == 1 && nsym_total <= hash_max) {
+        PackedView pv{spans[0].codes.p, spans[0].bad.p, spans[0].nsym};
+        // the write pass's statistics come back with the hash path's own final readback (one sync fewer per chunk)
+        e->ride_dev = st.p;
+        e->ride_len = sizeof(FnStats);
+        e->ride_done = false;
+        try {
+            sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
+        } catch (...) {
+            e->ride_dev = nullptr;
+            throw;
+        }
+        FnStats fs2;
+        if (e->ride_done) memcpy(&fs2, (const u8*)e->pin_small + 2048, sizeof fs2);
+        else { e->ride_dev = nullptr; fs2 = read_scalar<FnStats>(e, st.p); }
+        *need_exceptions = (fs2.packed2 >> 32) != 0;
+        return true;
     }
-    FnStats fs2;
-    if (e->ride_done) memcpy(&fs2, (const u8*)e->pin_small + 2048, sizeof fs2);
-    else { e->ride_dev = nullptr; fs2 = read_scalar<FnStats>(e, st.p); }
-    *need_exceptions = (fs2.packed2 >> 32) != 0;
+    if (!e->opt_big_chunks) return false;
+    std::vector<PackedView> pvs;
+    for (auto& sp : spans)
+        if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+    if (!sparse_chunk_hash_big(e, s, pvs, hash_max)) return false;
+    const FnStats fs3 = read_scalar<FnStats>(e, st.p);
+    *need_exceptions = (fs3.packed2 >> 32) != 0;
     return true;
 }
 
@@ -1340,6 +1518,8 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
     else if (n == "count_variant") e->opt_count_variant = (int)value;
+    else if (n == "big_chunks") e->opt_big_chunks = (int)value;
+    else if (n == "span_bytes") e->opt_span_bytes = value < 4096 ? 4096 : (value > (3ull << 30) ? (3ull << 30) : (u64)value);
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);

@@ -559,3 +559,31 @@ def test_sharded_sample_device_exchange(engine, tmp_path):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,c", [(21, 2), (31, 3), (9, 2)])
+def test_big_chunk_level0_partition(engine, k, c):
+    """a chunk with more windows than one hash batch holds: parsed in spans cut at header lines, keys partitioned
+    once into level-0 groups, each group counted by the two-level pipeline; the -c filter applies to the whole chunk"""
+    reset(engine)
+    text = synth_reads(5000, 150, seed=31, n_rate=0.002, lower_rate=0.0, genome_len=30000)
+    want = orc.find_kmers_text(text.decode(), k, c)
+    engine.set_option("hash_bucket_keys", 4)          # one hash batch = 400 * 128 * 4 = 204 800 keys
+    engine.set_option("span_bytes", 64 << 10)
+    engine.set_option("force_path", 2)
+    try:
+        launches0 = engine.stat("launches")
+        check(engine, text, k, c, want, f"big chunk k={k} c={c}")
+        engine.set_option("profile", 2)
+        engine.count_text(text, k, c).close()
+        prof = engine.profile()
+        engine.set_option("profile", 0)
+        assert "hk_scatter1_kernel" in prof and prof["hk_scatter1_kernel"]["launches"] >= 2, sorted(prof)
+        assert engine.stat("launches") > launches0
+        # the same chunk with the level-0 path switched off (sort fallback) gives the same table
+        engine.set_option("big_chunks", 0)
+        check(engine, text, k, c, want, f"sort fallback k={k} c={c}")
+    finally:
+        engine.set_option("big_chunks", 1)
+        engine.set_option("span_bytes", 1 << 30)
+        reset(engine)
