@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
 #include "mercat2_b200.h"
 #include "common.cuh"
 #include "parse.cuh"
@@ -148,6 +149,21 @@ static T read_scalar(mc2_engine* e, const T* dev) {
     memcpy(&v, e->pin_small, sizeof(T));
     return v;
 }
+
+// MC2_DEBUG_PHASES=1: wall time of coarse phases (synchronises the stream at every mark)
+struct PhaseTimer {
+    mc2_engine* e;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(mc2_engine* e_) : e(e_), on(getenv("MC2_DEBUG_PHASES") != nullptr) { if (on) { cudaStreamSynchronize(e->stream); t0 = std::chrono::steady_clock::now(); } }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(e->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[phase] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 template <typename T>
 static void d2h(mc2_engine* e, T* host, const T* dev, u64 n) {
@@ -937,12 +953,14 @@ static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vecto
     const size_t hist_smem = (size_t)nb0 * 4;
     int per_sm = 1;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
+    PhaseTimer pt(e);
     for (auto& pv : pvs) {
         const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
         if (grid) LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, nb0, ghist.p);
     }
     std::vector<u32> h(nb0);
     d2h(e, h.data(), (const u32*)ghist.p, nb0);
+    pt.mark("level-0 histogram");
     std::vector<u64> gbase(g0 + 1, 0);
     u64 gmax = 0;
     for (u32 g = 0; g < g0; ++g) {
@@ -983,12 +1001,14 @@ static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vecto
                          (const u64*)gbase_dev.p);
     }
     CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // gbase (host vector) was the source of an async copy
+    pt.mark("level-0 scatter");
     for (u32 g = 0; g < g0; ++g) {
         const u64 n = gbase[g + 1] - gbase[g];
         if (!n) continue;
         KeySpan ks{keys0.p + gbase[g], n, true};
         sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &ks);
     }
+    pt.mark("groups");
     return true;
 }
 
@@ -1025,6 +1045,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     st.zero();
     std::vector<FnSpan> spans(nspans);
     u64 nsym_total = 0;
+    PhaseTimer pt(e);
     for (size_t i = 0; i < nspans; ++i) {
         FnSpan& sp = spans[i];
         sp.text = dtext + cuts[i];
@@ -1058,6 +1079,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         nsym_total += sp.nsym;
     }
     if (nsym_total == 0) return true;
+    pt.mark("packed parse");
     if (s->plan.path == PATH_DENSE) {
         const Plan& plan = s->plan;
         const unsigned fgrid = (unsigned)div_up(plan.bins, 256);
@@ -1320,6 +1342,7 @@ static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u
 
 static mc2_table* sample_finish(mc2_sample* s) {
     mc2_engine* e = s->e;
+    PhaseTimer pt(e);
     std::unique_ptr<mc2_table> t(new mc2_table);
     t->e = e;
     t->k = s->k;
@@ -1341,8 +1364,10 @@ static mc2_table* sample_finish(mc2_sample* s) {
     } else if (!s->fast.empty()) {
         reduce_fast_parts(e, s->fast, s->k * enc_bits(t->enc), 1, t->fast);
     }
+    pt.mark("finish: packed rows");
     if (!s->wide.empty()) reduce_wide_parts(e, s->wide, s->k, 1, t->wide);
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    pt.mark("finish: literal rows");
     return t.release();
 }
 
