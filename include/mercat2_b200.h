@@ -139,6 +139,20 @@ int mc2_table_tsv_body(mc2_table* t, char* buf, uint64_t cap, uint64_t* size);
  * text yet).  mc2_sample_dense_plan forces that plan on a sample that has not seen text (a rank without pieces). */
 int mc2_sample_dense(mc2_sample* s, uint64_t** table, uint64_t* bins, int* encoding);
 int mc2_sample_dense_plan(mc2_sample* s, int encoding);
+/* ---- one piece split across GPUs BEFORE the filter (SURVEY 8e grain 3; `-s 0` on a file larger than one GPU) ----
+ * Every rank parses its byte range of the piece (cut at header lines) and partitions the 2-bit packed keys of all
+ * its windows into `groups` groups by key hash (mc2_partition_keys: device array grouped by group id + sizes).  The
+ * host layer sends group g to its owner rank (NCCL all-to-all on the device array), the owner counts the keys it
+ * received as ONE chunk (mc2_sample_add_keys: the -c filter then sees whole-piece counts, exactly like
+ * lib/mercat2_kmers.py:73-78 on the unsplit piece).  Windows outside the packed alphabet (N, lower case ...) are
+ * counted unfiltered by mc2_count_exceptions so that the caller can sum them across ranks before filtering. */
+typedef struct mc2_keys mc2_keys;
+int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, uint32_t groups, mc2_keys** out);
+/* keys: device array of *total keys, group g occupying sizes[0]+..+sizes[g-1] onward; sizes: groups entries */
+int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols);
+void mc2_keys_free(mc2_keys* ks);
+int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space);
+int mc2_count_exceptions(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, mc2_table** out);
 /* Device-to-device copy on the engine's stream, complete at return (moves a reduced table between engine memory and
  * a buffer owned by the communication library). */
 int mc2_device_copy(mc2_engine* e, void* dst, const void* src, uint64_t nbytes);

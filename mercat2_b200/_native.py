@@ -54,6 +54,11 @@ SYMBOLS = [
     ("mc2_sample_dense", _INT, [_VP, _PP, _PU64, C.POINTER(_INT)]),
     ("mc2_sample_dense_plan", _INT, [_VP, _INT]),
     ("mc2_device_copy", _INT, [_VP, _VP, _VP, _U64]),
+    ("mc2_partition_keys", _INT, [_VP, _VP, _U64, _INT, _INT, C.c_uint32, _PP]),
+    ("mc2_keys_info", _INT, [_VP, _PP, _VP, _PU64, _PU64]),
+    ("mc2_keys_free", None, [_VP]),
+    ("mc2_sample_add_keys", _INT, [_VP, _VP, _U64, _INT]),
+    ("mc2_count_exceptions", _INT, [_VP, _VP, _U64, _INT, _INT, _PP]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -303,6 +308,20 @@ class Engine:
                                                         wc.ctypes.data if nw else None, nw, C.byref(out)))
         return Table(self, out)
 
+    def partition_keys(self, data, k: int, groups: int) -> "Keys":
+        """2-bit packed keys of every window of a plain nucleotide FASTA text, grouped by key hash into `groups` groups."""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_partition_keys(self._h, addr, n, space, k, groups, C.byref(out)))
+        return Keys(self, out, groups)
+
+    def count_exceptions(self, data, k: int) -> Table:
+        """Unfiltered table of the windows that hold a symbol outside ACGT (literal-byte rows)."""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_count_exceptions(self._h, addr, n, space, k, C.byref(out)))
+        return Table(self, out)
+
     def device_copy(self, dst_ptr: int, src_ptr: int, nbytes: int):
         _check(self._lib, self._lib.mc2_device_copy(self._h, dst_ptr, src_ptr, nbytes))
 
@@ -344,6 +363,27 @@ class Engine:
         return self._metrics_arrays(out)
 
 
+class Keys:
+    """Device array of packed keys grouped by hash (Engine.partition_keys)."""
+
+    def __init__(self, engine, handle, groups):
+        self._engine, self._h, self.groups = engine, handle, groups
+        ptr, total, exc = C.c_void_p(), C.c_uint64(0), C.c_uint64(0)
+        sizes = np.zeros(groups, dtype=np.uint64)
+        lib = engine._lib
+        _check(lib, lib.mc2_keys_info(handle, C.byref(ptr), sizes.ctypes.data, C.byref(total), C.byref(exc)))
+        self.ptr, self.total, self.exception_symbols = ptr.value or 0, int(total.value), int(exc.value)
+        self.sizes = [int(x) for x in sizes]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._engine._h:
+            self._engine._lib.mc2_keys_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 class Sample:
     """Several files of one sample: each add_text() is chunked and counted like one chunk-file list."""
 
@@ -365,6 +405,11 @@ class Sample:
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
         lib = self._engine._lib
         _check(lib, lib.mc2_sample_add_rows(self._h, kmers.ctypes.data, counts.ctypes.data, len(counts)))
+
+    def add_keys(self, keys_ptr: int, n: int, on_device: bool = True):
+        """Count n packed keys at a raw address as ONE chunk of this sample (min_count applies to their totals)."""
+        lib = self._engine._lib
+        _check(lib, lib.mc2_sample_add_keys(self._h, keys_ptr or None, n, MC2_DEVICE if on_device else MC2_HOST))
 
     def dense(self):
         """(device address, bins, encoding) of the per-sample dense table; bins == 0 if the sample is not on the dense path."""

@@ -35,6 +35,7 @@
 
 #define HC_MULT1 0x9E3779B97F4A7C15ull           // bucket hash of a chunk's keys
 #define HC_MULT2 0xC2B2AE3D27D4EB4Full           // independent bucket hash inside a level-0 group (very large chunks)
+#define HC_MULT3 0xA0761D6478BD642Full           // level-0 hash of a key array that was itself selected by HC_MULT1 (keys received from other GPUs)
 __device__ __forceinline__ u32 hc_bucket(u64 key, u32 nb, u64 mult = HC_MULT1) {
     const u32 h = (u32)((key * mult) >> 32);
     return __umulhi(h, nb);                               // uniform in [0, nb)
@@ -276,7 +277,8 @@ hk_hist_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u64 mult, u32* __res
 }
 
 __global__ void __launch_bounds__(EX_THREADS, 3)
-hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u32 nb1, u64 mult, u32* __restrict__ cur1, u64* __restrict__ keys1) {
+hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u32 nb1, u64 mult, u32* __restrict__ cur1, u64* __restrict__ keys1,
+                   const u64* __restrict__ base64) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_TILE * 10 bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
     u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
@@ -294,7 +296,8 @@ hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u32 nb1, u64 mul
         if (i < n) { mine[j] = keys[i]; valid |= 1u << j; }
     }
     auto dig = [nb, mult](u64 key) { return hc_bucket(key, nb, mult) >> HC_NB2_LOG2; };
-    hc_group_and_write<false>([&](int i) { return mine[i]; }, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1);
+    auto key = [&](int i) { return mine[i]; };
+    hc_group_and_write2<false>(key, key, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1, base64);
 }
 
 // ---- hc_count: persistent CTAs, one sub-bucket at a time ---------------------------------------------------------

@@ -607,7 +607,8 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         }
     }
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p);
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p,
+               (const u64*)nullptr);
     } else if (pv) {
         if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
         else LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
@@ -934,45 +935,58 @@ static void fn_dense_span(mc2_engine* e, mc2_sample* s, const PackedView& pv) {
 // independent hash into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then
 // the usual two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact
 // for the whole chunk.  Returns false (nothing counted) when the keys do not fit in free device memory.
-static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, u64 hash_max) {
-    const int k = s->k;
-    u64 cap = 0;
-    for (auto& pv : pvs) cap += pv.n;
-    const u32 g0 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(2, div_up(cap, std::max<u64>(1, hash_max / 2))));
-    if (div_up(cap, g0) > hash_max) return false;
+// Level-0 partition of key sources into g0 groups by hash `mult`: keys0 (grouped, exact offsets in gbase[g0 + 1]).
+// Sources: packed symbol streams (their windows) or one key array.  Returns false if the result does not fit in
+// free device memory (`extra` = bytes the caller still needs afterwards) or a group would exceed `group_max` keys.
+struct Level0 {
+    DBuf<u64> keys0;
+    std::vector<u64> gbase;
+    u64 gmax = 0;
+};
+static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, u32 g0, u64 mult,
+                             u64 group_max, u64 extra, Level0& out) {
     const u32 nb0 = g0 * HC_NB2;
     DBuf<u32> ghist(e, nb0);
     ghist.zero();
-    {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            attr_set = true;
-        }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(hk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
+        attr_set = true;
     }
     const size_t hist_smem = (size_t)nb0 * 4;
-    int per_sm = 1;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
     PhaseTimer pt(e);
-    for (auto& pv : pvs) {
-        const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
-        if (grid) LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, nb0, ghist.p);
+    if (ks) {
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hk_hist_kernel, HK_HIST_THREADS, hist_smem));
+        const u64 grid = std::min<u64>(div_up(ks->n, HK_HIST_THREADS * 8), (u64)e->num_sms * std::max(per_sm, 1));
+        if (ks->n) LAUNCH(e, hk_hist_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, nb0, mult, ghist.p);
+    } else {
+        if (mult != HC_MULT1) throw Mc2Error(MC2_ERR_INVALID, "level-0 partition of packed streams uses the first hash (internal error)");
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
+        for (auto& pv : pvs) {
+            const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
+            if (grid) LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, nb0, ghist.p);
+        }
     }
     std::vector<u32> h(nb0);
     d2h(e, h.data(), (const u32*)ghist.p, nb0);
     pt.mark("level-0 histogram");
-    std::vector<u64> gbase(g0 + 1, 0);
-    u64 gmax = 0;
+    out.gbase.assign(g0 + 1, 0);
+    out.gmax = 0;
     for (u32 g = 0; g < g0; ++g) {
         u64 n = 0;
         for (u32 j = 0; j < HC_NB2; ++j) n += h[(u64)g * HC_NB2 + j];
-        gbase[g + 1] = gbase[g] + n;
-        gmax = std::max(gmax, n);
+        out.gbase[g + 1] = out.gbase[g] + n;
+        out.gmax = std::max(out.gmax, n);
     }
-    const u64 total = gbase[g0];
+    const u64 total = out.gbase[g0];
     if (total == 0) return true;
-    if (gmax > hash_max || gmax >= (1ull << 32)) return false;
-    {   // the level-0 array plus one group's working set must fit (free memory + what the pool holds unused)
+    if (out.gmax > group_max || out.gmax >= (1ull << 32)) return false;
+    {   // the level-0 array plus what follows must fit (free memory + what the pool holds unused)
         size_t free_b = 0, total_b = 0;
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         cudaMemPool_t pool;
@@ -981,34 +995,72 @@ static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vecto
         CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
         CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
         const u64 avail = (u64)free_b + (reserved > used ? (u64)(reserved - used) : 0);
-        const u64 need = total * 8 + gmax * 8 * 3 + (1ull << 30);
-        if (need > avail) return false;
+        if (total * 8 + extra + (1ull << 30) > avail) return false;
     }
-    DBuf<u64> keys0(e, total), gbase_dev(e, g0 + 1);
+    out.keys0.alloc(e, total);
+    DBuf<u64> gbase_dev(e, g0 + 1);
     DBuf<u32> cur0(e, g0);
     cur0.zero();
-    CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-    {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            attr_set = true;
+    CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    if (ks) {
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb0, g0, mult, cur0.p,
+               out.keys0.p, (const u64*)gbase_dev.p);
+    } else {
+        for (auto& pv : pvs) {
+            const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
+            if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, (size_t)HC_TILE * 10, pv, k, nb0, g0, cur0.p, out.keys0.p,
+                             (const u64*)gbase_dev.p);
         }
     }
-    for (auto& pv : pvs) {
-        const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
-        if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, (size_t)HC_TILE * 10, pv, k, nb0, g0, cur0.p, keys0.p,
-                         (const u64*)gbase_dev.p);
-    }
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // gbase (host vector) was the source of an async copy
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // (host vector was the source of an async copy)
     pt.mark("level-0 scatter");
+    return true;
+}
+
+static u32 level0_groups(u64 cap, u64 hash_max) {
+    return (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(2, div_up(cap, std::max<u64>(1, hash_max / 2))));
+}
+
+// A chunk with more windows than one hash batch holds (-s 0 on a large file): a level-0 partition of ALL its keys by an
+// independent hash into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then
+// the usual two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact
+// for the whole chunk.  Returns false (nothing counted) when the keys do not fit in free device memory.
+static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, const KeySpan* ks, u64 hash_max) {
+    u64 cap = ks ? ks->n : 0;
+    for (auto& pv : pvs) cap += pv.n;
+    const u32 g0 = level0_groups(cap, hash_max);
+    if (div_up(cap, g0) > hash_max) return false;
+    Level0 l0;
+    if (!level0_partition(e, s->k, pvs, ks, g0, ks ? HC_MULT3 : HC_MULT1, hash_max, 3 * 8 * div_up(cap, g0) * 2, l0)) return false;
+    PhaseTimer pt(e);
     for (u32 g = 0; g < g0; ++g) {
-        const u64 n = gbase[g + 1] - gbase[g];
+        const u64 n = l0.gbase[g + 1] - l0.gbase[g];
         if (!n) continue;
-        KeySpan ks{keys0.p + gbase[g], n, true};
-        sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &ks);
+        KeySpan span{l0.keys0.p + l0.gbase[g], n, true};
+        sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
     }
     pt.mark("groups");
+    return true;
+}
+
+// Spans of at most ~span_bytes, cut where the Chunker would cut (at a line containing '>'); only real header lines
+// may separate spans (the Chunker also cuts at a '>' inside a sequence line), so that no window crosses a cut.
+// cuts = span starts + len.  false: use the general path.
+static bool fn_span_cuts(mc2_engine* e, const u8* dtext, u64 len, std::vector<u64>& cuts) {
+    cuts.assign(1, 0);
+    if (len > e->opt_span_bytes) {
+        cuts = chunk_bounds(e, dtext, len, e->opt_span_bytes);
+        if (cuts.empty() || cuts[0] != 0) return false;
+    }
+    for (size_t i = 1; i < cuts.size(); ++i) {
+        u8 first = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&first, dtext + cuts[i], 1, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (first != '>') return false;
+    }
+    cuts.push_back(len);
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+        if (cuts[i + 1] - cuts[i] >= (1ull << 32)) return false;      // one record of 4 GiB
     return true;
 }
 
@@ -1025,21 +1077,8 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         return len <= hash_max || e->opt_big_chunks != 0;
     };
     if (s->plan.path != PATH_UNSET && !served(s->plan)) return false;
-    // spans of at most ~span_bytes, cut where the Chunker would cut (at a line containing '>'): no window crosses a cut
-    std::vector<u64> cuts{0};
-    if (len > e->opt_span_bytes) {
-        cuts = chunk_bounds(e, dtext, len, e->opt_span_bytes);
-        if (cuts.empty() || cuts[0] != 0) return false;
-    }
-    for (size_t i = 1; i < cuts.size(); ++i) {                         // the Chunker also cuts at a '>' inside a sequence line:
-        u8 first = 0;                                                  // only real header lines may separate spans
-        CUDA_CHECK(cudaMemcpyAsync(&first, dtext + cuts[i], 1, cudaMemcpyDeviceToHost, e->stream));
-        CUDA_CHECK(cudaStreamSynchronize(e->stream));
-        if (first != '>') return false;
-    }
-    cuts.push_back(len);
-    for (size_t i = 0; i + 1 < cuts.size(); ++i)
-        if (cuts[i + 1] - cuts[i] >= (1ull << 32)) return false;      // one record of 4 GiB: general path
+    std::vector<u64> cuts;
+    if (!fn_span_cuts(e, dtext, len, cuts)) return false;
     const size_t nspans = cuts.size() - 1;
     DBuf<FnStats> st(e, 1);
     st.zero();
@@ -1120,7 +1159,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     std::vector<PackedView> pvs;
     for (auto& sp : spans)
         if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
-    if (!sparse_chunk_hash_big(e, s, pvs, hash_max)) return false;
+    if (!sparse_chunk_hash_big(e, s, pvs, nullptr, hash_max)) return false;
     const FnStats fs3 = read_scalar<FnStats>(e, st.p);
     *need_exceptions = (fs3.packed2 >> 32) != 0;
     return true;
@@ -1785,6 +1824,130 @@ int mc2_sample_dense_plan(mc2_sample* s, int encoding) {
     s->dense_chunk.alloc(e, s->plan.bins);
     s->dense_chunk.zero();
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    API_END
+}
+
+struct mc2_keys {
+    mc2_engine* e = nullptr;
+    int k = 0;
+    u32 groups = 0;
+    Level0 l0;
+    u64 exception_symbols = 0;
+};
+
+int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, uint32_t groups, mc2_keys** out) {
+    API_BEGIN
+    check_count_args(e, text, nbytes, k);
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    if (k > 32) throw Mc2Error(MC2_ERR_LIMIT, "key partition needs k <= 32 (2-bit packed keys)");
+    if (groups < 1 || groups > HC_MAX_NB1) throw Mc2Error(MC2_ERR_INVALID, "groups must be in [1, 400]");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_keys> ks(new mc2_keys);
+    ks->e = e;
+    ks->k = k;
+    ks->groups = groups;
+    ks->l0.gbase.assign(groups + 1, 0);
+    if (nbytes) {
+        DBuf<u8> holder;
+        const u8* d = to_device(e, text, nbytes, space, holder);
+        std::vector<u64> cuts;
+        if (!fn_span_cuts(e, d, nbytes, cuts)) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text cannot be cut into spans at header lines");
+        DBuf<FnStats> st(e, 1);
+        st.zero();
+        std::vector<FnSpan> spans(cuts.size() - 1);
+        std::vector<PackedView> pvs;
+        for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+            FnSpan& sp = spans[i];
+            sp.text = d + cuts[i];
+            sp.len = cuts[i + 1] - cuts[i];
+            const FnStats fs = fn_count_pass(e, sp, false, st);
+            if (fs.complex) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text is not plain FASTA (whitespace, '*' or non-ASCII bytes in sequence lines)");
+            if (!sp.nsym) continue;
+            fn_write_pass(e, sp, st);
+            pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+        }
+        if (!level0_partition(e, k, pvs, nullptr, groups, HC_MULT1, (1ull << 32) - 1, 0, ks->l0))
+            throw Mc2Error(MC2_ERR_LIMIT, "key partition: the keys do not fit in free device memory");
+        const FnStats fs2 = read_scalar<FnStats>(e, st.p);
+        ks->exception_symbols = fs2.packed2 >> 32;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *out = ks.release();
+    API_END
+}
+
+int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols) {
+    API_BEGIN
+    if (!ks) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (keys) *keys = (const uint64_t*)ks->l0.keys0.p;
+    if (sizes)
+        for (u32 g = 0; g < ks->groups; ++g) sizes[g] = ks->l0.gbase[g + 1] - ks->l0.gbase[g];
+    if (total) *total = ks->l0.gbase[ks->groups];
+    if (exception_symbols) *exception_symbols = ks->exception_symbols;
+    API_END
+}
+
+void mc2_keys_free(mc2_keys* ks) {
+    if (!ks) return;
+    cudaSetDevice(ks->e->device);
+    delete ks;
+}
+
+int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space) {
+    API_BEGIN
+    if (!s || (n && !keys)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    mc2_engine* e = s->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    if (s->k > 32) throw Mc2Error(MC2_ERR_LIMIT, "packed keys need k <= 32");
+    if (s->plan.path == PATH_UNSET) {
+        s->plan.enc = ENC_NT2;
+        s->plan.path = PATH_SPARSE;
+    } else if (s->plan.enc != ENC_NT2 || s->plan.path != PATH_SPARSE) {
+        throw Mc2Error(MC2_ERR_INVALID, "the sample is not counting 2-bit packed keys");
+    }
+    s->n_chunks++;
+    e->chunks++;
+    if (n) {
+        DBuf<u64> holder;
+        const u64* d = keys;
+        if (space != MC2_DEVICE) {
+            holder.alloc(e, n);
+            CUDA_CHECK(cudaMemcpyAsync(holder.p, keys, n * 8, cudaMemcpyHostToDevice, e->stream));
+            e->h2d_bytes += n * 8;
+            d = holder.p;
+        }
+        const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
+        KeySpan span{d, n, true};
+        if (n <= hash_max) sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
+        else if (!sparse_chunk_hash_big(e, s, std::vector<PackedView>(), &span, hash_max))
+            throw Mc2Error(MC2_ERR_LIMIT, "add_keys: the keys do not fit in free device memory");
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    API_END
+}
+
+int mc2_count_exceptions(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, mc2_table** out) {
+    API_BEGIN
+    check_count_args(e, text, nbytes, k);
+    if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    mc2_sample s;
+    s.e = e;
+    s.k = k;
+    s.c = 1;
+    s.plan.enc = ENC_NT2;
+    s.plan.path = k <= 32 ? PATH_SPARSE : PATH_WIDE;
+    if (nbytes) {
+        DBuf<u8> holder;
+        const u8* d = to_device(e, text, nbytes, space, holder);
+        Parsed ps;
+        parse_text(e, d, nbytes, 0, ps);
+        SymView v{ps.sym.p, ps.nsym};
+        const u64 n_slow = ps.stats.n_ascii - ps.stats.n_acgt;
+        if (ps.nsym && k > 32) wide_chunk<ENC_BYTE, 1>(e, &s, v, ~0ull);
+        else if (ps.nsym && n_slow) wide_chunk<ENC_NT2, 0>(e, &s, v, std::max<u64>(1024, n_slow * (u64)k));
+    }
+    *out = sample_finish(&s);
     API_END
 }
 

@@ -330,3 +330,79 @@ def count_sample_sharded(engine, pieces, k: int, min_count: int, dist, device, o
     if out_path:
         write_tsv_sharded(part, out_path, basename, dist)
     return part
+
+
+# =====================================================================================================
+# One piece split across GPUs before the filter (SURVEY.md 8e grain 3)
+# =====================================================================================================
+def split_at_headers(text: bytes, world: int) -> list:
+    """Cut one FASTA text into `world` byte ranges of similar size, each starting at a header line (so that no
+    window crosses a cut).  Host helper for callers that hold the whole text; ranks that read their own byte range
+    of a file do the same with two seeks."""
+    n = len(text)
+    cuts = [0]
+    for r in range(1, world):
+        at = max(cuts[-1], (n * r) // world)
+        pos = 0 if at == 0 else text.find(b"\n>", at - 1)
+        cuts.append(n if pos < 0 else pos + 1)
+    cuts.append(n)
+    return [text[cuts[i]:cuts[i + 1]] for i in range(world)]
+
+
+def _sum_rows(parts_k, parts_c, k):
+    """numpy reduce-by-key of literal-byte rows (few)."""
+    kk = np.concatenate([np.asarray(x, np.uint8).reshape(-1, k) for x in parts_k]) if parts_k else np.zeros((0, k), np.uint8)
+    cc = np.concatenate([np.asarray(x, np.uint64) for x in parts_c]) if parts_c else np.zeros(0, np.uint64)
+    if not len(cc):
+        return kk, cc
+    keys = _as_keys(kk, k)
+    uniq, inv = np.unique(keys, return_inverse=True)
+    sums = np.zeros(len(uniq), dtype=np.uint64)
+    np.add.at(sums, inv, cc)
+    return np.frombuffer(uniq.tobytes(), dtype=np.uint8).reshape(-1, k), sums
+
+
+def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, device, out_path=None,
+                                 basename: str = "sample", groups_per_rank: int = 4):
+    """ONE piece (chunk) whose text is split by position over the ranks (each part starts at a header line).  The
+    `-c` filter must see whole-piece counts, so keys are exchanged BEFORE counting: every rank partitions the packed
+    keys of its windows by hash into world * groups_per_rank groups on its GPU, one NCCL all-to-all moves each group
+    to its owner, the owner counts what it received as one chunk.  The (few) windows outside ACGT are counted
+    unfiltered, summed across ranks and filtered on rank 0.  The surviving rows are then re-partitioned by key range
+    (merge_table_device) so that rank order = sorted order, and the TSV is written by byte ranges.
+    Returns this rank's part of the final table."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    groups = world * groups_per_rank
+    keys = engine.partition_keys(my_text, k, groups)
+    send = [sum(keys.sizes[r * groups_per_rank:(r + 1) * groups_per_rank]) for r in range(world)]
+    matrix = _agree(dist, (send, keys.exception_symbols))
+    recv = [matrix[src][0][rank] for src in range(world)]
+    send_t = _to_tensor(engine, keys.ptr, keys.total, device)
+    keys.close()
+    recv_t = torch.empty(sum(recv), dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_to_all_single(recv_t, send_t, recv, send)
+    else:
+        recv_t.copy_(send_t)
+    del send_t
+    torch.cuda.synchronize(device)
+    sample = engine.sample(k, min_count)
+    sample.add_keys(recv_t.data_ptr(), int(recv_t.numel()))
+    del recv_t
+    if any(m[1] > 0 for m in matrix):                    # literal-byte windows: unfiltered local tables -> sum -> filter
+        t = engine.count_exceptions(my_text, k)
+        wk, wc = t.wide_arrays()
+        t.close()
+        gathered = _agree(dist, (wk, wc))
+        if rank == 0:
+            sk, sc = _sum_rows([g[0] for g in gathered], [g[1] for g in gathered], k)
+            keep = sc >= np.uint64(max(1, min_count))
+            if keep.any():
+                sample.add_rows(sk[keep], sc[keep])
+    table = sample.finish()
+    part = merge_table_device(engine, table, dist, device)
+    table.close()
+    if out_path:
+        write_tsv_sharded(part, out_path, basename, dist)
+    return part

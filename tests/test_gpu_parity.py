@@ -556,6 +556,22 @@ def test_sharded_sample_device_exchange(engine, tmp_path):
                 assert out.read_bytes() == orc.tsv_bytes("s", want)
             else:
                 assert not out.exists()
+        # one piece split by position, keys exchanged before the filter (whole-piece counts)
+        whole = b"".join(reads)
+        assert b"".join(mcd.split_at_headers(whole, 3)) == whole
+        for k, c in ((21, 2), (31, 3), (12, 4)):
+            out = tmp_path / f"p_{k}_{c}.tsv"
+            part = mcd.count_piece_position_sharded(engine, whole, k, c, dist, dev, out_path=out, basename="s")
+            want = orc.find_kmers_text(whole.decode(), k, c)
+            assert part.to_dict() == want, diff_msg(part.to_dict(), want)
+            assert out.read_bytes() == orc.tsv_bytes("s", want)
+        engine.set_option("hash_bucket_keys", 4)          # received keys exceed one hash batch: local level-0 partition
+        try:
+            part = mcd.count_piece_position_sharded(engine, whole, 21, 2, dist, dev)
+            want = orc.find_kmers_text(whole.decode(), 21, 2)
+            assert part.to_dict() == want, diff_msg(part.to_dict(), want)
+        finally:
+            reset(engine)
     finally:
         if created:
             dist.destroy_process_group()

@@ -61,6 +61,40 @@ def main():
             good = got == exp
             ok &= good
             print(f"k={k} c={c}: rows {len(want)} {'OK' if good else 'MISMATCH'}", flush=True)
+    # one piece split by position: keys are exchanged before the filter
+    whole = b"".join(reads)
+    mine_text = mcd.split_at_headers(whole, world)[rank]
+    for k, c in ((21, 2), (31, 3), (12, 4)):
+        out = tmp / f"position_{k}_{c}.tsv"
+        if rank == 0 and out.exists():
+            out.unlink()
+        dist.barrier()
+        mcd.count_piece_position_sharded(engine, mine_text, k, c, dist, dev, out_path=out, basename="s")
+        dist.barrier()
+        if rank == 0:
+            want = orc.find_kmers_text(whole.decode(), k, c)
+            got = out.read_bytes() if out.exists() else b""
+            exp = orc.tsv_bytes("s", want) if want else b""
+            good = got == exp
+            ok &= good
+            print(f"position-sharded k={k} c={c}: rows {len(want)} {'OK' if good else 'MISMATCH'}", flush=True)
+    # throughput of the position-sharded path on synthetic reads (per rank: 4 M reads = 0.6 Gbp)
+    import bench
+    genomes = bench.make_genomes(dev, 0.05)
+    big = bench.make_reads_text(dev, genomes, 4_000_000, rank * 4_000_000)
+    torch.cuda.synchronize()
+    for it in range(2):
+        dist.barrier()
+        t0 = time.perf_counter()
+        part = mcd.count_piece_position_sharded(engine, big, 31, 2, dist, dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        rows = part.rows
+        part.close()
+    if rank == 0:
+        print(f"position-sharded -c 2: {world} x 0.6 Gbp in {dt * 1e3:.1f} ms = {world * 0.6 / dt:.2f} Gbases/s, rows on rank 0: {rows}", flush=True)
+    del big, genomes
     # timing: exchange of a large table of random 62-bit keys
     n = 20_000_000
     g = torch.Generator(device=dev)
