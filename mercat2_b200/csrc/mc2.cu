@@ -45,7 +45,7 @@ struct mc2_engine {
     int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
     // stats
-    u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0;
+    u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0, ovf_buckets = 0;
     double device_us = 0;
     // pinned scratch
     void* pin_small = nullptr;                 // 4 KiB for scalar readbacks
@@ -254,6 +254,7 @@ struct mc2_sample {
     std::vector<FastPart> fast;
     std::vector<WidePart> wide;
     u64 n_chunks = 0;
+    double bucket_scale = 1.0;             // shrinks when many hash buckets overflow (heavily duplicated keys)
 };
 
 struct mc2_table {
@@ -537,7 +538,10 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
     const u64 mult = ks ? HC_MULT2 : HC_MULT1;
     const bool stream_order = pv || (ks && ks->stream_order);
-    const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, e->opt_hash_bucket_keys * HC_NB2)));
+    // (`cap` of a symbol stream counts ~25 % more positions than windows; a key array is exact, so aim lower there to
+    // keep the same head room below the 4096 keys a bucket may hold)
+    const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * (ks ? 0.8 : 1.0)));
+    const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
     DBuf<u32> ghist(e, nb), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
     struct Tail { ull total, out_n; u32 ovf_n, pad; };
@@ -721,6 +725,8 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     }
     const Tail t = read_scalar<Tail>(e, tail.p);
     if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
+    if (ks && getenv("MC2_DEBUG_PHASES"))
+        fprintf(stderr, "[phase]   group: %llu keys, %u buckets, %llu survivors, %u overflowed buckets\n", (ull)cap, nb, (ull)t.out_n, t.ovf_n);
     if (dbg) {                                                    // the sort path on the same keys must agree
         mc2_sample tmp;
         tmp.e = e; tmp.k = k; tmp.c = s->c;
@@ -736,15 +742,33 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         part.sorted = false;
         s->fast.push_back(std::move(part));
     }
-    if (t.ovf_n) {                                             // tables that filled up: redo those ranges by sorting
+    if (t.ovf_n) {
+        // Buckets the tables could not take (more keys than the prefetch registers hold, or too many distinct
+        // repeats): their keys are gathered into ONE array and counted by a single sort + run-length pass (buckets
+        // hold disjoint key sets).  Heavily duplicated data makes bucket sizes spread (sigma ~ sqrt(size * copies)),
+        // so the overflow rate also steers the bucket size of the sample's next chunks.
         std::vector<u32> ovf(t.ovf_n), base(nb + 1);
         d2h(e, ovf.data(), ovf_list.p, t.ovf_n);
         d2h(e, base.data(), sub_base.p, nb + 1);
-        for (u32 b : ovf) {
-            const u64 m = base[b + 1] - base[b];
-            if (stream_order && m) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, keys2.p + base[b], m, k);
-            count_key_range_sorted(e, s, keys2.p + base[b], m, kb);
+        std::vector<u64> src_off(t.ovf_n), dst_off(t.ovf_n);
+        u64 m = 0;
+        for (u32 i = 0; i < t.ovf_n; ++i) {
+            src_off[i] = base[ovf[i]];
+            dst_off[i] = m;
+            m += base[ovf[i] + 1] - base[ovf[i]];
         }
+        if (m) {
+            DBuf<u64> so(e, t.ovf_n), dof(e, t.ovf_n), gathered(e, m);
+            CUDA_CHECK(cudaMemcpyAsync(so.p, src_off.data(), t.ovf_n * 8ull, cudaMemcpyHostToDevice, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(dof.p, dst_off.data(), t.ovf_n * 8ull, cudaMemcpyHostToDevice, e->stream));
+            LAUNCH(e, gather_ranges_kernel, (unsigned)std::min<u64>(div_up(m, 256), 65535), 256, 0, (const u64*)keys2.p, (const u64*)so.p,
+                   (const u64*)dof.p, t.ovf_n, m, gathered.p);
+            if (stream_order) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, gathered.p, m, k);
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));          // (host vectors were the sources of async copies)
+            count_key_range_sorted(e, s, gathered.p, m, kb);
+        }
+        e->ovf_buckets += t.ovf_n;
+        if ((u64)t.ovf_n * 200 > nb && s->bucket_scale > 0.3) s->bucket_scale *= 0.8;      // > 0.5 % of the buckets overflowed
     }
 }
 
@@ -997,10 +1021,12 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
         const u64 avail = (u64)free_b + (reserved > used ? (u64)(reserved - used) : 0);
         if (total * 8 + extra + (1ull << 30) > avail) return false;
     }
+    pt.mark("level-0 memory check");
     out.keys0.alloc(e, total);
     DBuf<u64> gbase_dev(e, g0 + 1);
     DBuf<u32> cur0(e, g0);
     cur0.zero();
+    pt.mark("level-0 allocation");
     CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if (ks) {
         LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb0, g0, mult, cur0.p,
@@ -1597,6 +1623,7 @@ int64_t mc2_engine_get_stat(mc2_engine* e, const char* name) {
     if (n == "h2d_bytes") return (int64_t)e->h2d_bytes;
     if (n == "d2h_bytes") return (int64_t)e->d2h_bytes;
     if (n == "chunks") return (int64_t)e->chunks;
+    if (n == "overflow_buckets") return (int64_t)e->ovf_buckets;
     if (n == "device_us") return (int64_t)e->device_us;
     if (n == "num_sms") return e->num_sms;
     return -1;

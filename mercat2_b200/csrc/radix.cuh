@@ -277,3 +277,13 @@ __global__ void lower_bound_kernel(const u64* __restrict__ keys, u64 n, const u6
     }
     out[i] = lo;
 }
+
+// concatenate ranges [src_off[r], src_off[r] + len) of src into dst at dst_off[r] (one CTA per 2048 output items)
+__global__ void gather_ranges_kernel(const u64* __restrict__ src, const u64* __restrict__ src_off, const u64* __restrict__ dst_off,
+                                     u32 nranges, u64 total, u64* __restrict__ dst) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        u32 lo = 0, hi = nranges;                              // last range with dst_off <= i
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (dst_off[mid] <= i) lo = mid; else hi = mid; }
+        dst[i] = src[src_off[lo] + (i - dst_off[lo])];
+    }
+}

@@ -371,10 +371,23 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
     unfiltered, summed across ranks and filtered on rank 0.  The surviving rows are then re-partitioned by key range
     (merge_table_device) so that rank order = sorted order, and the TSV is written by byte ranges.
     Returns this rank's part of the final table."""
+    import os
+    import time
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
+    trace = os.environ.get("MC2_DEBUG_PHASES") and rank == 0
+    t_last = [time.perf_counter()]
+
+    def mark(what):
+        if trace:
+            torch.cuda.synchronize(device)
+            now = time.perf_counter()
+            print(f"[phase] sharded: {what:<24s} {(now - t_last[0]) * 1e3:9.3f} ms", flush=True)
+            t_last[0] = now
+
     groups = world * groups_per_rank
     keys = engine.partition_keys(my_text, k, groups)
+    mark("partition_keys")
     send = [sum(keys.sizes[r * groups_per_rank:(r + 1) * groups_per_rank]) for r in range(world)]
     matrix = _agree(dist, (send, keys.exception_symbols))
     recv = [matrix[src][0][rank] for src in range(world)]
@@ -387,9 +400,11 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
         recv_t.copy_(send_t)
     del send_t
     torch.cuda.synchronize(device)
+    mark("all_to_all")
     sample = engine.sample(k, min_count)
     sample.add_keys(recv_t.data_ptr(), int(recv_t.numel()))
     del recv_t
+    mark("add_keys")
     if any(m[1] > 0 for m in matrix):                    # literal-byte windows: unfiltered local tables -> sum -> filter
         t = engine.count_exceptions(my_text, k)
         wk, wc = t.wide_arrays()
@@ -401,8 +416,10 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
             if keep.any():
                 sample.add_rows(sk[keep], sc[keep])
     table = sample.finish()
+    mark("finish")
     part = merge_table_device(engine, table, dist, device)
     table.close()
+    mark("key-range merge")
     if out_path:
         write_tsv_sharded(part, out_path, basename, dist)
     return part

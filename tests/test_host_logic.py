@@ -102,3 +102,32 @@ def test_cli_flags_and_classification():
     assert cli.classify("x/Test_R1.fastq") == ("fastq", "Test_R1")
     assert cli.classify("x/a.b.fasta") == ("nucleotide", "a.b")
     assert cli.classify("x/readme.txt")[0] is None
+
+
+def test_distributed_host_helpers():
+    """host-side pieces of the multi-GPU paths: header-aligned position split, packed-key text, literal-row sums"""
+    import numpy as np
+    from mercat2_b200 import distributed as mcd
+    from oracle import mercat2_oracle as orc
+    text = b">a x\nACGT\nAC\n>b\nGG\n>c y z\nTTTT\nAA\n>d\nC\n"
+    for world in (1, 2, 3, 5, 9):
+        parts = mcd.split_at_headers(text, world)
+        assert len(parts) == world and b"".join(parts) == text
+        assert all((not p) or p[:1] == b">" for p in parts)
+        # splitting at header lines loses no window: per-part counts (unfiltered) sum to the whole
+        whole = orc.find_kmers_text(text.decode(), 2, 1)
+        summed = orc.merge_counts(orc.find_kmers_text(p.decode(), 2, 1) for p in parts if p)
+        assert summed == whole
+    # packed key -> text, all layouts (csrc/tsv.cuh::tsv_decode)
+    assert mcd.decode_key(0b00011011, 4, mcd.ENC_NT2, mcd.KEY_CODE) == b"ACGT"
+    assert mcd.decode_key((12 << 10) | (0 << 5) | 25, 3, mcd.ENC_AA5, mcd.KEY_CODE) == b"MAZ"
+    assert mcd.decode_key((ord("a") << 8) | ord("N"), 2, mcd.ENC_BYTE, mcd.KEY_CODE) == b"aN"
+    assert mcd.decode_key(2 * 26 * 26 + 0 * 26 + 25, 3, mcd.ENC_AA5, mcd.KEY_DENSE_AA) == b"CAZ"
+    # literal-byte rows summed by text
+    k = 3
+    a = (np.frombuffer(b"ANTNNNANT", np.uint8).reshape(-1, k), np.array([2, 5, 1], np.uint64))
+    b = (np.frombuffer(b"NNNacg", np.uint8).reshape(-1, k), np.array([7, 4], np.uint64))
+    sk, sc = mcd._sum_rows([a[0], b[0]], [a[1], b[1]], k)
+    got = {bytes(r): int(c) for r, c in zip(sk, sc)}
+    assert got == {b"ANT": 3, b"NNN": 12, b"acg": 4}
+    assert [bytes(r) for r in sk] == sorted(got)

@@ -119,6 +119,13 @@ def main():
     run(engine, "S3': 10 M reads x 150 bp, k=12 -c 10 -s 100", reads, int(10e6 * sc) * 150, 12, 10, 100 << 20, args.reps)
     run(engine, "10 M reads x 150 bp, k=31 -c 2 -s 100 (survivors) + TSV", reads, int(10e6 * sc) * 150, 31, 2, 100 << 20, args.reps, tsv=True)
     del reads, genomes
+    for scale, label in ((0.025, "24x"), (0.005, "120x")):          # heavily duplicated keys: isolate-genome coverage per piece
+        genomes = bench.make_genomes(dev, scale)
+        reads = bench.make_reads_text(dev, genomes, int(4e6 * sc), 0)
+        ov0 = engine.stat("overflow_buckets")
+        run(engine, f"4 M reads x 150 bp at {label} coverage, k=31 -c 10 -s 100", reads, int(4e6 * sc) * 150, 31, 10, 100 << 20, args.reps, tsv=True)
+        print(json.dumps({"overflow_buckets": engine.stat("overflow_buckets") - ov0}), flush=True)
+        del reads, genomes
 
     text, n = protein_text(dev, int(50000 * sc), 1000)
     run(engine, "S5 x10: 50 k proteins, k=5 -c 10 (dense 26^5)", text, n, 5, 10, 0, args.reps, tsv=True)

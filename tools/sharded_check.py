@@ -83,7 +83,7 @@ def main():
     genomes = bench.make_genomes(dev, 0.05)
     big = bench.make_reads_text(dev, genomes, 4_000_000, rank * 4_000_000)
     torch.cuda.synchronize()
-    for it in range(2):
+    for it in range(4):
         dist.barrier()
         t0 = time.perf_counter()
         part = mcd.count_piece_position_sharded(engine, big, 31, 2, dist, dev)
