@@ -280,8 +280,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         import psutil
-        need = nbytes * (world if world > 1 else 1)
-        if psutil.virtual_memory().available > 3 * need + (8 << 30):
+        # every rank pins its own shard; the decision is taken once (rank 0) so that all ranks agree
+        fits = [psutil.virtual_memory().available > int(1.25 * nbytes * world) + (16 << 30)]
+        if world > 1:
+            dist.broadcast_object_list(fits, src=0)
+        if fits[0]:
             host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             host.copy_(text)
             torch.cuda.synchronize()
