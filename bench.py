@@ -221,6 +221,7 @@ def main():
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_bound = mercat2_b200.bind_to_gpu_numa(local) if world > 1 else False     # pinned shards next to their GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -353,7 +354,7 @@ def main():
             "config": {"workload": f"cfg4 shard: synthetic 150-bp metagenome reads, nucleotide k={args.k} -c {args.c} -s {args.s}",
                        "reads_per_gpu": n_reads, "bases_per_gpu_per_step": bases_per_step, "text_bytes_per_gpu": nbytes,
                        "chunks_per_gpu": n_chunks, "surviving_rows": rows, "parallelism": f"chunk-sharded x{world}" + (" + NCCL key-range all-to-all of the filtered tables" if world > 1 else ""),
-                       "l2_policy": "input per step (>= 1 GB) is larger than L2; no flush needed"},
+                       "numa_bound": numa_bound, "l2_policy": "input per step (>= 1 GB) is larger than L2; no flush needed"},
             "clocks": clocks,
             "gpu_launches": launches,
             "device_ms_per_step": dev_us / args.steps / 1e3,

@@ -12,5 +12,5 @@ fallback: without the built library and a CUDA device these calls raise.
 __version__ = "0.1.0"
 
 from . import _native  # noqa: F401
-from ._native import Engine, Mc2Error, NonAsciiError, default_engine  # noqa: F401
+from ._native import Engine, Mc2Error, NonAsciiError, bind_to_gpu_numa, default_engine  # noqa: F401
 from . import mercat2_kmers, mercat2_Chunker, mercat2_metrics, mercat2_fasta, pipeline  # noqa: F401

@@ -446,3 +446,23 @@ def default_engine(device: int | None = None) -> Engine:
     if eng is None:
         eng = _default_engines[device] = Engine(device)
     return eng
+
+
+def bind_to_gpu_numa(device: int) -> bool:
+    """Pin the calling process to the CPUs next to GPU `device` (NVML's ideal affinity).  Host buffers allocated
+    afterwards (pinned memory in particular) land on that NUMA node, so uploads do not cross sockets when several
+    ranks feed several GPUs.  Opt-in: it changes the process's CPU affinity.  Returns False if NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device
+        if visible:
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                index = int(ids[device])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
