@@ -625,13 +625,14 @@ __global__ void hc_verify_kernel(const u64* __restrict__ keys, const u32* __rest
     if (i < sub_base[lo_b] || i >= sub_base[hi_b]) atomicAdd(bad_count, 1ull);
 }
 
-// ---- hc_count3: 16-bit counter pre-filter, no returning atomics on the common path (min_count >= 2) --------------
-// Measured: shared-memory atomics that RETURN a value (test-and-set on the bitmap of hc_count2, rank counters) run
-// at ~1-2 cycles per lane, ~10x slower than reductions without return (~5 per clock and SM).  Here every key first
-// adds 1 to a 16-bit hashed counter with RED (no return); after a barrier it reads the counter back with a plain
+// ---- hc_count3: 16-bit counter pre-filter (experiment, engine option count_variant=3; slower than hc_count2) -------
+// Every key first adds 1 to a 16-bit hashed counter with RED; after a barrier it reads the counter back with a plain
 // load.  A key occurring m >= 2 times reads >= m >= 2 at EVERY occurrence, so all its occurrences enter the exact
 // table and the table count is exact without a second pass; a key occurring once enters only on a counter collision
 // (~5 %) and is dropped by the threshold.  Counters cannot wrap: a bucket holds at most 4096 keys.
+// It was built on the guess that shared-memory atomics which return a value are much slower than reductions; the
+// microbenchmark (tools/microbench.cu) shows both at ~2.2 T lane-ops/s, and with 128 KB of counters only one CTA
+// fits per SM, so the extra barrier is not hidden: 0.50 ms vs 0.38 ms per 76.7 M keys when it was measured.
 #define HC3_THREADS 1024
 #define HC3_PREFETCH 4
 #define HC3_CNT_LOG2 16                                   // 2^16 counters of 16 bits = 128 KB
