@@ -90,6 +90,13 @@ typedef struct mc2_sample mc2_sample;
 int mc2_sample_begin(mc2_engine* e, int k, int64_t min_count, mc2_sample** out);
 int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int space, uint64_t chunk_bytes,
                         uint64_t* n_chunks);
+/* The same for a FILE read by the engine itself (lib/mercat2_kmers.py:47: gzip.open(file,'rt') if the suffix is
+ * '.gz' else open(file); gunzip = 1 / 0 / -1 = decide by the ".gz" suffix): a reader thread fills pinned buffers
+ * (read(2) or zlib inflate), each goes to the device with cudaMemcpyAsync while the next one is being filled, and
+ * the text that has arrived is chunked and counted; the device keeps a sliding window of the text, not the file.
+ * chunk_bytes: the caller applies the reference's trigger on the on-disk size (bin/mercat2.py:101), 0 = one piece. */
+int mc2_sample_add_file(mc2_sample* s, const char* path, int gunzip, uint64_t chunk_bytes, uint64_t* n_chunks,
+                        uint64_t* text_bytes);
 /* Add already counted rows (rows*k bytes of k-mer text + rows counts, host memory) to the sample: the serial dict
  * merge of bin/mercat2.py:121-127 for tables that were counted elsewhere (another GPU / rank).  Equal k-mers are
  * summed by mc2_sample_finish on the device. */

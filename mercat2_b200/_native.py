@@ -35,6 +35,7 @@ SYMBOLS = [
     ("mc2_chunk_offsets", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64, _U64, _PU64]),
     ("mc2_sample_begin", _INT, [_VP, _INT, _I64, _PP]),
     ("mc2_sample_add_text", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64]),
+    ("mc2_sample_add_file", _INT, [_VP, C.c_char_p, _INT, _U64, _PU64, _PU64]),
     ("mc2_sample_add_rows", _INT, [_VP, _VP, _VP, _U64]),
     ("mc2_sample_finish", _INT, [_VP, _PP]),
     ("mc2_sample_abort", None, [_VP]),
@@ -397,6 +398,15 @@ class Sample:
         nchunks = C.c_uint64(0)
         lib = self._engine._lib
         _check(lib, lib.mc2_sample_add_text(self._h, addr, n, space, chunk_bytes, C.byref(nchunks)))
+        return int(nchunks.value)
+
+    def add_file(self, path, chunk_bytes: int = 0, gunzip=None) -> int:
+        """Stream a file through the engine's own reader (pinned buffers, inflate for '.gz'); returns the pieces counted."""
+        nchunks, nbytes = C.c_uint64(0), C.c_uint64(0)
+        lib = self._engine._lib
+        flag = -1 if gunzip is None else int(bool(gunzip))
+        _check(lib, lib.mc2_sample_add_file(self._h, os.fsencode(str(path)), flag, chunk_bytes, C.byref(nchunks), C.byref(nbytes)))
+        self.text_bytes = int(nbytes.value)
         return int(nchunks.value)
 
     def add_rows(self, kmers, counts):

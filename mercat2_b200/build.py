@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmercat2_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "mc2.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "mc2.cu"), "-lz"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     proc = subprocess.run(cmd, capture_output=True, text=True)

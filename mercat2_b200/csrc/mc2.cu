@@ -53,6 +53,7 @@ struct mc2_engine {
     size_t ride_len = 0;
     bool ride_done = false;
     u8* pin_stage[2] = {nullptr, nullptr};     // H2D staging for pageable sources
+    u8* file_pin[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned pool of the streaming file reader (lazy)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     static constexpr u64 STAGE_BYTES = 32ull << 20;
@@ -1405,6 +1406,8 @@ static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u
     if (bounds_out) *bounds_out = bounds;
 }
 
+#include "filestream.inl"
+
 static mc2_table* sample_finish(mc2_sample* s) {
     mc2_engine* e = s->e;
     PhaseTimer pt(e);
@@ -1585,6 +1588,8 @@ void mc2_engine_destroy(mc2_engine* e) {
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (e->pin_stage[i]) cudaFreeHost(e->pin_stage[i]);
+        if (e->file_pin[2 * i]) cudaFreeHost(e->file_pin[2 * i]);
+        if (e->file_pin[2 * i + 1]) cudaFreeHost(e->file_pin[2 * i + 1]);
         if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
     }
     if (e->pin_small) cudaFreeHost(e->pin_small);
@@ -1680,6 +1685,22 @@ int mc2_sample_add_text(mc2_sample* s, const void* text, uint64_t nbytes, int sp
     u64 nc = 0;
     sample_add(s, text, nbytes, space, chunk_bytes, &nc, nullptr);
     if (n_chunks) *n_chunks = nc;
+    API_END
+}
+
+int mc2_sample_add_file(mc2_sample* s, const char* path, int gunzip, uint64_t chunk_bytes, uint64_t* n_chunks, uint64_t* text_bytes) {
+    API_BEGIN
+    if (!s || !path) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(s->e->device));
+    bool gz = gunzip > 0;
+    if (gunzip < 0) {
+        const size_t n = strlen(path);
+        gz = n >= 3 && strcmp(path + n - 3, ".gz") == 0;
+    }
+    u64 nc = 0, nb = 0;
+    sample_add_file(s, path, gz, chunk_bytes, &nc, &nb);
+    if (n_chunks) *n_chunks = nc;
+    if (text_bytes) *text_bytes = nb;
     API_END
 }
 

@@ -40,5 +40,7 @@ def find_kmers(file: Path, kmer: int, min_count: int) -> dict:
     (``.suffix`` decides gzip)."""
     if kmer < 1:
         raise ValueError("kmer must be >= 1")
-    table = _native.default_engine().count_text(read_text_bytes(file), kmer, min_count)
-    return table.to_dict()
+    file = Path(file)
+    sample = _native.default_engine().sample(kmer, min_count)
+    sample.add_file(file, 0, gunzip=file.suffix == ".gz")          # one piece = the whole file (kmers.py:47-78)
+    return sample.finish().to_dict()

@@ -10,7 +10,6 @@ import os
 from pathlib import Path
 
 from . import _native
-from .mercat2_kmers import read_text_bytes
 
 
 def chunk_trigger(filename, chunk_size_mb: int) -> int:
@@ -27,7 +26,8 @@ def count_files(files, kmer: int, min_count: int, chunk_size_mb: int = 0, engine
     sample = engine.sample(kmer, min_count)
     pieces = 0
     for file in files:
-        pieces += sample.add_text(read_text_bytes(Path(file)), chunk_trigger(file, chunk_size_mb))
+        # the engine reads the file itself: reader thread -> pinned buffers (inflate for '.gz') -> device window
+        pieces += sample.add_file(Path(file), chunk_trigger(file, chunk_size_mb), gunzip=Path(file).suffix == ".gz")
     return sample.finish(), pieces
 
 

@@ -603,3 +603,39 @@ def test_big_chunk_level0_partition(engine, k, c):
         engine.set_option("big_chunks", 1)
         engine.set_option("span_bytes", 1 << 30)
         reset(engine)
+
+
+def test_streaming_file_reader(engine, tmp_path):
+    """mc2_sample_add_file (reader thread -> pinned buffers -> device window) against add_text of the same bytes:
+    plain and gzip files, chunked and unchunked, an empty file, a missing file"""
+    import mercat2_b200
+    reset(engine)
+    text = synth_reads(30000, 150, seed=41, n_rate=0.001, lower_rate=0.0, genome_len=200000)      # ~4.9 MB
+    plain = tmp_path / "reads.fna"
+    plain.write_bytes(text)
+    gz = tmp_path / "reads.fna.gz"
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(text)
+    for k, c, chunk in ((21, 2, 0), (21, 2, 1 << 20), (5, 3, 1 << 20), (31, 1, 700000)):
+        s0 = engine.sample(k, c)
+        pieces0 = s0.add_text(text, chunk)
+        want = s0.finish().to_dict()
+        for path in (plain, gz):
+            s1 = engine.sample(k, c)
+            pieces1 = s1.add_file(path, chunk)
+            assert s1.text_bytes == len(text)
+            got = s1.finish().to_dict()
+            assert pieces1 == pieces0, (path.name, k, c, chunk, pieces1, pieces0)
+            assert got == want, f"{path.name} k={k} c={c} chunk={chunk}: {diff_msg(got, want)}"
+    empty = tmp_path / "empty.fna"
+    empty.write_bytes(b"")
+    s2 = engine.sample(5, 1)
+    assert s2.add_file(empty, 0) == 1 and s2.finish().rows == 0
+    s3 = engine.sample(5, 1)
+    with pytest.raises(mercat2_b200.Mc2Error):
+        s3.add_file(tmp_path / "missing.fna", 0)
+    bad = tmp_path / "broken.fna.gz"
+    bad.write_bytes(gz.read_bytes()[: gz.stat().st_size // 2])
+    s4 = engine.sample(5, 1)
+    with pytest.raises(mercat2_b200.Mc2Error):
+        s4.add_file(bad, 0)

@@ -127,6 +127,25 @@ def main():
         print(json.dumps({"overflow_buckets": engine.stat("overflow_buckets") - ov0}), flush=True)
         del reads, genomes
 
+    # a FILE through the engine's own reader (page cache -> pinned buffers -> device), chunked like the CLI would
+    genomes = bench.make_genomes(dev, 0.05)
+    reads = bench.make_reads_text(dev, genomes, int(6e6 * sc), 0)
+    fpath = TSV_PATH + ".reads.fna"
+    with open(fpath, "wb") as f:
+        f.write(reads.cpu().numpy().tobytes())
+    nbytes = os.path.getsize(fpath)
+    del reads, genomes
+    for _ in range(2):
+        t0 = time.perf_counter()
+        smp = engine.sample(31, 10)
+        pieces = smp.add_file(fpath, 100 << 20)
+        tbl = smp.finish()
+        dt = time.perf_counter() - t0
+        tbl.close()
+    print(json.dumps({"workload": "file reader: 6 M reads FASTA file (page cache), k=31 -c 10 -s 100", "file_bytes": nbytes, "pieces": pieces,
+                      "seconds": round(dt, 4), "symbols_per_s": round(6e6 * sc * 150 / dt), "file_GB_per_s": round(nbytes / dt / 1e9, 2)}), flush=True)
+    os.unlink(fpath)
+
     text, n = protein_text(dev, int(50000 * sc), 1000)
     run(engine, "S5 x10: 50 k proteins, k=5 -c 10 (dense 26^5)", text, n, 5, 10, 0, args.reps, tsv=True)
     run(engine, "50 k proteins, k=3 -c 10 (dense, shared memory)", text, n, 3, 10, 0, args.reps, tsv=True)
