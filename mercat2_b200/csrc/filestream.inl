@@ -68,7 +68,8 @@ struct FileSource {
 // gzip stream is sequential (T = 1).  No CUDA call happens on a reader thread.
 struct PinnedReader {
     static constexpr int NBUF = 4;
-    static constexpr u64 PIECE = 32ull << 20;
+    static constexpr u64 PIECE_MAX = 32ull << 20;             // size of a pinned buffer
+    u64 PIECE;                                                // bytes per piece (engine option file_piece_bytes; tests shrink it)
     FileSource* src;
     int nthreads;
     u8* buf[NBUF] = {nullptr, nullptr, nullptr, nullptr};
@@ -83,9 +84,9 @@ struct PinnedReader {
     std::condition_variable cv;
     std::vector<std::thread> th;
 
-    PinnedReader(mc2_engine* e, FileSource* s) : src(s), nthreads(s->gz ? 1 : NBUF) {
+    PinnedReader(mc2_engine* e, FileSource* s) : PIECE(std::min<u64>(PIECE_MAX, std::max<u64>(4096, e->opt_file_piece))), src(s), nthreads(s->gz ? 1 : NBUF) {
         for (int i = 0; i < NBUF; ++i) {                         // the pinned pool lives with the engine (allocated once)
-            if (!e->file_pin[i]) CUDA_CHECK(cudaMallocHost((void**)&e->file_pin[i], PIECE));
+            if (!e->file_pin[i]) CUDA_CHECK(cudaMallocHost((void**)&e->file_pin[i], PIECE_MAX));
             buf[i] = e->file_pin[i];
         }
         for (int j = 0; j < nthreads; ++j) th.emplace_back([this, j] { run(j); });
@@ -99,7 +100,7 @@ struct PinnedReader {
         for (auto& t : th) if (t.joinable()) t.join();
     }
     size_t fill(u64 piece, u8* dst) {
-        if (src->gz) return src->read_some(dst, PIECE);
+        if (src->gz) return src->read_some(dst, (size_t)PIECE);
         size_t got = 0;
         while (got < PIECE) {
             const ssize_t n = pread(src->fd, dst + got, PIECE - got, (off_t)(piece * PIECE + got));
@@ -187,7 +188,7 @@ struct StreamText {
     cudaEvent_t last_ev = nullptr;
 
     StreamText(mc2_engine* e_, PinnedReader* r, u64 initial) : e(e_), rd(r) {
-        cap = std::max<u64>(initial, 4 * PinnedReader::PIECE);
+        cap = std::max<u64>(initial, 4 * rd->PIECE);
         dev.alloc(e, cap + 16);
         for (auto& ev : slot_ev) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&last_ev, cudaEventDisableTiming));
@@ -218,7 +219,7 @@ struct StreamText {
         if (keep + more <= cap && head >= keep) {                  // non-overlapping move to the front
             if (keep) CUDA_CHECK(cudaMemcpyAsync(dev.p, dev.p + head, keep, cudaMemcpyDeviceToDevice, e->copy_stream));
         } else {
-            const u64 ncap = std::max<u64>(2 * cap, keep + more + PinnedReader::PIECE);
+            const u64 ncap = std::max<u64>(2 * cap, keep + more + rd->PIECE);
             DBuf<u8> bigger(e, ncap + 16);
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
             if (keep) CUDA_CHECK(cudaMemcpyAsync(bigger.p, dev.p + head, keep, cudaMemcpyDeviceToDevice, e->copy_stream));
@@ -268,9 +269,9 @@ static void sample_add_file(mc2_sample* s, const char* path, bool gunzip, u64 ch
     struct stat stt;
     u64 disk = 0;
     if (stat(path, &stt) == 0) disk = (u64)stt.st_size;
-    const u64 margin = 4ull << 20;
+    const u64 margin = std::min<u64>(4ull << 20, reader.PIECE);
     // window: a chunked file needs a few pieces; an unchunked one its whole text (size known for plain files)
-    const u64 initial = chunk_bytes ? 2 * (chunk_bytes + margin) + 2 * PinnedReader::PIECE : (gunzip ? disk * 4 : disk) + PinnedReader::PIECE;
+    const u64 initial = chunk_bytes ? 2 * (chunk_bytes + margin) + 2 * reader.PIECE : (gunzip ? disk * 2 : disk) + reader.PIECE;   // (a gzip text of unknown size: the window grows by doubling)
     StreamText st(e, &reader, initial);
     u64 pieces = 0;
     while (true) {

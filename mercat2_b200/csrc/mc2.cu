@@ -39,6 +39,7 @@ struct mc2_engine {
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
     int opt_big_chunks = 1;                // chunks beyond one hash batch: level-0 key partition in HBM (0 = sort fallback)
+    u64 opt_file_piece = 32ull << 20;      // bytes per piece of the streaming file reader
     u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
     int opt_count_variant = 2;             // min_count >= 2: 2 = bitmap pre-filter (faster as measured), 3 = 16-bit counter pre-filter
     int opt_scatter_variant = 0;           // bit0: stage destination indices, bit1: max shared-memory carveout
@@ -1614,6 +1615,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
     else if (n == "count_variant") e->opt_count_variant = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
+    else if (n == "file_piece_bytes") e->opt_file_piece = (u64)std::max<int64_t>(4096, value);
     else if (n == "span_bytes") e->opt_span_bytes = value < 4096 ? 4096 : (value > (3ull << 30) ? (3ull << 30) : (u64)value);
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
     else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }

@@ -627,6 +627,21 @@ def test_streaming_file_reader(engine, tmp_path):
             got = s1.finish().to_dict()
             assert pieces1 == pieces0, (path.name, k, c, chunk, pieces1, pieces0)
             assert got == want, f"{path.name} k={k} c={c} chunk={chunk}: {diff_msg(got, want)}"
+    # small pieces: the same files now span ~75 pieces, the device window is compacted and (unchunked) grown
+    engine.set_option("file_piece_bytes", 64 << 10)
+    try:
+        for k, c, chunk in ((21, 2, 0), (21, 2, 300000), (31, 1, 1 << 20)):
+            s0 = engine.sample(k, c)
+            pieces0 = s0.add_text(text, chunk)
+            want = s0.finish().to_dict()
+            for path in (plain, gz):
+                s1 = engine.sample(k, c)
+                pieces1 = s1.add_file(path, chunk)
+                got = s1.finish().to_dict()
+                assert pieces1 == pieces0 and s1.text_bytes == len(text)
+                assert got == want, f"small pieces {path.name} k={k} c={c} chunk={chunk}: {diff_msg(got, want)}"
+    finally:
+        engine.set_option("file_piece_bytes", 32 << 20)
     empty = tmp_path / "empty.fna"
     empty.write_bytes(b"")
     s2 = engine.sample(5, 1)
