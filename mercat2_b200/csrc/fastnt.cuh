@@ -320,6 +320,136 @@ fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
     }
 }
 
+// ---- K1f in ONE pass: classification, line state, symbol offsets by chained look-back, packed write -----------------
+// The two-pass version reads the text twice (count, then write at scanned offsets).  Here every tile publishes its
+// symbol count in a descriptor word (flag | value) and obtains its exclusive offset by walking back over its
+// predecessors' descriptors until it meets one that already carries an inclusive prefix ("decoupled look-back").
+// Tiles take their index from an atomic ticket, so a tile only ever waits for tiles that are already running or
+// done.  A bounded spin turns any protocol failure into the `complex` flag (the chunk is then redone by the general
+// parser) instead of a hang.  STATS: also the kept / non-ACGT totals of the count pass (first piece of a sample).
+#define FN_DESC_AGG (1ull << 62)
+#define FN_DESC_PREFIX (2ull << 62)
+#define FN_DESC_MASK ((1ull << 62) - 1)
+#define FN_SPIN_LIMIT (1u << 24)
+
+template <bool STATS>
+__global__ void __launch_bounds__(FN_THREADS)
+fn_parse_single_kernel(const u8* __restrict__ text, u64 len, u32 ntiles, ull* __restrict__ desc, u32* __restrict__ ticket,
+                       u32* __restrict__ codes, u32* __restrict__ bad, FnStats* stats) {
+    __shared__ u32 sm[FN_WARPS + 1];
+    __shared__ u32 s_state, s_tile_id;
+    __shared__ ull s_off, s_red[FN_WARPS];
+    __shared__ u32 s_c[260], s_b[132];
+    if (threadIdx.x == 0) s_tile_id = atomicAdd(ticket, 1u);
+    for (u32 i = threadIdx.x; i < 260; i += FN_THREADS) s_c[i] = 0;
+    for (u32 i = threadIdx.x; i < 132; i += FN_THREADS) s_b[i] = 0;
+    BLOCK_SYNC();
+    const u32 tile = s_tile_id;
+    const ParseTileView v = make_view(text, len);
+    const u64 tile_v = (u64)tile * FN_TILE;
+    const u64 p0 = tile_v + (u64)threadIdx.x * 16;
+    u32 w[4];
+    load16(v, p0, w);
+    const FnMasks m = fn_classify<true>(w);
+    if (threadIdx.x < 32) {
+        bool cx = false;
+        const u32 st = tile_v <= v.lo ? (u32)ST_S0 : fn_tile_state(text, tile_v - v.lo, cx);
+        if (threadIdx.x == 0) {
+            s_state = st;
+            if (cx) atomicAdd(&stats->complex, 1ull);
+        }
+    }
+    const u32 pre = block_exclusive_scan<FwdOp, FN_WARPS>(fn_summary(m), sm, nullptr);   // barriers publish s_state
+    const u32 state = FwdOp::apply(pre, s_state);
+    const FnEmit e = fn_emit_masks(m, state);
+    const u32 cnt = __popc(e.emit);
+    u32 total;
+    const u32 off = block_exclusive_scan<OpAdd, FN_WARPS>(cnt, sm, &total);
+    if (e.cx) atomicAdd(&stats->complex, 1ull);
+    // ---- chained offsets ----
+    if (threadIdx.x == 0) {
+        ull excl = 0;
+        if (tile == 0) {
+            atomicExch(&desc[0], FN_DESC_PREFIX | (ull)total);
+        } else {
+            atomicExch(&desc[tile], FN_DESC_AGG | (ull)total);
+            u32 spins = 0;
+            for (u32 p = tile; p-- > 0;) {
+                ull d;
+                while (((d = *(volatile ull*)&desc[p]) >> 62) == 0) {
+                    if (++spins > FN_SPIN_LIMIT) break;
+                    __nanosleep(20);
+                }
+                if ((d >> 62) == 0) { atomicAdd(&stats->complex, 1ull); break; }     // give up: the host falls back
+                excl += d & FN_DESC_MASK;
+                if (d & FN_DESC_PREFIX) break;
+            }
+            atomicExch(&desc[tile], FN_DESC_PREFIX | (excl + total));
+        }
+        s_off = excl;
+        if (tile == ntiles - 1) stats->n_sym = excl + total;
+    }
+    // ---- statistics ----
+    {
+        const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
+        if (STATS) {
+            ull t = (ull)kept | ((ull)slow << 32);
+            __syncwarp();
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+        } else {
+            __syncwarp();
+            if (__ballot_sync(0xffffffffu, slow != 0)) {                  // rare: only warps that see a non-ACGT byte report
+                u32 t = slow;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&stats->packed2, (ull)t << 32);
+            }
+        }
+    }
+    BLOCK_SYNC();                                                          // s_off, s_red
+    if (STATS && threadIdx.x == 0) {
+        ull t = 0;
+#pragma unroll
+        for (int i = 0; i < FN_WARPS; ++i) t += s_red[i];
+        if (t) {
+            atomicAdd(&stats->packed, t);
+            if (t >> 32) atomicAdd(&stats->packed2, t & 0xFFFFFFFF00000000ull);
+        }
+    }
+    if (total == 0) return;
+    const u64 s_tile = s_off;                                              // global symbol index of the tile's first symbol
+    const u64 base_sym = s_tile & ~31ull;
+    const u32 rel0 = (u32)(s_tile - base_sym);
+    if (cnt) {
+        const u32 rel = rel0 + off;
+        const u32 cf = fn_compress<2>(m.codes, e.emit);
+        const u32 bf = fn_compress<1>(e.bad, e.emit);
+        const u64 cv = (u64)(cnt == 16 ? cf : (cf & ((1u << (2 * cnt)) - 1u))) << (2 * (rel & 15));
+        atomicOr(&s_c[rel >> 4], (u32)cv);
+        if (cv >> 32) atomicOr(&s_c[(rel >> 4) + 1], (u32)(cv >> 32));
+        const u64 bv = (u64)(bf & ((1u << cnt) - 1u)) << (rel & 31);
+        atomicOr(&s_b[rel >> 5], (u32)bv);
+        if (bv >> 32) atomicOr(&s_b[(rel >> 5) + 1], (u32)(bv >> 32));
+    }
+    BLOCK_SYNC();
+    const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;
+    u32* gc = codes + (base_sym >> 4);
+    for (u32 i = fw + threadIdx.x; i < nw; i += FN_THREADS) {
+        const u32 val = s_c[i];
+        if (i == fw || i == nw - 1) { if (val) atomicOr(&gc[i], val); }
+        else gc[i] = val;
+    }
+    const u32 nbw = (rel0 + total + 31) >> 5;
+    u32* gb = bad + (base_sym >> 5);
+    for (u32 i = threadIdx.x; i < nbw; i += FN_THREADS) {
+        const u32 val = s_b[i];
+        if (i == 0 || i == nbw - 1) { if (val) atomicOr(&gb[i], val); }
+        else gb[i] = val;
+    }
+}
+
 // ---- dense tables straight from the packed stream (4^k bins, k <= 15) -----------------------------------------
 // Index = the window's code with its first symbol most significant (the layout of the sample table), obtained from
 // the stream-order key by one bit reversal.  SMEM: per-CTA histogram replicated per warp group, flushed once;

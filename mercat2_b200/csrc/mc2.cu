@@ -39,6 +39,7 @@ struct mc2_engine {
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
     int opt_big_chunks = 1;                // chunks beyond one hash batch: level-0 key partition in HBM (0 = sort fallback)
+    int opt_parse_single = 0;              // packed lane: 1 = one pass over the text with chained look-back (measured slower: 0.39 vs 0.28 ms per 100 MiB)
     u64 opt_file_piece = 32ull << 20;      // bytes per piece of the streaming file reader
     u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
     int opt_count_variant = 2;             // min_count >= 2: 2 = bitmap pre-filter (faster as measured), 3 = 16-bit counter pre-filter
@@ -926,6 +927,33 @@ static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<Fn
     return fs;
 }
 
+// count + write in one pass over the text (chained look-back for the symbol offsets, see fn_parse_single_kernel)
+static FnStats fn_single_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
+    const u64 mis = (u64)(uintptr_t)sp.text & 15ull;
+    sp.ntiles = div_up(mis + sp.len, FN_TILE);
+    const u64 cap_sym = sp.len + 1;                              // every symbol comes from its own text byte
+    sp.codes.alloc(e, div_up(cap_sym, 16) + 4);
+    sp.bad.alloc(e, div_up(cap_sym, 32) + 4);
+    sp.codes.zero();
+    sp.bad.zero();
+    DBuf<ull> desc(e, sp.ntiles);
+    DBuf<u32> ticket(e, 1);
+    desc.zero();
+    ticket.zero();
+    if (with_stats)
+        LAUNCHN(e, "fn_parse_single_kernel<stats>", fn_parse_single_kernel<true>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len,
+                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad.p, st.p);
+    else
+        LAUNCHN(e, "fn_parse_single_kernel", fn_parse_single_kernel<false>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len,
+                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad.p, st.p);
+    const FnStats fs = read_scalar<FnStats>(e, st.p);
+    sp.nsym = fs.n_sym;
+    if (getenv("MC2_DEBUG_FAST"))
+        fprintf(stderr, "[fast_nt] single pass len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)sp.len, fs.n_sym,
+                fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
+    return fs;
+}
+
 // write pass: 2-bit codes + bad bits (also counts the kept non-ACGT bytes into st->packed2)
 static void fn_write_pass(mc2_engine* e, FnSpan& sp, DBuf<FnStats>& st) {
     sp.codes.alloc(e, div_up(sp.nsym, 16) + 4);
@@ -1118,7 +1146,8 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         sp.text = dtext + cuts[i];
         sp.len = cuts[i + 1] - cuts[i];
         const bool plan_known = s->plan.path != PATH_UNSET;
-        const FnStats fs = fn_count_pass(e, sp, !plan_known, st);
+        const bool single = e->opt_parse_single != 0;
+        const FnStats fs = single ? fn_single_pass(e, sp, !plan_known, st) : fn_count_pass(e, sp, !plan_known, st);
         if (fs.complex) return false;
         if (!plan_known) {
             // kept / ACGT counts are exact from the statistics pass; later spans learn their non-ACGT count in the write pass
@@ -1142,7 +1171,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
             }
             if (!served(s->plan)) return false;
         }
-        if (sp.nsym) fn_write_pass(e, sp, st);
+        if (sp.nsym && !single) fn_write_pass(e, sp, st);
         nsym_total += sp.nsym;
     }
     if (nsym_total == 0) return true;
@@ -1615,6 +1644,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
     else if (n == "count_variant") e->opt_count_variant = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
+    else if (n == "parse_single") e->opt_parse_single = (int)value;
     else if (n == "file_piece_bytes") e->opt_file_piece = (u64)std::max<int64_t>(4096, value);
     else if (n == "span_bytes") e->opt_span_bytes = value < 4096 ? 4096 : (value > (3ull << 30) ? (3ull << 30) : (u64)value);
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
@@ -1910,10 +1940,11 @@ int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int spa
             FnSpan& sp = spans[i];
             sp.text = d + cuts[i];
             sp.len = cuts[i + 1] - cuts[i];
-            const FnStats fs = fn_count_pass(e, sp, false, st);
+            const bool single = e->opt_parse_single != 0;
+            const FnStats fs = single ? fn_single_pass(e, sp, false, st) : fn_count_pass(e, sp, false, st);
             if (fs.complex) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text is not plain FASTA (whitespace, '*' or non-ASCII bytes in sequence lines)");
             if (!sp.nsym) continue;
-            fn_write_pass(e, sp, st);
+            if (!single) fn_write_pass(e, sp, st);
             pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
         }
         if (!level0_partition(e, k, pvs, nullptr, groups, HC_MULT1, (1ull << 32) - 1, 0, ks->l0))

@@ -37,6 +37,7 @@ def reset(engine):
     engine.set_option("sparse_algo", 0)
     engine.set_option("fast_nt", 1)
     engine.set_option("hash_bucket_keys", 3500)
+    engine.set_option("parse_single", 0)
 
 
 def diff_msg(got, want):
@@ -345,11 +346,12 @@ def test_fast_lane_wrapped_genome(engine, line_end):
     text = b"".join(recs)
     for k, c in ((31, 2), (32, 2), (13, 3), (2, 2), (1, 2)):
         want = orc.find_kmers_text(text.decode(), k, c)
-        for fast in (1, 0):
+        for fast, single in ((1, 1), (1, 0), (0, 1)):          # packed lane with the one-pass and the two-pass parse, general lane
             engine.set_option("force_path", 2)
             engine.set_option("fast_nt", fast)
+            engine.set_option("parse_single", single)
             try:
-                check(engine, text, k, c, want, f"genome le={line_end!r} k={k} c={c} fast={fast}")
+                check(engine, text, k, c, want, f"genome le={line_end!r} k={k} c={c} fast={fast} single={single}")
             finally:
                 reset(engine)
 
