@@ -39,6 +39,7 @@ struct mc2_engine {
     int opt_force_enc = -1;
     int opt_fast_nt = 1;                   // use the SWAR/packed nucleotide lane when the text is simple
     int opt_big_chunks = 1;                // chunks beyond one hash batch: level-0 key partition in HBM (0 = sort fallback)
+    int opt_prefetch_pass = 1;             // run the next chunk's count pass behind the current chunk (one sync fewer per chunk)
     int opt_parse_single = 0;              // packed lane: 1 = one pass over the text with chained look-back (measured slower: 0.39 vs 0.28 ms per 100 MiB)
     u64 opt_file_piece = 32ull << 20;      // bytes per piece of the streaming file reader
     u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
@@ -246,6 +247,26 @@ struct Plan {
     u32 nrep = 1;
 };
 
+// One span (< 4 GiB, starting at a line start) of simple FASTA text on its way to packed symbols.
+struct FnSpan {
+    const u8* text = nullptr;
+    u64 len = 0, ntiles = 0, nsym = 0;
+    DBuf<u8> tstate;
+    DBuf<u32> tcnt;
+    DBuf<u64> toff;
+    DBuf<u32> codes, bad;
+};
+
+// The count pass of the NEXT chunk, enqueued ahead of the current chunk's final readback so that one host
+// synchronisation serves both (its statistics land in the pinned scratch at offset 3072).
+struct PrePass {
+    bool valid = false;
+    const u8* text = nullptr;
+    u64 len = 0;
+    FnSpan sp;
+    DBuf<struct FnStats> st;
+};
+
 struct mc2_sample {
     mc2_engine* e = nullptr;
     int k = 0;
@@ -258,6 +279,9 @@ struct mc2_sample {
     std::vector<WidePart> wide;
     u64 n_chunks = 0;
     double bucket_scale = 1.0;             // shrinks when many hash buckets overflow (heavily duplicated keys)
+    PrePass pre;
+    const u8* next_text = nullptr;         // the chunk that follows the one being counted (resident text), for PrePass
+    u64 next_len = 0;
 };
 
 struct mc2_table {
@@ -528,6 +552,8 @@ static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys
 
 // hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch.  Keys come either from
 // the byte symbol stream `v` (encoding ENC) or, when `pv` is given, from the packed nucleotide stream.
+static void prefetch_next_count_pass(mc2_engine* e, mc2_sample* s);
+
 struct KeySpan {               // keys already extracted (one level-0 group of a very large chunk)
     const u64* keys;
     u64 n;
@@ -726,6 +752,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         LAUNCH(e, hc_count_kernel, cgrid, HC_THREADS, HC_COUNT_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
                part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
     }
+    if (pv && !ks) prefetch_next_count_pass(e, s);               // rides on the synchronisation below
     const Tail t = read_scalar<Tail>(e, tail.p);
     if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
     if (ks && getenv("MC2_DEBUG_PHASES"))
@@ -895,18 +922,9 @@ static void adopt_symbols(mc2_engine* e, const u8* dsym, u64 len, Parsed& out) {
 // holds non-ACGT symbols whose windows still have to be counted by the wide path.
 static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 chunk_bytes);
 
-// One span (< 4 GiB, starting at a line start) of simple FASTA text on its way to packed symbols.
-struct FnSpan {
-    const u8* text = nullptr;
-    u64 len = 0, ntiles = 0, nsym = 0;
-    DBuf<u8> tstate;
-    DBuf<u32> tcnt;
-    DBuf<u64> toff;
-    DBuf<u32> codes, bad;
-};
 
 // count pass: tile line states + symbols per tile (+ alphabet statistics on the first piece of a sample)
-static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
+static void fn_count_pass_launch(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
     const u64 mis = (u64)(uintptr_t)sp.text & 15ull;
     sp.ntiles = div_up(mis + sp.len, FN_TILE);
     sp.tstate.alloc(e, sp.ntiles);
@@ -919,12 +937,36 @@ static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<Fn
         LAUNCH(e, fn_parse_kernel<2>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len, sp.tstate.p, sp.tcnt.p, (const u64*)nullptr,
                (u32*)nullptr, (u32*)nullptr, st.p);
     dev_exclusive_scan<u32, u64>(e, sp.tcnt.p, sp.toff.p, sp.ntiles, &st.p->n_sym);
+}
+static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
+    fn_count_pass_launch(e, sp, with_stats, st);
     const FnStats fs = read_scalar<FnStats>(e, st.p);
     sp.nsym = fs.n_sym;
     if (getenv("MC2_DEBUG_FAST"))
         fprintf(stderr, "[fast_nt] len=%llu n_sym=%llu kept=%llu non_acgt=%llu complex=%llu\n", (ull)sp.len, fs.n_sym,
                 fs.packed & 0xFFFFFFFFull, fs.packed >> 32, fs.complex);
     return fs;
+}
+
+static void prefetch_next_count_pass(mc2_engine* e, mc2_sample* s) {
+    if (!s->next_len || s->pre.valid || !e->opt_prefetch_pass) return;
+    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
+    const bool ok = e->opt_fast_nt && !e->opt_parse_single && s->k <= 32 && s->c >= 2 && e->opt_sparse_algo != 1 &&
+                    s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE && e->opt_force_enc <= 0 && e->opt_force_path != PATH_WIDE &&
+                    s->next_len <= std::min<u64>(e->opt_span_bytes, hash_max);
+    if (!ok) { s->next_len = 0; return; }
+    PrePass& p = s->pre;
+    p.text = s->next_text;
+    p.len = s->next_len;
+    p.sp = FnSpan();
+    p.sp.text = p.text;
+    p.sp.len = p.len;
+    p.st.alloc(e, 1);
+    p.st.zero();
+    fn_count_pass_launch(e, p.sp, false, p.st);
+    CUDA_CHECK(cudaMemcpyAsync((u8*)e->pin_small + 3072, p.st.p, sizeof(FnStats), cudaMemcpyDeviceToHost, e->stream));
+    p.valid = true;
+    s->next_len = 0;
 }
 
 // count + write in one pass over the text (chained look-back for the symbol offsets, see fn_parse_single_kernel)
@@ -1136,18 +1178,37 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     std::vector<u64> cuts;
     if (!fn_span_cuts(e, dtext, len, cuts)) return false;
     const size_t nspans = cuts.size() - 1;
-    DBuf<FnStats> st(e, 1);
-    st.zero();
+    DBuf<FnStats> st;
     std::vector<FnSpan> spans(nspans);
+    // the count pass of this chunk may already have run behind the previous chunk (its statistics arrived with that
+    // chunk's final synchronisation)
+    const bool prefetched = s->pre.valid && nspans == 1 && s->pre.text == dtext && s->pre.len == len && s->plan.path != PATH_UNSET;
+    if (prefetched) {
+        spans[0] = std::move(s->pre.sp);
+        st = std::move(s->pre.st);
+    } else {
+        st.alloc(e, 1);
+        st.zero();
+    }
+    if (s->pre.valid) {                                            // consumed or stale
+        s->pre.valid = false;
+        if (!prefetched) { s->pre.sp = FnSpan(); s->pre.st.release(); }
+    }
     u64 nsym_total = 0;
     PhaseTimer pt(e);
     for (size_t i = 0; i < nspans; ++i) {
         FnSpan& sp = spans[i];
-        sp.text = dtext + cuts[i];
-        sp.len = cuts[i + 1] - cuts[i];
         const bool plan_known = s->plan.path != PATH_UNSET;
-        const bool single = e->opt_parse_single != 0;
-        const FnStats fs = single ? fn_single_pass(e, sp, !plan_known, st) : fn_count_pass(e, sp, !plan_known, st);
+        const bool single = e->opt_parse_single != 0 && !prefetched;
+        FnStats fs;
+        if (prefetched) {
+            memcpy(&fs, (const u8*)e->pin_small + 3072, sizeof fs);
+            sp.nsym = fs.n_sym;
+        } else {
+            sp.text = dtext + cuts[i];
+            sp.len = cuts[i + 1] - cuts[i];
+            fs = single ? fn_single_pass(e, sp, !plan_known, st) : fn_count_pass(e, sp, !plan_known, st);
+        }
         if (fs.complex) return false;
         if (!plan_known) {
             // kept / ACGT counts are exact from the statistics pass; later spans learn their non-ACGT count in the write pass
@@ -1403,8 +1464,16 @@ static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u
         bounds = chunk_bounds(e, d, nbytes, chunk_bytes);
         for (size_t i = 0; i < bounds.size(); ++i) {
             const u64 a = bounds[i], b = i + 1 < bounds.size() ? bounds[i + 1] : nbytes;
+            if (i + 1 < bounds.size()) {
+                s->next_text = d + b;
+                s->next_len = (i + 2 < bounds.size() ? bounds[i + 2] : nbytes) - b;
+            } else {
+                s->next_len = 0;
+            }
             count_chunk(e, s, d + a, b - a);
         }
+        s->next_len = 0;
+        if (s->pre.valid) { s->pre.valid = false; s->pre.sp = FnSpan(); s->pre.st.release(); }
     } else {
         // host text, chunked: overlap the upload with chunking + counting.  The boundary after `b` is the first
         // candidate line whose translated offset from b reaches chunk_bytes (lib/mercat2_Chunker.py:45-52); it is
@@ -1645,6 +1714,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "count_variant") e->opt_count_variant = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
     else if (n == "parse_single") e->opt_parse_single = (int)value;
+    else if (n == "prefetch_pass") e->opt_prefetch_pass = (int)value;
     else if (n == "file_piece_bytes") e->opt_file_piece = (u64)std::max<int64_t>(4096, value);
     else if (n == "span_bytes") e->opt_span_bytes = value < 4096 ? 4096 : (value > (3ull << 30) ? (3ull << 30) : (u64)value);
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
