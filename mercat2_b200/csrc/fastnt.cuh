@@ -140,9 +140,16 @@ __device__ __forceinline__ u32 fn_compress(u32 src, u32 mask) {
     return out;
 }
 
-// ---- K1f: count pass (WRITE = false) and write pass (WRITE = true) --------------------------------------
+// ---- K1f: count pass and write pass ---------------------------------------------------------------------------
 // MODE 0: count pass with alphabet statistics (first piece of a sample); MODE 1: write pass (also counts the kept
 // non-ACGT bytes); MODE 2: light count pass (line structure only).
+// Every thread owns FN_V consecutive 16-byte groups (64 bytes), so one pair of block scans (line state, symbol offset)
+// serves a 16 KiB tile: the barriers, not the SWAR arithmetic, bounded the 4 KiB-tile version.
+#define FN_V 4
+#define FN_VTILE (FN_THREADS * 16 * FN_V)
+#define FN_SC_WORDS (FN_VTILE / 16 + 4)
+#define FN_SB_WORDS (FN_VTILE / 32 + 4)
+
 template <int MODE>
 __global__ void __launch_bounds__(FN_THREADS)
 fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_state, u32* __restrict__ tile_cnt,
@@ -150,13 +157,19 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
     constexpr bool WRITE = MODE == 1;
     __shared__ u32 sm[FN_WARPS + 1];
     __shared__ u32 s_state;
-    __shared__ u32 s_c[WRITE ? 260 : 1], s_b[WRITE ? 132 : 1];
+    __shared__ u32 s_c[WRITE ? FN_SC_WORDS : 1], s_b[WRITE ? FN_SB_WORDS : 1];
     const ParseTileView v = make_view(text, len);
-    const u64 tile_v = (u64)blockIdx.x * FN_TILE;
-    const u64 p0 = tile_v + (u64)threadIdx.x * 16;
-    u32 w[4];
-    load16(v, p0, w);
-    const FnMasks m = fn_classify<MODE != 2>(w);
+    const u64 tile_v = (u64)blockIdx.x * FN_VTILE;
+    const u64 p0 = tile_v + (u64)threadIdx.x * (16 * FN_V);
+    FnMasks m[FN_V];
+    u32 summary = FwdOp::identity();
+#pragma unroll
+    for (int g = 0; g < FN_V; ++g) {
+        u32 w[4];
+        load16(v, p0 + 16 * g, w);
+        m[g] = fn_classify<MODE != 2>(w);
+        summary = FwdOp::combine(summary, fn_summary(m[g]));
+    }
     if (!WRITE) {
         if (threadIdx.x < 32) {
             bool cx = false;
@@ -169,29 +182,38 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
         }
     } else {
         if (threadIdx.x == 0) s_state = tile_state[blockIdx.x];
-        for (u32 i = threadIdx.x; i < 260; i += FN_THREADS) s_c[i] = 0;
-        for (u32 i = threadIdx.x; i < 132; i += FN_THREADS) s_b[i] = 0;
+        for (u32 i = threadIdx.x; i < FN_SC_WORDS; i += FN_THREADS) s_c[i] = 0;
+        for (u32 i = threadIdx.x; i < FN_SB_WORDS; i += FN_THREADS) s_b[i] = 0;
     }
-    const u32 pre = block_exclusive_scan<FwdOp, FN_WARPS>(fn_summary(m), sm, nullptr);   // barriers publish s_state
-    const u32 state = FwdOp::apply(pre, s_state);
-    const FnEmit e = fn_emit_masks(m, state);
-    const u32 cnt = __popc(e.emit);
+    const u32 pre = block_exclusive_scan<FwdOp, FN_WARPS>(summary, sm, nullptr);   // barriers publish s_state
+    u32 state = FwdOp::apply(pre, s_state);
+    u32 emit[FN_V], bads[FN_V];
+    u32 cnt = 0, kept = 0, slow = 0, cx = 0;
+#pragma unroll
+    for (int g = 0; g < FN_V; ++g) {
+        const FnEmit e = fn_emit_masks(m[g], state);
+        state = FwdOp::apply(fn_summary(m[g]), state);
+        emit[g] = e.emit;
+        bads[g] = e.bad;
+        cnt += __popc(e.emit);
+        kept += __popc(e.keep);
+        slow += __popc(e.keep & ~m[g].acgt);
+        cx |= e.cx;
+    }
     u32 total;
     const u32 off = block_exclusive_scan<OpAdd, FN_WARPS>(cnt, sm, &total);
     if (!WRITE) {
         if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
         // statistics: one 64-bit atomic per tile (kept | non-ACGT << 32); `complex` only when it happens
         if (MODE == 0) {
-            const u32 kept = __popc(e.keep), slow = __popc(e.keep & ~m.acgt);
             u32 t_kept, t_slow;
             block_exclusive_scan<OpAdd, FN_WARPS>(kept, sm, &t_kept);
             block_exclusive_scan<OpAdd, FN_WARPS>(slow, sm, &t_slow);
             if (threadIdx.x == 0 && (t_kept | t_slow)) atomicAdd(&stats->packed, (ull)t_kept | ((ull)t_slow << 32));
         }
-        if (e.cx) atomicAdd(&stats->complex, 1ull);
+        if (cx) atomicAdd(&stats->complex, 1ull);
     } else {
         {   // kept bytes outside ACGT (their windows go to the wide path): rare, so only warps that see one report
-            const u32 slow = __popc(e.keep & ~m.acgt);
             __syncwarp();
             if (__ballot_sync(0xffffffffu, slow != 0)) {
                 u32 t = slow;
@@ -204,16 +226,21 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
         const u64 s_tile = tile_off[blockIdx.x];            // global symbol index of the tile's first symbol
         const u64 base_sym = s_tile & ~31ull;
         const u32 rel0 = (u32)(s_tile - base_sym);
-        if (cnt) {
-            const u32 rel = rel0 + off;
-            const u32 cf = fn_compress<2>(m.codes, e.emit);
-            const u32 bf = fn_compress<1>(e.bad, e.emit);
-            const u64 cv = (u64)(cnt == 16 ? cf : (cf & ((1u << (2 * cnt)) - 1u))) << (2 * (rel & 15));
-            atomicOr(&s_c[rel >> 4], (u32)cv);
-            if (cv >> 32) atomicOr(&s_c[(rel >> 4) + 1], (u32)(cv >> 32));
-            const u64 bv = (u64)(bf & ((1u << cnt) - 1u)) << (rel & 31);
-            atomicOr(&s_b[rel >> 5], (u32)bv);
-            if (bv >> 32) atomicOr(&s_b[(rel >> 5) + 1], (u32)(bv >> 32));
+        u32 rel = rel0 + off;
+#pragma unroll
+        for (int g = 0; g < FN_V; ++g) {
+            const u32 c = __popc(emit[g]);
+            if (c) {
+                const u32 cf = fn_compress<2>(m[g].codes, emit[g]);
+                const u32 bf = fn_compress<1>(bads[g], emit[g]);
+                const u64 cv = (u64)(c == 16 ? cf : (cf & ((1u << (2 * c)) - 1u))) << (2 * (rel & 15));
+                atomicOr(&s_c[rel >> 4], (u32)cv);
+                if (cv >> 32) atomicOr(&s_c[(rel >> 4) + 1], (u32)(cv >> 32));
+                const u64 bv = (u64)(bf & ((1u << c) - 1u)) << (rel & 31);
+                atomicOr(&s_b[rel >> 5], (u32)bv);
+                if (bv >> 32) atomicOr(&s_b[(rel >> 5) + 1], (u32)(bv >> 32));
+                rel += c;
+            }
         }
         BLOCK_SYNC();
         const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;

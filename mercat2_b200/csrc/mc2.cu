@@ -926,7 +926,7 @@ static std::vector<u64> chunk_bounds(mc2_engine* e, const u8* dtext, u64 n, u64 
 // count pass: tile line states + symbols per tile (+ alphabet statistics on the first piece of a sample)
 static void fn_count_pass_launch(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<FnStats>& st) {
     const u64 mis = (u64)(uintptr_t)sp.text & 15ull;
-    sp.ntiles = div_up(mis + sp.len, FN_TILE);
+    sp.ntiles = div_up(mis + sp.len, FN_VTILE);
     sp.tstate.alloc(e, sp.ntiles);
     sp.tcnt.alloc(e, sp.ntiles);
     sp.toff.alloc(e, sp.ntiles);
