@@ -656,3 +656,16 @@ def test_streaming_file_reader(engine, tmp_path):
     s4 = engine.sample(5, 1)
     with pytest.raises(mercat2_b200.Mc2Error):
         s4.add_file(bad, 0)
+
+
+def test_inputs_beyond_4_gib():
+    """one chunk of more than 2^32 bytes on each lane (packed dense with the 64-bit fold, level-0 partition, general
+    parser): sum of counts = number of windows, all 4^3 / 20^3 rows present and sorted (tools/big_sanity.py)"""
+    import importlib.util
+    import torch
+    if torch.cuda.mem_get_info()[0] < (60 << 30):
+        pytest.skip("needs 60 GB of free device memory")
+    spec = importlib.util.spec_from_file_location("big_sanity", os.path.join(os.path.dirname(__file__), "..", "tools", "big_sanity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main() == 0
