@@ -92,22 +92,28 @@ hc_hist_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32* __restrict__ ghist
 __global__ void __launch_bounds__(1024)
 hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __restrict__ sub_base, u32* __restrict__ cur1,
                u32* __restrict__ cur2, u32* __restrict__ tile_pref, ull* __restrict__ total_out) {
+    extern __shared__ __align__(16) u8 dyn_scan[];                 // nb words: the histogram, then its exclusive prefix
+    u32* h = reinterpret_cast<u32*>(dyn_scan);
     __shared__ u64 sm[1024 / 32 + 1];
     __shared__ u32 s_l1[HC_MAX_NB1 + 1];
+    for (u32 i = threadIdx.x; i < nb; i += 1024) h[i] = ghist[i];   // coalesced; the serial part below runs on shared memory
+    BLOCK_SYNC();
     const u32 per = (nb + 1023) / 1024;
     const u32 t0 = min(nb, threadIdx.x * per), t1 = min(nb, t0 + per);
     u64 acc = 0;
-    for (u32 t = t0; t < t1; ++t) acc += ghist[t];
+    for (u32 t = t0; t < t1; ++t) acc += h[t];
     u64 total;
     u64 base = block_exclusive_sum64<32>(acc, sm, &total);
     for (u32 t = t0; t < t1; ++t) {
-        sub_base[t] = (u32)base;
-        cur2[t] = (u32)base;
-        if (t % nb2 == 0) { cur1[t / nb2] = (u32)base; s_l1[t / nb2] = (u32)base; }
-        base += ghist[t];
+        const u32 c = h[t];
+        h[t] = (u32)base;
+        if (t % nb2 == 0) s_l1[t / nb2] = (u32)base;
+        base += c;
     }
     if (threadIdx.x == 0) { sub_base[nb] = (u32)total; s_l1[nb1] = (u32)total; *total_out = total; }
     BLOCK_SYNC();
+    for (u32 i = threadIdx.x; i < nb; i += 1024) { const u32 b = h[i]; sub_base[i] = b; cur2[i] = b; }
+    for (u32 i = threadIdx.x; i < nb1; i += 1024) cur1[i] = s_l1[i];
     // tiles per level-1 bucket -> exclusive prefix
     u64 tl = 0;
     if (threadIdx.x < nb1) tl = (s_l1[threadIdx.x + 1] - s_l1[threadIdx.x] + HC_TILE - 1) / HC_TILE;

@@ -612,7 +612,14 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         const u64 grid = std::min<u64>(div_up(cap, EX_TILE), (u64)e->num_sms * std::max(per_sm, 1));
         LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, hist_smem, v, (u64)0, v.n, k, nb, ghist.p);
     }
-    LAUNCH(e, hc_scan_kernel, 1, 1024, 0, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
+    {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(hc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HC_MAX_NB1 * HC_NB2 * 4)));
+            attr_set = true;
+        }
+    }
+    LAUNCH(e, hc_scan_kernel, 1, 1024, (size_t)nb * 4, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
     DBuf<u64> keys1(e, cap), keys2(e, cap);
     const bool dbg = getenv("MC2_DEBUG_HASH") != nullptr;
     if (dbg) {
