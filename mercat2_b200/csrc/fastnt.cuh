@@ -522,7 +522,7 @@ fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1
                    const u64* __restrict__ base64) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
-    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)EX_TILE * 8);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + HC_SDST_OFFSET);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;

@@ -31,7 +31,10 @@
 #define HC_NB2 (1u << HC_NB2_LOG2)
 #define HC_MAX_NB1 400u
 #define HC_TILE 4096u
-#define HC_SCATTER_SMEM ((size_t)HC_TILE * 12)     // staged keys (8 B) + destination indices (4 B)
+#define HC_STAGE_SLOTS (HC_TILE + 2)                    // one tile + a spare slot for invalid keys (kept 16-byte aligned)
+#define HC_SDST_OFFSET ((size_t)HC_STAGE_SLOTS * 8)
+#define HC_SCATTER_SMEM ((size_t)HC_STAGE_SLOTS * 12)  // staged keys (8 B) + destination indices (4 B)
+#define HC_SCATTER_SMEM16 ((size_t)HC_STAGE_SLOTS * 10) // staged keys (8 B) + 16-bit digits
 
 #define HC_MULT1 0x9E3779B97F4A7C15ull           // bucket hash of a chunk's keys
 #define HC_MULT2 0xC2B2AE3D27D4EB4Full           // independent bucket hash inside a level-0 group (very large chunks)
@@ -131,21 +134,27 @@ hc_scan_kernel(const u32* __restrict__ ghist, u32 nb, u32 nb1, u32 nb2, u32* __r
 // lets the keys die in between (fewer live registers, more resident CTAs).
 // `base64` (may be NULL): 64-bit start of every digit's region; the cursors are then relative to it (level-0 groups of
 // chunks with more than 2^32 windows).
-template <bool USE_DST, class KeyFn, class KeyFn2, class DigitFn>
-__device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
+// FULL: all 16 keys of every thread are valid (interior tiles): no per-key tests.  Otherwise the rank atomic is
+// predicated in PTX and invalid keys are staged into a spare slot, so the unrolled per-key code stays free of
+// branches (every branch re-derives the shared-memory window base and brackets itself with BSSY/BSYNC).
+__device__ __forceinline__ u32 smem_atom_inc_if(u32 addr32, u32 pred) {
+    u32 old = 0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(old) : "r"(addr32), "r"(pred) : "memory");
+    return old;
+}
+
+template <bool USE_DST, bool FULL, class KeyFn, class KeyFn2, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write3(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                     u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
-                                                    u64* __restrict__ out, const u64* __restrict__ base64 = nullptr) {
-    u32 rk[8], dg[8];                       // 16-bit rank within (tile, digit) and digit of each key
+                                                    u64* __restrict__ out, const u64* __restrict__ base64, u32 spare /*stage slot for invalid keys*/) {
+    u32 rd[16];                             // (rank within (tile, digit)) << 16 | digit
+    const u32 cnt32 = (u32)__cvta_generic_to_shared(cnt);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { rk[j] = 0; dg[j] = 0; }
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if ((valid >> i) & 1u) {
-            const u32 d = dig(mine(i));
-            const u32 r = atomicAdd(&cnt[d], 1u);
-            rk[i >> 1] |= r << (16 * (i & 1));
-            dg[i >> 1] |= d << (16 * (i & 1));
-        }
+    for (int i = 0; i < 16; ++i) {
+        const u32 d = dig(mine(i));
+        const u32 r = FULL ? atomicAdd(&cnt[d], 1u) : smem_atom_inc_if(cnt32 + 4u * d, (valid >> i) & 1u);
+        rd[i] = (r << 16) | d;
+    }
     BLOCK_SYNC();
     const u32 per = (nd + EX_THREADS - 1) / EX_THREADS;
     u32 acc = 0;
@@ -163,15 +172,15 @@ __device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u3
     }
     BLOCK_SYNC();
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if ((valid >> i) & 1u) {
-            const u32 d = (dg[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-            const u32 r = (rk[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-            const u32 pos = loff[d] + r;
-            stage[pos] = again(i);
-            if (USE_DST) sdst[pos] = gbase[d] + r;
-            else reinterpret_cast<u16*>(sdst)[pos] = (u16)d;
-        }
+    for (int i = 0; i < 16; ++i) {
+        const u32 d = rd[i] & 0xFFFFu;
+        const u32 r = rd[i] >> 16;
+        u32 pos = loff[d] + r;
+        if (!FULL) pos = ((valid >> i) & 1u) ? pos : spare;
+        stage[pos] = again(i);
+        if (USE_DST) sdst[pos] = gbase[d] + r;
+        else reinterpret_cast<u16*>(sdst)[pos] = (u16)d;
+    }
     BLOCK_SYNC();
     if (USE_DST) {
         for (u32 i = threadIdx.x; i < total; i += EX_THREADS) out[sdst[i]] = stage[i];
@@ -182,6 +191,14 @@ __device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u3
             out[at] = stage[i];
         }
     }
+}
+
+template <bool USE_DST, class KeyFn, class KeyFn2, class DigitFn>
+__device__ __forceinline__ void hc_group_and_write2(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
+                                                    u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
+                                                    u64* __restrict__ out, const u64* __restrict__ base64 = nullptr) {
+    // (stage / sdst hold one spare slot behind the tile: HC_SPARE_SLOT)
+    hc_group_and_write3<USE_DST, false>(mine, again, valid, nd, dig, stage, sdst, cnt, loff, gbase, sm, cursors, out, base64, HC_TILE);
 }
 
 template <bool USE_DST, class KeyFn, class DigitFn>
@@ -199,7 +216,7 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, u32 nb, u32 nb1, u32* __res
     __shared__ u32 s_meta[EX_THREADS + EX_HALO];
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
-    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)EX_TILE * 8);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + HC_SDST_OFFSET);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
@@ -226,7 +243,7 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
                    u32 nb, u32 nb1, u32 nb2, u32* __restrict__ cur2, u64* __restrict__ keys2, u64 mult) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
-    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + HC_SDST_OFFSET);
     __shared__ u32 cnt[HC_NB2], loff[HC_NB2], gbase[HC_NB2];
     __shared__ u32 sm[EX_WARPS + 1];
     __shared__ u32 s_b1;
@@ -251,7 +268,11 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
         if (i < hi) { mine[j] = keys1[i]; valid |= 1u << j; }
     }
     auto dig = [nb, nb2, mult](u64 key) { return hc_bucket(key, nb, mult) & (nb2 - 1); };
-    if (RELOAD) {
+    const bool full = base + HC_TILE <= hi;                  // (block-uniform) interior tile: every key slot is valid
+    if (!RELOAD && full) {
+        auto key = [&](int i) { return mine[i]; };
+        hc_group_and_write3<USE_DST, true>(key, key, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2, nullptr, HC_TILE);
+    } else if (RELOAD) {
         // the staging phase reads the keys again (an L2 hit: the tile was read a few microseconds ago) instead of
         // carrying 32 registers across two barriers
         auto again = [&](int j) {
@@ -287,7 +308,7 @@ hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, u32 nb, u32 nb1, u64 mul
                    const u64* __restrict__ base64) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_TILE * 10 bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
-    u32* sdst = reinterpret_cast<u32*>(dyn_sc + (size_t)HC_TILE * 8);
+    u32* sdst = reinterpret_cast<u32*>(dyn_sc + HC_SDST_OFFSET);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
     for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;

@@ -627,7 +627,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
     const bool use_dst = (e->opt_scatter_variant & 1) && !ks;
-    const size_t sc_smem = use_dst ? HC_SCATTER_SMEM : (size_t)HC_TILE * 10;
+    const size_t sc_smem = use_dst ? HC_SCATTER_SMEM : HC_SCATTER_SMEM16;
     {
         static thread_local int attr_variant = -1;
         if (attr_variant != e->opt_scatter_variant) {
@@ -647,7 +647,7 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         }
     }
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p,
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, HC_SCATTER_SMEM16, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p,
                (const u64*)nullptr);
     } else if (pv) {
         if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
@@ -1108,12 +1108,12 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     pt.mark("level-0 allocation");
     CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, (size_t)HC_TILE * 10, ks->keys, ks->n, nb0, g0, mult, cur0.p,
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM16, ks->keys, ks->n, nb0, g0, mult, cur0.p,
                out.keys0.p, (const u64*)gbase_dev.p);
     } else {
         for (auto& pv : pvs) {
             const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
-            if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, (size_t)HC_TILE * 10, pv, k, nb0, g0, cur0.p, out.keys0.p,
+            if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM16, pv, k, nb0, g0, cur0.p, out.keys0.p,
                              (const u64*)gbase_dev.p);
         }
     }
