@@ -331,14 +331,15 @@ fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
     u32* hist = reinterpret_cast<u32*>(dyn);
     for (u32 i = threadIdx.x; i < nb; i += FN_HIST_THREADS) hist[i] = 0;
     BLOCK_SYNC();
+    const u32 hist32 = (u32)__cvta_generic_to_shared(hist);
     const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
     const u64 nwords = (pv.n + 15) >> 4;
     for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
         u64 keys[16];
         const u32 valid = fn_windows(pv, g, k, mask, keys);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if ((valid >> j) & 1u) atomicAdd(&hist[hc_bucket(keys[j], nb)], 1u);
+        for (int j = 0; j < 16; ++j)                       // predicated reduction: no branch per window
+            smem_red_inc_if(hist32 + 4u * hc_bucket(keys[j], nb), (valid >> j) & 1u);
     }
     BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < nb; b += FN_HIST_THREADS) {
@@ -497,14 +498,18 @@ fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ tabl
         BLOCK_SYNC();
     }
     u32* my = SMEM ? hist + (u32)((threadIdx.x >> 5) % nrep) * bins : table;
+    const u32 my32 = SMEM ? (u32)__cvta_generic_to_shared(my) : 0u;
     const u64 mask = (1ull << (2 * k)) - 1;
     const u64 nwords = (pv.n + 15) >> 4;
     for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
         u64 keys[16];
         const u32 valid = fn_windows(pv, g, k, mask, keys);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if ((valid >> j) & 1u) atomicAdd(&my[fn_dense_index((u32)keys[j], k)], 1u);
+        for (int j = 0; j < 16; ++j) {
+            const u32 idx = fn_dense_index((u32)keys[j], k);
+            if (SMEM) smem_red_inc_if(my32 + 4u * idx, (valid >> j) & 1u);           // predicated: no branch per window
+            else if ((valid >> j) & 1u) atomicAdd(&my[idx], 1u);
+        }
     }
     if (SMEM) {
         BLOCK_SYNC();

@@ -143,6 +143,10 @@ __device__ __forceinline__ u32 smem_atom_inc_if(u32 addr32, u32 pred) {
     return old;
 }
 
+__device__ __forceinline__ void smem_red_inc_if(u32 addr32, u32 pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q red.shared.add.u32 [%0], 1;\n\t}" :: "r"(addr32), "r"(pred) : "memory");
+}
+
 template <bool USE_DST, bool FULL, class KeyFn, class KeyFn2, class DigitFn>
 __device__ __forceinline__ void hc_group_and_write3(KeyFn mine, KeyFn2 again, u32 valid, u32 nd, DigitFn dig, u64* stage, u32* sdst,
                                                     u32* cnt, u32* loff, u32* gbase, u32* sm, u32* __restrict__ cursors,
