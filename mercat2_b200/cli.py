@@ -126,7 +126,7 @@ def mercat_main(argv=None):
         with open(tsv, "w") as writer:
             print("Sample", "seq_name", "length", "PI", "MW", "Hydro", sep="\t", file=writer)
             for base, file in samples["protein"].items():
-                for header, name, length, pi, mw, hydro in mercat2_metrics.file_metrics(file):
+                for header, name, length, pi, mw, hydro in pipeline.sample_metric_rows(file, args.s):
                     print(header, name, length, "" if pi is None else pi, mw, hydro, sep="\t", file=writer)
     if world > 1:
         import torch.distributed as dist

@@ -52,3 +52,24 @@ def run_mercat2(basename: str, files: list, out_file, kmer, min_count, num_cores
     if not quiet:
         print("No significant k-mers found")
     return basename, None
+
+
+def sample_metric_rows(file, chunk_size_mb: int = 0, engine=None):
+    """Rows of report/metrics-protein.tsv for one protein sample the way the reference's driver produces them:
+    ``samples[type][name] = [orig] + chunk_files(orig)`` (bin/mercat2.py:319-326, 422-429) and plot_sample_metrics
+    walks EVERY file of that list (lib/mercat2_figures.py:157-186) -- so each sequence appears once for the original
+    file (sorted by length, descending) and once more for the piece that holds it (each piece sorted on its own; the
+    original again when the file was not chunked).  Pieces are the engine's virtual pieces: no files are written."""
+    from . import mercat2_metrics
+    from .mercat2_kmers import read_text_bytes
+    engine = engine or _native.default_engine()
+    data = read_text_bytes(Path(file))
+    rows = mercat2_metrics.file_metrics_text(data, engine)
+    yield from rows
+    chunk = chunk_trigger(file, chunk_size_mb)
+    if not chunk:
+        yield from rows
+        return
+    offsets = list(engine.chunk_offsets(data, chunk)) + [len(data)]
+    for a, b in zip(offsets[:-1], offsets[1:]):
+        yield from mercat2_metrics.file_metrics_text(data[a:b], engine)

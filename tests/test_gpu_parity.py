@@ -669,3 +669,23 @@ def test_inputs_beyond_4_gib():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main() == 0
+
+
+def test_sample_metric_rows_orig_and_pieces(engine, tmp_path):
+    """metrics-protein.tsv lists every file of [orig] + chunk_files(orig): the reference's committed table holds the
+    4852 proteins of DJ_pro twice, each block sorted by length; with chunking the second block is the pieces"""
+    from mercat2_b200 import pipeline, mercat2_metrics
+    src = GOLDEN / "data/faa_gz/DJ_pro.faa.gz"
+    once = mercat2_metrics.file_metrics(src, engine)
+    rows = list(pipeline.sample_metric_rows(src, 100, engine))              # below the trigger: [orig, orig]
+    assert len(rows) == 2 * 4852 and rows[:4852] == once and rows[4852:] == once
+    plain = tmp_path / "DJ_pro.faa"
+    plain.write_bytes(read_maybe_gz(src))
+    rows = list(pipeline.sample_metric_rows(plain, 1, engine))              # 1 MiB pieces
+    assert rows[:4852] == once
+    tail = rows[4852:]
+    assert sorted(tail) == sorted(once)
+    lengths = [r[2] for r in tail]
+    runs = 1 + sum(1 for a, b in zip(lengths, lengths[1:]) if b > a)
+    pieces = len(engine.chunk_offsets(plain.read_bytes(), 1 << 20))
+    assert pieces >= 2 and runs == pieces
