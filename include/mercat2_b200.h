@@ -164,6 +164,23 @@ int mc2_count_exceptions(mc2_engine* e, const void* text, uint64_t nbytes, int s
  * a buffer owned by the communication library). */
 int mc2_device_copy(mc2_engine* e, void* dst, const void* src, uint64_t nbytes);
 
+/* ---- sample x k-mer table (row N3: merge_tsv / merge_tsv_T, lib/mercat2_report.py:98-194) --------------------
+ * mc2_merge_tables: union of the tables' k-mers (sorted) x one count column per table, 0 where a sample lacks the
+ * k-mer -- from tables that are still on the device; mc2_table_from_tsv parses a per-sample TSV file's bytes
+ * ("<header line>\n" then "<k-mer>\t<count>\n" rows) on the device so that the reference's file-based entry
+ * point keeps working.  mc2_matrix_write_tsv: corner = first header cell ("k-mer" / "sample"), names = column (or,
+ * transposed, row) labels in table order; transposed = 0 writes merge_tsv's layout, 1 merge_tsv_T's (its columns in
+ * sorted k-mer order; the reference's order there is a Python set's). */
+typedef struct mc2_matrix mc2_matrix;
+int mc2_table_from_tsv(mc2_engine* e, const void* text, uint64_t nbytes, int space, mc2_table** out);
+int mc2_merge_tables(mc2_engine* e, mc2_table* const* tables, uint32_t n, mc2_matrix** out);
+uint64_t mc2_matrix_rows(const mc2_matrix* m);
+int mc2_matrix_k(const mc2_matrix* m);
+/* kmers: rows*k bytes; counts: rows*n entries, row-major */
+int mc2_matrix_export(mc2_matrix* m, char* kmers, uint64_t* counts);
+int mc2_matrix_write_tsv(mc2_matrix* m, const char* path, const char* corner, const char* const* names, int transposed);
+void mc2_matrix_free(mc2_matrix* m);
+
 /* ---- protein metrics ----------------------------------------------------------------------------
  * Replaces the numeric part of plot_sample_metrics (lib/mercat2_figures.py:157-183) and
  * predict_isoelectric_point_ProMoST / calculate_MW / calculate_hydro (lib/mercat2_metrics.py:57-170)

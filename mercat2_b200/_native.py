@@ -60,6 +60,13 @@ SYMBOLS = [
     ("mc2_keys_free", None, [_VP]),
     ("mc2_sample_add_keys", _INT, [_VP, _VP, _U64, _INT]),
     ("mc2_count_exceptions", _INT, [_VP, _VP, _U64, _INT, _INT, _PP]),
+    ("mc2_table_from_tsv", _INT, [_VP, _VP, _U64, _INT, _PP]),
+    ("mc2_merge_tables", _INT, [_VP, _VP, C.c_uint32, _PP]),
+    ("mc2_matrix_rows", _U64, [_VP]),
+    ("mc2_matrix_k", _INT, [_VP]),
+    ("mc2_matrix_export", _INT, [_VP, _VP, _VP]),
+    ("mc2_matrix_write_tsv", _INT, [_VP, C.c_char_p, C.c_char_p, _VP, _INT]),
+    ("mc2_matrix_free", None, [_VP]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -225,6 +232,46 @@ class Table:
         return bytes(buf)
 
 
+class Matrix:
+    """Sample x k-mer count matrix (merge_tsv): rows = sorted union of the samples' k-mers, one column per sample."""
+
+    def __init__(self, engine, handle, samples):
+        self._engine, self._h, self.samples = engine, handle, samples
+
+    def close(self):
+        if getattr(self, "_h", None) and self._engine._h:
+            self._engine._lib.mc2_matrix_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def rows(self) -> int:
+        return int(self._engine._lib.mc2_matrix_rows(self._h))
+
+    @property
+    def k(self) -> int:
+        return int(self._engine._lib.mc2_matrix_k(self._h))
+
+    def arrays(self):
+        """(kmers uint8[rows, k], counts uint64[rows, samples])"""
+        rows, k = self.rows, self.k
+        kmers = np.empty((rows, k), dtype=np.uint8)
+        counts = np.empty((rows, self.samples), dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_matrix_export(self._h, kmers.ctypes.data, counts.ctypes.data))
+        return kmers, counts
+
+    def write_tsv(self, path, corner: str, names, transposed: bool = False):
+        names = [str(n).encode() for n in names]
+        if len(names) != self.samples:
+            raise ValueError("one name per sample")
+        arr = (C.c_char_p * len(names))(*names)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_matrix_write_tsv(self._h, os.fsencode(str(path)), corner.encode(), arr, 1 if transposed else 0))
+
+
 class Engine:
     """One CUDA device + stream.  Not thread-safe: one host thread per engine."""
 
@@ -308,6 +355,21 @@ class Engine:
                                                         MC2_DEVICE if on_device else MC2_HOST, wk.ctypes.data if nw else None,
                                                         wc.ctypes.data if nw else None, nw, C.byref(out)))
         return Table(self, out)
+
+    def table_from_tsv(self, data) -> Table:
+        """Parse the bytes of a per-sample TSV file (header line, then '<k-mer>\\t<count>' rows) on the device."""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_table_from_tsv(self._h, addr, n, space, C.byref(out)))
+        return Table(self, out)
+
+    def merge_tables(self, tables) -> Matrix:
+        """Sample x k-mer matrix of several tables (columns in the given order)."""
+        tables = list(tables)
+        arr = (C.c_void_p * len(tables))(*[t._h for t in tables])
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_merge_tables(self._h, arr, len(tables), C.byref(out)))
+        return Matrix(self, out, len(tables))
 
     def partition_keys(self, data, k: int, groups: int) -> "Keys":
         """2-bit packed keys of every window of a plain nucleotide FASTA text, grouped by key hash into `groups` groups."""

@@ -20,6 +20,7 @@
 #include "fastnt.cuh"
 #include "metrics.cuh"
 #include "tsv.cuh"
+#include "merge.cuh"
 
 static thread_local std::string g_err;
 
@@ -2107,6 +2108,205 @@ int mc2_count_exceptions(mc2_engine* e, const void* text, uint64_t nbytes, int s
     }
     *out = sample_finish(&s);
     API_END
+}
+
+// ---- merge_tsv (sample x k-mer matrix) ------------------------------------------------------------------------------
+struct mc2_matrix {
+    mc2_engine* e = nullptr;
+    int k = 0;
+    u32 samples = 0;
+    u64 rows = 0;
+    DBuf<u8> kmers;        // rows * k bytes, sorted
+    DBuf<u64> counts;      // rows * samples, row-major
+};
+
+int mc2_table_from_tsv(mc2_engine* e, const void* text, uint64_t nbytes, int space, mc2_table** out) {
+    API_BEGIN
+    if (!e || !out || (nbytes && !text)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_table> t(new mc2_table);
+    t->e = e;
+    t->enc = ENC_BYTE;
+    DBuf<u8> holder;
+    const u8* d = to_device(e, text, nbytes, space, holder);
+    // the text must end with a newline for the row scan: work on a copy with one appended when it does not
+    DBuf<u8> padded;
+    u64 n = nbytes;
+    if (nbytes) {
+        u8 last = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&last, d + nbytes - 1, 1, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (last != '\n') {
+            padded.alloc(e, nbytes + 1);
+            CUDA_CHECK(cudaMemcpyAsync(padded.p, d, nbytes, cudaMemcpyDeviceToDevice, e->stream));
+            CUDA_CHECK(cudaMemsetAsync(padded.p + nbytes, '\n', 1, e->stream));
+            d = padded.p;
+            n = nbytes + 1;
+        }
+    }
+    const u64 ntiles = div_up(std::max<u64>(n, 1), MG_TILE);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, mg_newline_count_kernel, (unsigned)ntiles, MG_THREADS, 0, d, n, tc.p);
+    const u64 nlines = offsets_from_counts(e, tc.p, to.p, ntiles);
+    if (nlines >= 2) {
+        DBuf<u64> nl(e, nlines);
+        LAUNCH(e, mg_newline_write_kernel, (unsigned)ntiles, MG_THREADS, 0, d, n, (const u64*)to.p, nl.p);
+        // k = length of the first row's first column
+        u64 ends[2];
+        d2h(e, ends, (const u64*)nl.p, 2);
+        const u64 a = ends[0] + 1, len1 = ends[1] - a;
+        std::vector<u8> first(std::min<u64>(len1, 4096));
+        d2h(e, first.data(), d + a, first.size());
+        size_t tab = 0;
+        while (tab < first.size() && first[tab] != '\t') ++tab;
+        if (tab == 0 || tab >= first.size()) throw Mc2Error(MC2_ERR_INVALID, "TSV: the first row has no <k-mer>\\t<count>");
+        if (tab > 128) throw Mc2Error(MC2_ERR_LIMIT, "TSV: k > 128");
+        t->k = (int)tab;
+        const u64 nrows = nlines - 1;
+        t->wide.n = nrows;
+        t->wide.sorted = false;
+        t->wide.rows.alloc(e, nrows * (u64)t->k);
+        t->wide.counts.alloc(e, nrows);
+        DBuf<ull> bad(e, 1);
+        bad.zero();
+        LAUNCH(e, mg_parse_rows_kernel, (unsigned)div_up(nrows, 256), 256, 0, d, (const u64*)nl.p, nrows, t->k, t->wide.rows.p, t->wide.counts.p, bad.p);
+        if (read_scalar<ull>(e, bad.p)) throw Mc2Error(MC2_ERR_INVALID, "TSV: a row is not <k-mer of the first row's length>\\t<decimal count>");
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *out = t.release();
+    API_END
+}
+
+// all rows of a table as k literal bytes + counts (appended to rows/counts at row offset `at`)
+static void table_text_rows(mc2_engine* e, mc2_table* t, u8* rows, u64* counts) {
+    const int k = t->k;
+    const u64 nf = t->fast.n, nw = t->wide.n;
+    if (nf) {
+        const int kind = t->key_kind == KEY_DENSE_AA ? TSV_DENSE_AA : t->enc == ENC_NT2 ? TSV_NT2 : t->enc == ENC_AA5 ? TSV_AA5 : TSV_BYTE;
+        LAUNCH(e, mg_decode_rows_kernel, (unsigned)div_up(nf, 256), 256, 0, (const u64*)t->fast.keys.p, nf, k, kind, rows);
+        CUDA_CHECK(cudaMemcpyAsync(counts, t->fast.counts.p, nf * 8, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    if (nw) {
+        CUDA_CHECK(cudaMemcpyAsync(rows + nf * (u64)k, t->wide.rows.p, nw * (u64)k, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(counts + nf, t->wide.counts.p, nw * 8, cudaMemcpyDeviceToDevice, e->stream));
+    }
+}
+
+int mc2_merge_tables(mc2_engine* e, mc2_table* const* tables, uint32_t n, mc2_matrix** out) {
+    API_BEGIN
+    if (!e || !out || (n && !tables)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_matrix> m(new mc2_matrix);
+    m->e = e;
+    m->samples = n;
+    int k = 0;
+    u64 total = 0;
+    for (u32 i = 0; i < n; ++i) {
+        if (!tables[i]) throw Mc2Error(MC2_ERR_INVALID, "NULL table");
+        const u64 r = tables[i]->fast.n + tables[i]->wide.n;
+        if (!r) continue;
+        if (k && tables[i]->k != k) throw Mc2Error(MC2_ERR_INVALID, "merge: the tables hold k-mers of different lengths");
+        k = tables[i]->k;
+        total += r;
+    }
+    m->k = k;
+    if (total) {
+        DBuf<u8> rows(e, total * (u64)k);
+        DBuf<u64> counts(e, total), pos(e, total);
+        std::vector<u64> at(n + 1, 0);
+        for (u32 i = 0; i < n; ++i) {
+            const u64 r = tables[i]->fast.n + tables[i]->wide.n;
+            if (r) table_text_rows(e, tables[i], rows.p + at[i] * k, counts.p + at[i]);
+            at[i + 1] = at[i] + r;
+        }
+        LAUNCH(e, wide_row_positions_kernel, (unsigned)div_up(total, 256), 256, 0, pos.p, total, k);
+        WidePart uni;
+        wide_reduce(e, rows.p, pos.p, nullptr, total, k, 1, uni);                 // sorted unique k-mers of all samples
+        m->rows = uni.n;
+        m->kmers = std::move(uni.rows);
+        m->counts.alloc(e, uni.n * (u64)n);
+        m->counts.zero();
+        for (u32 i = 0; i < n; ++i) {
+            const u64 r = at[i + 1] - at[i];
+            if (r) LAUNCH(e, mg_fill_kernel, (unsigned)div_up(r, 256), 256, 0, (const u8*)m->kmers.p, m->rows, k, (const u8*)rows.p + at[i] * k,
+                          (const u64*)counts.p + at[i], r, m->counts.p, n, i);
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *out = m.release();
+    API_END
+}
+
+uint64_t mc2_matrix_rows(const mc2_matrix* m) { return m ? m->rows : 0; }
+int mc2_matrix_k(const mc2_matrix* m) { return m ? m->k : 0; }
+
+int mc2_matrix_export(mc2_matrix* m, char* kmers, uint64_t* counts) {
+    API_BEGIN
+    if (!m) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (m->rows && (!kmers || !counts)) throw Mc2Error(MC2_ERR_INVALID, "NULL buffer");
+    CUDA_CHECK(cudaSetDevice(m->e->device));
+    d2h(m->e, (u8*)kmers, (const u8*)m->kmers.p, m->rows * (u64)m->k);
+    d2h(m->e, (u64*)counts, (const u64*)m->counts.p, m->rows * (u64)m->samples);
+    API_END
+}
+
+// cells of `nrows` x `ncols` formatted on the device and streamed into f
+static void matrix_emit(mc2_matrix* m, FILE* f, const u64* vals, u64 stride_r, u64 stride_c, u64 nrows, u64 ncols, u32 label_len, const u8* labels,
+                        bool* ok) {
+    mc2_engine* e = m->e;
+    const u64 cells = nrows * ncols;
+    if (!cells) return;
+    DBuf<u32> len(e, cells);
+    DBuf<u64> off(e, cells);
+    DBuf<ull> total(e, 1);
+    LAUNCH(e, mg_cell_len_kernel, (unsigned)div_up(cells, 256), 256, 0, vals, stride_r, stride_c, nrows, ncols, label_len, len.p);
+    dev_exclusive_scan<u32, u64>(e, len.p, off.p, cells, total.p);
+    const u64 nbytes = (u64)read_scalar<ull>(e, total.p);
+    DBuf<u8> body(e, nbytes);
+    LAUNCH(e, mg_cell_write_kernel, (unsigned)div_up(cells, 256), 256, 0, vals, stride_r, stride_c, nrows, ncols, label_len, labels,
+           (const u64*)off.p, body.p);
+    download_pipelined(e, (const u8*)body.p, nbytes, [&](const u8* src, u64, u64 n) { *ok = *ok && fwrite(src, 1, n, f) == n; });
+}
+
+int mc2_matrix_write_tsv(mc2_matrix* m, const char* path, const char* corner, const char* const* names, int transposed) {
+    API_BEGIN
+    if (!m || !path || !corner || (m->samples && !names)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    mc2_engine* e = m->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    FILE* f = fopen(path, "wb");
+    if (!f) throw Mc2Error(MC2_ERR_IO, std::string("cannot open ") + path);
+    bool ok = true;
+    std::string head = corner;
+    if (!transposed) {
+        // lib/mercat2_report.py:118: print(header, '\t'.join(names), sep='\t'); then one line per k-mer of the sorted union
+        for (u32 s = 0; s < m->samples; ++s) { head += '\t'; head += names[s]; }
+        head += '\n';
+        ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+        matrix_emit(m, f, m->counts.p, m->samples, 1, m->rows, m->samples, (u32)m->k, m->kmers.p, &ok);
+    } else {
+        // lib/mercat2_report.py:176-193: 'sample' + every k-mer as a column (the reference's column order is the
+        // iteration order of a Python set; here: sorted), then one line per sample
+        std::vector<u8> km(m->rows * (u64)m->k);
+        d2h(e, km.data(), (const u8*)m->kmers.p, km.size());
+        for (u64 u = 0; u < m->rows; ++u) { head += '\t'; head.append((const char*)&km[u * m->k], m->k); }
+        head += '\n';
+        ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+        for (u32 s = 0; s < m->samples && ok; ++s) {
+            ok = fwrite(names[s], 1, strlen(names[s]), f) == strlen(names[s]);
+            if (m->rows) matrix_emit(m, f, m->counts.p + s, 0, m->samples, 1, m->rows, 0, nullptr, &ok);
+            else ok = ok && fputc('\n', f) != EOF;
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
+    API_END
+}
+
+void mc2_matrix_free(mc2_matrix* m) {
+    if (!m) return;
+    cudaSetDevice(m->e->device);
+    delete m;
 }
 
 int mc2_sample_finish(mc2_sample* s, mc2_table** out) {

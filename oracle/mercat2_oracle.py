@@ -370,3 +370,86 @@ def sample_metrics(file) -> list:
             rows[name] = (name, name.split()[0], float(len(seq)),
                           predict_isoelectric_point_ProMoST(seq), calculate_MW(seq), calculate_hydro(seq))
     return sorted(rows.values(), key=lambda r: -r[2])
+
+
+# ---- merge_tsv / merge_tsv_T (lib/mercat2_report.py:98-194; row N3 of SURVEY.md 8f) ------------------------------
+def _read_counts_tsv(path):
+    with open(path) as handle:
+        head = handle.readline()
+        rows = [line.split() for line in handle if line.strip()]
+    return head.split("\t")[0], {r[0]: r[1] for r in rows}
+
+
+def merge_tsv(tsv_list: dict, out_file) -> None:
+    """The reference's k-way merge, step for step (lib/mercat2_report.py:98-160).  Every file has a current row; the
+    row label of an output line is the smallest NEXT key among the files that advanced on the previous line (all files
+    at the start); a file emits its count and advances when its current key is <= the label, else emits '0'.
+    NB: because files that did not advance are left out of that minimum, a pending smaller key can be emitted under a
+    larger label -- with differing key sets the reference's table has out-of-order / repeated labels and misattributed
+    counts (visible in tests/golden/merged_protein_k3.tsv.gz: 'CCR' twice around 'CCQ').  With identical key sets
+    (e.g. nucleotide k=3) it is the plain sorted union.  ``merge_tsv_union`` below is the intended table."""
+    names = sorted(tsv_list.keys())
+    handles, lines, header = {}, {}, ""
+    for name in names:
+        handles[name] = open(tsv_list[name])
+        head = handles[name].readline()
+        if not header:
+            header = head.split("\t")[0]
+    try:
+        with open(out_file, "w") as writer:
+            print(header, "\t".join(names), sep="\t", file=writer)
+            kmers = set()
+            for name in names:
+                lines[name] = handles[name].readline().split()
+                kmers.add(lines[name][0])
+            kmer = sorted(kmers)[0]
+            while True:
+                line = [kmer]
+                kmers = set()
+                for name in names:
+                    if not lines[name] or lines[name][0] > kmer:
+                        line.append("0")
+                    else:
+                        line.append(lines[name][1])
+                        nxt = handles[name].readline().strip("\n").split("\t")
+                        lines[name] = [x for x in nxt if len(x) > 0]
+                        if lines[name]:
+                            kmers.add(lines[name][0])
+                print("\t".join(line), file=writer)
+                if not kmers:
+                    break
+                kmer = sorted(kmers)[0]
+    finally:
+        for h in handles.values():
+            h.close()
+
+
+def merge_tsv_union(tsv_list: dict, out_file) -> None:
+    """What merge_tsv is meant to produce: one row per k-mer of the sorted union of all samples, '0' where a sample
+    lacks it.  Equal to the reference's output whenever all samples hold the same k-mers."""
+    names = sorted(tsv_list.keys())
+    header, tables = "", {}
+    for name in names:
+        head, table = _read_counts_tsv(tsv_list[name])
+        header = header or head
+        tables[name] = table
+    kmers = sorted(set().union(*[set(t) for t in tables.values()])) if tables else []
+    with open(out_file, "w") as writer:
+        print(header, "\t".join(names), sep="\t", file=writer)
+        for kmer in kmers:
+            print("\t".join([kmer] + [tables[n].get(kmer, "0") for n in names]), file=writer)
+
+
+def merge_tsv_T(tsv_list: dict, out_file) -> None:
+    """Transposed table (lib/mercat2_report.py:164-194).  The reference's column order is a Python set's iteration
+    order; this restatement sorts the columns (only the cell contents are comparable)."""
+    names = sorted(tsv_list.keys())
+    tables = {n: _read_counts_tsv(tsv_list[n])[1] for n in names}
+    kmers = sorted(set().union(*[set(t) for t in tables.values()])) if tables else []
+    with open(out_file, "w") as writer:
+        print("sample", "\t".join(kmers), sep="\t", file=writer)
+        for n in names:
+            writer.write(n)
+            for kmer in kmers:
+                writer.write("\t" + tables[n].get(kmer, "0"))
+            writer.write("\n")

@@ -689,3 +689,51 @@ def test_sample_metric_rows_orig_and_pieces(engine, tmp_path):
     runs = 1 + sum(1 for a, b in zip(lengths, lengths[1:]) if b > a)
     pieces = len(engine.chunk_offsets(plain.read_bytes(), 1 << 20))
     assert pieces >= 2 and runs == pieces
+
+
+@pytest.mark.parametrize("label", ["nucleotide_k3", "protein_k3"])
+def test_merge_tsv_vs_reference(engine, tmp_path, label):
+    """merge_tsv / merge_tsv_T on the engine (device TSV parse, union, matrix, text) against the reference's own
+    merged tables; and the same matrix from tables that never left the device"""
+    from mercat2_b200 import mercat2_report
+    exp = GOLDEN / "expected"
+    tsv_list, sources = {}, {}
+    for f in sorted(exp.glob("*_k3_c10.tsv*")):
+        if ("_pro_" in f.name) != (label == "protein_k3"):
+            continue
+        name = f.name.split("_k3_")[0]
+        dst = tmp_path / f"{name}_counts.tsv"
+        dst.write_bytes(read_maybe_gz(f))
+        tsv_list[name] = str(dst)
+    # the engine writes the sorted union; the reference's own k-way merge equals it when all samples hold the same
+    # k-mers (nucleotide k=3) and is scrambled otherwise (see oracle.merge_tsv) -- then the clean union is the target
+    ref = gzip.open(GOLDEN / f"merged_{label}.tsv.gz", "rb").read()
+    union = tmp_path / "union.tsv"
+    orc.merge_tsv_union(tsv_list, union)
+    want = union.read_bytes()
+    assert (want == ref) == (label == "nucleotide_k3")
+    out = tmp_path / "combined.tsv"
+    mercat2_report.merge_tsv(tsv_list, out, engine)
+    assert out.read_bytes() == want
+    out_t = tmp_path / "combined_T.tsv"
+    mercat2_report.merge_tsv_T(tsv_list, out_t, engine)
+    ref_t = tmp_path / "ref_T.tsv"
+    orc.merge_tsv_T(tsv_list, ref_t)                      # (sorted columns, like the engine)
+    assert out_t.read_bytes() == ref_t.read_bytes()
+    # resident tables: count the samples again and merge without touching the TSVs
+    reset(engine)
+    kind = "faa_gz" if label == "protein_k3" else "fna_gz"
+    tables = {}
+    for name in tsv_list:
+        src = next((GOLDEN / "data" / kind).glob(name + ".*"))
+        tables[name] = engine.count_text(read_maybe_gz(src), 3, 10)
+    if label == "protein_k3":                              # (the nucleotide goldens were counted on removeN-cleaned files)
+        out2 = tmp_path / "combined_resident.tsv"
+        mercat2_report.merge_tables(tables, out2, "k-mer", engine)
+        assert out2.read_bytes() == want
+    # a k-mer missing from some samples, literal-byte rows, a file without trailing newline
+    a = tmp_path / "a.tsv"; a.write_bytes(b"k-mer\ta_Count\nAAC\t5\nACN\t7\nTTT\t1")
+    b = tmp_path / "b.tsv"; b.write_bytes(b"k-mer\tb_Count\nAAC\t2\nGGG\t123456789012\n")
+    out3 = tmp_path / "ab.tsv"
+    mercat2_report.merge_tsv({"b": str(b), "a": str(a)}, out3, engine)
+    assert out3.read_bytes() == b"k-mer\ta\tb\nAAC\t5\t2\nACN\t7\t0\nGGG\t0\t123456789012\nTTT\t1\t0\n"

@@ -116,3 +116,38 @@ def test_metrics_odd_sequences(capsys):
         assert orc.predict_isoelectric_point_ProMoST(item["seq"]) == item["pI"], item
         assert orc.calculate_MW(item["seq"]) == item["MW"]
         assert orc.calculate_hydro(item["seq"]) == item["hydro"]
+
+
+def _merge_inputs(tmp_path, label):
+    import gzip as _gzip
+    exp = GOLDEN / "expected"
+    tsv_list = {}
+    for f in sorted(exp.glob("*_k3_c10.tsv*")):
+        pro = "_pro_" in f.name
+        if pro != (label == "protein_k3"):
+            continue
+        name = f.name.split("_k3_")[0]
+        dst = tmp_path / f"{name}_counts.tsv"
+        dst.write_bytes(_gzip.open(f, "rb").read() if f.suffix == ".gz" else f.read_bytes())
+        tsv_list[name] = str(dst)
+    return tsv_list
+
+
+@pytest.mark.parametrize("label", ["nucleotide_k3", "protein_k3"])
+def test_oracle_merge_tsv_vs_reference(tmp_path, label):
+    """merge_tsv restatement against the reference's own output on the committed per-sample tables
+    (oracle/make_golden_merge.py); merge_tsv_T: same cells (the reference's column order is a set's)"""
+    import gzip as _gzip
+    tsv_list = _merge_inputs(tmp_path, label)
+    assert len(tsv_list) == 5
+    out = tmp_path / "combined.tsv"
+    orc.merge_tsv(tsv_list, out)
+    assert out.read_bytes() == _gzip.open(GOLDEN / f"merged_{label}.tsv.gz", "rb").read()
+    out_t = tmp_path / "combined_T.tsv"
+    orc.merge_tsv_T(tsv_list, out_t)
+
+    def cells(blob):
+        lines = blob.decode().splitlines()
+        cols = lines[0].split("\t")[1:]
+        return {(row.split("\t")[0], c): v for row in lines[1:] for c, v in zip(cols, row.split("\t")[1:])}
+    assert cells(out_t.read_bytes()) == cells(_gzip.open(GOLDEN / f"merged_{label}_T.tsv.gz", "rb").read())
