@@ -1,0 +1,205 @@
+// Part of mc2.cu (textually included there, in this order): K1 host side (parse driver), path planning, reductions over sorted sequences.
+
+// =====================================================================================================
+// K1 parse
+// =====================================================================================================
+struct Parsed {
+    DBuf<u8> sym;
+    u64 nsym = 0;
+    ParseStats stats;
+};
+
+static void parse_text(mc2_engine* e, const u8* dtext, u64 len, int toupper, Parsed& out) {
+    memset(&out.stats, 0, sizeof out.stats);
+    out.nsym = 0;
+    if (len == 0) return;
+    const u64 mis = (u64)(uintptr_t)dtext & 15ull;
+    const u64 ntiles = div_up(mis + len, PARSE_TILE);
+    if (ntiles >= (1ull << 31)) throw Mc2Error(MC2_ERR_LIMIT, "parse: text larger than 8 TiB");
+    DBuf<u8> tf(e, ntiles), tr(e, ntiles);
+    DBuf<u32> cnt(e, ntiles);
+    DBuf<u64> off(e, ntiles);
+    DBuf<ParseStats> st(e, 1);
+    st.zero();
+    LAUNCH(e, parse_summarize_kernel, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, st.p);
+    LAUNCH(e, parse_scan_tiles_kernel, 1, SCAN1_THREADS, 0, tf.p, tr.p, (u32)ntiles);
+    LAUNCH(e, parse_emit_kernel<false>, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, cnt.p,
+           (const u64*)nullptr, (u8*)nullptr, st.p, toupper);
+    dev_exclusive_scan<u32, u64>(e, cnt.p, off.p, ntiles, &st.p->n_sym);
+    out.stats = read_scalar<ParseStats>(e, st.p);
+    if (out.stats.n_bad)
+        throw Mc2Error(MC2_ERR_NON_ASCII, "input contains " + std::to_string(out.stats.n_bad) +
+                                              " non-ASCII byte(s); only 7-bit ASCII FASTA text is supported");
+    out.nsym = out.stats.n_sym;
+    out.sym.alloc(e, (out.nsym + 64) & ~15ull);
+    if (out.nsym)
+        LAUNCH(e, parse_emit_kernel<true>, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, cnt.p,
+               (const u64*)off.p, out.sym.p, st.p, toupper);
+}
+
+// =====================================================================================================
+// planning
+// =====================================================================================================
+static int enc_bits(int enc) { return enc == ENC_NT2 ? 2 : enc == ENC_AA5 ? 5 : 8; }
+
+static void make_plan(mc2_engine* e, const ParseStats& st, int k, Plan& plan) {
+    int enc;
+    if (e->opt_force_enc >= 0) enc = e->opt_force_enc;
+    else if (st.n_ascii == 0 || st.n_acgt * 10 >= st.n_ascii * 9) enc = ENC_NT2;
+    else if (st.n_upper * 2 >= st.n_ascii) enc = ENC_AA5;
+    else enc = ENC_BYTE;
+    plan.enc = enc;
+    const int kb = k * enc_bits(enc);
+    int path = kb <= 64 ? PATH_SPARSE : PATH_WIDE;
+    u64 bins = 0;
+    if (path == PATH_SPARSE && enc != ENC_BYTE) {
+        const u64 base = enc == ENC_NT2 ? 4 : 26;
+        bins = 1;
+        for (int i = 0; i < k && bins <= (1ull << 40); ++i) bins *= base;
+        if (bins <= e->opt_dense_max_bins && bins < (1ull << 31)) path = PATH_DENSE;
+    }
+    if (e->opt_force_path == PATH_SPARSE && kb <= 64) path = PATH_SPARSE;
+    if (e->opt_force_path == PATH_WIDE) path = PATH_WIDE;
+    if (e->opt_force_path == PATH_DENSE && bins && bins < (1ull << 31)) path = PATH_DENSE;
+    plan.path = path;
+    plan.bins = path == PATH_DENSE ? (u32)bins : 0;
+    plan.smem = path == PATH_DENSE && bins <= e->opt_smem_max_bins && bins * 4 <= 200 * 1024;
+    plan.nrep = 1;
+    if (plan.smem) {
+        u64 r = (48 * 1024) / (bins * 4);
+        plan.nrep = (u32)std::min<u64>(EX_WARPS, std::max<u64>(1, r));
+    }
+}
+
+// =====================================================================================================
+// reductions over sorted sequences
+// =====================================================================================================
+// unit weights: survivors of a sorted sequence of m items; returns count and fills start/count buffers
+template <class Acc>
+static u64 rle_threshold(mc2_engine* e, Acc acc, u64 m, u64 c, DBuf<u64>& start, DBuf<u64>& count) {
+    const u64 ntiles = div_up(m, RLE_THREADS);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, rle_count_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, c, tc.p);
+    const u64 ns = offsets_from_counts(e, tc.p, to.p, ntiles);
+    start.alloc(e, ns);
+    count.alloc(e, ns);
+    if (ns) LAUNCH(e, rle_write_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, c, (const u64*)to.p, start.p, count.p);
+    return ns;
+}
+
+// weighted: sorted items with weights w_sorted[i]; survivors have weight sum >= c
+template <class Acc>
+static u64 seg_reduce(mc2_engine* e, Acc acc, u64 m, const u64* w_sorted, u64 c, DBuf<u64>& start, DBuf<u64>& count) {
+    const u64 ntiles = div_up(m, RLE_THREADS);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, seg_count_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, tc.p);
+    const u64 nseg = offsets_from_counts(e, tc.p, to.p, ntiles);
+    DBuf<u64> seg_start(e, nseg), seg_sum(e, nseg);
+    LAUNCH(e, seg_write_kernel<Acc>, (unsigned)ntiles, RLE_THREADS, 0, acc, m, (const u64*)to.p, seg_start.p);
+    DBuf<u64> wprefix(e, m);
+    DBuf<ull> wtotal(e, 1);
+    dev_exclusive_scan<u64, u64>(e, w_sorted, wprefix.p, m, wtotal.p);
+    const u64 wt = (u64)read_scalar<ull>(e, wtotal.p);
+    const u64 nt2 = div_up(nseg, RLE_THREADS);
+    DBuf<u32> tc2(e, nt2);
+    DBuf<u64> to2(e, nt2);
+    LAUNCH(e, seg_sum_count_kernel, (unsigned)nt2, RLE_THREADS, 0, (const u64*)seg_start.p, nseg, m, (const u64*)wprefix.p, wt, c,
+           seg_sum.p, tc2.p);
+    const u64 ns = offsets_from_counts(e, tc2.p, to2.p, nt2);
+    start.alloc(e, ns);
+    count.alloc(e, ns);
+    if (ns)
+        LAUNCH(e, seg_compact_kernel, (unsigned)nt2, RLE_THREADS, 0, (const u64*)seg_start.p, (const u64*)seg_sum.p, nseg, c,
+               (const u64*)to2.p, start.p, count.p);
+    return ns;
+}
+
+// merge several (key, count) parts: concat, sort pairs, sum equal keys, keep sums >= c
+static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int key_bits, u64 c, FastPart& out) {
+    u64 M = 0;
+    for (auto& p : parts) M += p.n;
+    out.n = 0;
+    if (M == 0) return;
+    if (c <= 1) {
+        FastPart* only = nullptr;
+        int nonempty = 0;
+        for (auto& p : parts) if (p.n) { only = &p; nonempty++; }
+        if (nonempty == 1 && only->sorted) { out = std::move(*only); return; }
+    }
+    DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(k0.p + at, p.keys.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(v0.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += p.n;
+    }
+    const int r = radix_sort<u64, true>(e, k0.p, k1.p, v0.p, v1.p, M, 0, std::min(64, (key_bits + 7) & ~7));
+    const u64* ks = r ? k1.p : k0.p;
+    const u64* vs = r ? v1.p : v0.p;
+    DBuf<u64> start, count;
+    KeyEq acc{ks};
+    const u64 ns = seg_reduce(e, acc, M, vs, c, start, count);
+    out.n = ns;
+    out.sorted = true;
+    out.keys.alloc(e, ns);
+    out.counts = std::move(count);
+    if (ns) LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, out.keys.p);
+}
+
+// order m windows (k bytes each, at src + pos[i]) and reduce; weights == nullptr means unit weights
+static void wide_reduce(mc2_engine* e, const u8* src, const u64* pos, const u64* weights, u64 m, int k, u64 c, WidePart& out) {
+    out.n = 0;
+    if (m == 0) return;
+    if (m >= (1ull << 32)) throw Mc2Error(MC2_ERR_LIMIT, "wide path: more than 2^32-1 windows in one batch");
+    DBuf<u32> i0(e, m), i1(e, m);
+    DBuf<u64> k0(e, m), k1(e, m);
+    LAUNCH(e, iota_u32_kernel, (unsigned)div_up(m, 256), 256, 0, i0.p, m);
+    u32* idx[2] = {i0.p, i1.p};
+    int cur = 0;
+    const int L = (k + 7) / 8;
+    for (int limb = L - 1; limb >= 0; --limb) {
+        LAUNCH(e, wide_gather_limb_kernel, (unsigned)div_up(m, 256), 256, 0, src, pos, (const u32*)idx[cur], m, k, limb, k0.p);
+        const int nb = std::min(8, k - 8 * limb);
+        const int r = radix_sort<u32, true>(e, k0.p, k1.p, idx[cur], idx[1 - cur], m, 8 * (8 - nb), 64);
+        if (r) cur ^= 1;     // an odd number of passes leaves the payload in the other buffer
+    }
+    const u32* sidx = idx[cur];
+    WindowEq acc{src, pos, sidx, k};
+    DBuf<u64> start, count;
+    u64 ns;
+    if (!weights) {
+        ns = rle_threshold(e, acc, m, c, start, count);
+    } else {
+        DBuf<u64> ws(e, m);
+        LAUNCH(e, gather_u64_by_u32_kernel, (unsigned)div_up(m, 256), 256, 0, weights, sidx, m, ws.p);
+        ns = seg_reduce(e, acc, m, (const u64*)ws.p, c, start, count);
+    }
+    out.n = ns;
+    out.rows.alloc(e, ns * (u64)k);
+    out.counts = std::move(count);
+    if (ns)
+        LAUNCH(e, wide_gather_rows_kernel, (unsigned)div_up(ns * (u64)k, 256), 256, 0, src, pos, sidx, (const u64*)start.p, ns, k,
+               out.rows.p);
+}
+
+static void reduce_wide_parts(mc2_engine* e, std::vector<WidePart>& parts, int k, u64 c, WidePart& out) {
+    u64 M = 0;
+    for (auto& p : parts) M += p.n;
+    out.n = 0;
+    if (M == 0) return;
+    if (parts.size() == 1 && c <= 1 && parts[0].sorted) { out = std::move(parts[0]); return; }
+    DBuf<u8> rows(e, M * (u64)k);
+    DBuf<u64> w(e, M), pos(e, M);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(rows.p + at * k, p.rows.p, p.n * (u64)k, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(w.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += p.n;
+    }
+    LAUNCH(e, wide_row_positions_kernel, (unsigned)div_up(M, 256), 256, 0, pos.p, M, k);
+    wide_reduce(e, rows.p, pos.p, w.p, M, k, c, out);
+}

@@ -737,3 +737,29 @@ def test_merge_tsv_vs_reference(engine, tmp_path, label):
     out3 = tmp_path / "ab.tsv"
     mercat2_report.merge_tsv({"b": str(b), "a": str(a)}, out3, engine)
     assert out3.read_bytes() == b"k-mer\ta\tb\nAAC\t5\t2\nACN\t7\t0\nGGG\t0\t123456789012\nTTT\t1\t0\n"
+
+
+@pytest.mark.parametrize("option,value", [("count_variant", 3), ("scatter_variant", 1), ("scatter_variant", 8), ("parse_single", 1),
+                                          ("prefetch_pass", 0)])
+def test_experiment_variants_stay_exact(engine, option, value):
+    """the kernel variants kept behind engine options (measured, not the default -- DESIGN.md §4) count the same tables"""
+    reset(engine)
+    text = synth_reads(6000, 150, seed=55, n_rate=0.002, lower_rate=0.01, genome_len=40000)
+    pieces = 3
+    want = None
+    for setting in (None, value):
+        if setting is not None:
+            engine.set_option(option, setting)
+        try:
+            table, offs = engine.count_sample(text, 25, 2, len(text) // pieces)
+            got = table.to_dict()
+        finally:
+            defaults = {"count_variant": 2, "scatter_variant": 0, "parse_single": 0, "prefetch_pass": 1}
+            engine.set_option(option, defaults[option])
+        if want is None:
+            want = got
+            ref = orc.merge_counts(orc.find_kmers_text(text[a:b].decode(), 25, 2)
+                                   for a, b in zip(offs, list(offs[1:]) + [len(text)]))
+            assert got == ref, diff_msg(got, ref)
+        else:
+            assert got == want, f"{option}={value}: {diff_msg(got, want)}"
