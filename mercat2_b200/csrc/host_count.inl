@@ -66,11 +66,11 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
     const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * (ks ? 0.8 : 1.0)));
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
-    DBuf<u32> ghist(e, nb), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
     struct Tail { ull total, out_n; u32 ovf_n, pad; };
-    DBuf<Tail> tail(e, 1);
+    // (the bucket histogram and the result counters share one allocation: one memset per chunk instead of two)
+    DBuf<u32> ghist(e, nb + sizeof(Tail) / 4), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
+    struct { Tail* p; } tail{reinterpret_cast<Tail*>(ghist.p + nb)};       // nb is a multiple of 128: 8-byte aligned
     ghist.zero();
-    tail.zero();
     const size_t hist_smem = (size_t)nb * 4;
     if (ks) {
         static thread_local bool attr_set = false;
@@ -475,20 +475,17 @@ static FnStats fn_single_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<F
     const u64 mis = (u64)(uintptr_t)sp.text & 15ull;
     sp.ntiles = div_up(mis + sp.len, FN_TILE);
     const u64 cap_sym = sp.len + 1;                              // every symbol comes from its own text byte
-    sp.codes.alloc(e, div_up(cap_sym, 16) + 4);
-    sp.bad.alloc(e, div_up(cap_sym, 32) + 4);
-    sp.codes.zero();
-    sp.bad.zero();
+    sp.alloc_packed(e, cap_sym);
     DBuf<ull> desc(e, sp.ntiles);
     DBuf<u32> ticket(e, 1);
     desc.zero();
     ticket.zero();
     if (with_stats)
         LAUNCHN(e, "fn_parse_single_kernel<stats>", fn_parse_single_kernel<true>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len,
-                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad.p, st.p);
+                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad, st.p);
     else
         LAUNCHN(e, "fn_parse_single_kernel", fn_parse_single_kernel<false>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len,
-                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad.p, st.p);
+                (u32)sp.ntiles, desc.p, ticket.p, sp.codes.p, sp.bad, st.p);
     const FnStats fs = read_scalar<FnStats>(e, st.p);
     sp.nsym = fs.n_sym;
     if (getenv("MC2_DEBUG_FAST"))
@@ -499,12 +496,9 @@ static FnStats fn_single_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<F
 
 // write pass: 2-bit codes + bad bits (also counts the kept non-ACGT bytes into st->packed2)
 static void fn_write_pass(mc2_engine* e, FnSpan& sp, DBuf<FnStats>& st) {
-    sp.codes.alloc(e, div_up(sp.nsym, 16) + 4);
-    sp.bad.alloc(e, div_up(sp.nsym, 32) + 4);
-    sp.codes.zero();
-    sp.bad.zero();
+    sp.alloc_packed(e, sp.nsym);
     LAUNCH(e, fn_parse_kernel<1>, (unsigned)sp.ntiles, FN_THREADS, 0, sp.text, sp.len, sp.tstate.p, sp.tcnt.p, (const u64*)sp.toff.p,
-           sp.codes.p, sp.bad.p, st.p);
+           sp.codes.p, sp.bad, st.p);
     sp.tstate.release();
     sp.tcnt.release();
     sp.toff.release();
@@ -744,7 +738,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         const bool wide_counts = nsym_total >= (1ull << 32);              // a u32 bin could wrap: fold span by span into 64 bits
         for (auto& sp : spans) {
             if (!sp.nsym) continue;
-            fn_dense_span(e, s, PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+            fn_dense_span(e, s, PackedView{sp.codes.p, sp.bad, sp.nsym});
             if (wide_counts) {
                 if (!s->dense_chunk64.p) { s->dense_chunk64.alloc(e, plan.bins); s->dense_chunk64.zero(); }
                 LAUNCH(e, dense_fold_batch_kernel, fgrid, 256, 0, s->dense_chunk.p, s->dense_chunk64.p, plan.bins);
@@ -757,7 +751,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         return true;
     }
     if (nspans == 1 && nsym_total <= hash_max) {
-        PackedView pv{spans[0].codes.p, spans[0].bad.p, spans[0].nsym};
+        PackedView pv{spans[0].codes.p, spans[0].bad, spans[0].nsym};
         // the write pass's statistics come back with the hash path's own final readback (one sync fewer per chunk)
         e->ride_dev = st.p;
         e->ride_len = sizeof(FnStats);
@@ -777,7 +771,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     if (!e->opt_big_chunks) return false;
     std::vector<PackedView> pvs;
     for (auto& sp : spans)
-        if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+        if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
     if (!sparse_chunk_hash_big(e, s, pvs, nullptr, hash_max)) return false;
     const FnStats fs3 = read_scalar<FnStats>(e, st.p);
     *need_exceptions = (fs3.packed2 >> 32) != 0;

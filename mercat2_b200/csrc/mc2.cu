@@ -185,6 +185,11 @@ static void dev_exclusive_scan(mc2_engine* e, const T* in, O* out, u64 n, ull* t
         if (total_dev) CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(ull), e->stream));
         return;
     }
+    if (n <= SCAN_SMALL_MAX) {
+        auto small = scan_small_kernel<T, O>;
+        LAUNCHN(e, "scan_small_kernel", small, 1, SCAN1_THREADS, 0, in, out, (u32)n, total_dev);
+        return;
+    }
     const u64 ntiles = div_up(n, SCAN_TILE);
     DBuf<u64> sums(e, ntiles);
     LAUNCH(e, scan_reduce_kernel<T>, (unsigned)ntiles, SCAN_THREADS, 0, in, n, sums.p);
@@ -255,7 +260,14 @@ struct FnSpan {
     DBuf<u8> tstate;
     DBuf<u32> tcnt;
     DBuf<u64> toff;
-    DBuf<u32> codes, bad;
+    DBuf<u32> codes;                        // 2-bit codes, followed in the same allocation by the bad bits (one memset)
+    u32* bad = nullptr;
+    void alloc_packed(mc2_engine* e, u64 nsym) {
+        const u64 wc = (div_up(nsym, 16) + 4 + 3) & ~3ull, wb = div_up(nsym, 32) + 4;
+        codes.alloc(e, wc + wb);
+        codes.zero();
+        bad = codes.p + wc;
+    }
 };
 
 // The count pass of the NEXT chunk, enqueued ahead of the current chunk's final readback so that one host
@@ -691,7 +703,7 @@ int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int spa
             if (fs.complex) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text is not plain FASTA (whitespace, '*' or non-ASCII bytes in sequence lines)");
             if (!sp.nsym) continue;
             if (!single) fn_write_pass(e, sp, st);
-            pvs.push_back(PackedView{sp.codes.p, sp.bad.p, sp.nsym});
+            pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
         }
         if (!level0_partition(e, k, pvs, nullptr, groups, HC_MULT1, (1ull << 32) - 1, 0, ks->l0))
             throw Mc2Error(MC2_ERR_LIMIT, "key partition: the keys do not fit in free device memory");

@@ -62,6 +62,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const T* in, O*
     }
 }
 
+// small inputs (<= SCAN_SMALL_MAX elements): one CTA does the whole scan -- one launch instead of three
+#define SCAN_SMALL_MAX 32768u
+template <typename T, typename O>
+__global__ void __launch_bounds__(SCAN1_THREADS) scan_small_kernel(const T* in, O* out, u32 n, ull* total_out) {
+    __shared__ u64 sm[SCAN1_THREADS / 32 + 1];
+    const u32 per = (n + SCAN1_THREADS - 1) / SCAN1_THREADS;           // <= 32 consecutive elements per thread
+    const u32 t0 = min(n, threadIdx.x * per), t1 = min(n, t0 + per);
+    T v[32];
+    u64 acc = 0;
+#pragma unroll
+    for (u32 j = 0; j < 32; ++j) {
+        v[j] = (j < per && t0 + j < t1) ? in[t0 + j] : (T)0;
+        acc += (u64)v[j];
+    }
+    u64 total;
+    u64 run = block_exclusive_sum64<SCAN1_THREADS / 32>(acc, sm, &total);
+#pragma unroll
+    for (u32 j = 0; j < 32; ++j) {
+        if (j < per && t0 + j < t1) out[t0 + j] = (O)run;
+        run += (u64)v[j];
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+
 // ---- radix sort -----------------------------------------------------------------------------------
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)

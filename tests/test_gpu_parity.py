@@ -763,3 +763,32 @@ def test_experiment_variants_stay_exact(engine, option, value):
             assert got == ref, diff_msg(got, ref)
         else:
             assert got == want, f"{option}={value}: {diff_msg(got, want)}"
+
+
+def test_bench_json_contract():
+    """bench.py prints ONE JSON line with the keys the driver reads (both arms), on a small shard"""
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(__file__), "..")
+    common = ["--reads-per-gpu", "700000", "--steps", "2", "--warmup", "3", "--cpu-reads", "20000"]
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *common], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["value"] > 0 and line["gpu_launches"] > 0
+    assert "workload" in line["config"] and line["vs_baseline"] is None and line["dtype"] == "u64"
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in line["e2e"], key
+    assert line["e2e"]["h2d_bytes_per_step"] == 700000 * 164 and line["e2e"]["value"] > 0
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in line["cpu_baseline"], key
+    ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-reads", "20000"], capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    rline = json.loads(ref.stdout.strip().splitlines()[-1])
+    assert rline["impl"] == "reference" and rline["metric"] == line["metric"] and rline["unit"] == line["unit"]
+    assert rline["cpu_baseline"]["kind"] in ("port", "reference") and rline["e2e"]["h2d_bytes_per_step"] == 0
