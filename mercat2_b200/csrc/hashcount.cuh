@@ -284,7 +284,9 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
             asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x) : "l"(keys1 + base + j * EX_THREADS + threadIdx.x));
             return x;
         };
-        hc_group_and_write2<USE_DST>([&](int i) { return mine[i]; }, again, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
+        auto first = [&](int i) { return mine[i]; };
+        if (full) hc_group_and_write3<USE_DST, true>(first, again, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2, nullptr, HC_TILE);
+        else hc_group_and_write2<USE_DST>(first, again, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
     } else {
         hc_group_and_write<USE_DST>([&](int i) { return mine[i]; }, valid, nb2, dig, stage, sdst, cnt, loff, gbase, sm, cur2 + b1 * nb2, keys2);
     }
