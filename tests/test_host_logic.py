@@ -131,3 +131,16 @@ def test_distributed_host_helpers():
     got = {bytes(r): int(c) for r, c in zip(sk, sc)}
     assert got == {b"ANT": 3, b"NNN": 12, b"acg": 4}
     assert [bytes(r) for r in sk] == sorted(got)
+
+
+def test_bind_to_gpu_numa_is_safe_without_a_gpu():
+    """the NUMA helper must never raise (no NVML / no device -> False) and must not change affinity then"""
+    import os
+    import mercat2_b200
+    before = os.sched_getaffinity(0)
+    ok = mercat2_b200.bind_to_gpu_numa(0)
+    assert ok in (True, False)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
