@@ -261,7 +261,9 @@ def main():
     for _ in range(args.warmup):
         rows, n_chunks = step_resident()
     launches0 = engine.stat("launches")
-    engine.set_option("profile", 2)          # per-kernel CUDA-event timing, totals cleared
+    # CUDA events on the engine's stream around the three long kernels of the path (scatter 1, scatter 2, count) -- the
+    # dominant kernel is one of them; MC2_BENCH_PROFILE=2 times every launch (costs ~6 % of the step)
+    engine.set_option("profile", int(os.environ.get("MC2_BENCH_PROFILE", "3")))
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -328,7 +330,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         # dominant kernel: largest share of the per-kernel event time
-        tot_us = sum(v["us"] for v in profile.values()) or 1.0
+        tot_us = dev_us if dev_us > 0 else (sum(v["us"] for v in profile.values()) or 1.0)   # device time of the timed steps
         top = max(profile.items(), key=lambda kv: kv[1]["us"]) if profile else ("none", {"launches": 1, "us": 1.0})
         windows_per_chunk = (bases_per_step * (READ_LEN - args.k + 1) / READ_LEN) / max(1, n_chunks)
         alg = algorithmic_bytes(top[0], windows_per_chunk, nbytes / max(1, n_chunks), args.k)

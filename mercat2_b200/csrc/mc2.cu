@@ -90,16 +90,24 @@ struct mc2_engine {
     }
 };
 
+// profile 1/2: CUDA events around every kernel; 3: only around the three long kernels of the sparse path (the events
+// themselves cost ~6 % of a step when every launch carries a pair)
+static inline bool prof_on(const mc2_engine* e, const char* name) {
+    if (!e->profile) return false;
+    if (e->profile != 3) return true;
+    return !strncmp(name, "hc_scatter2", 11) || !strncmp(name, "fn_scatter1", 11) || !strncmp(name, "hc_count2", 9);
+}
+
 #define LAUNCHN(e, name, kern, grid, block, smem, ...)                            \
     do {                                                                          \
         cudaEvent_t _pa = nullptr, _pb = nullptr;                                 \
-        if ((e)->profile) {                                                       \
+        if (prof_on((e), name)) {                                                 \
             _pa = (e)->get_event();                                               \
             _pb = (e)->get_event();                                               \
             cudaEventRecord(_pa, (e)->stream);                                    \
         }                                                                         \
         kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);              \
-        if ((e)->profile) {                                                       \
+        if (_pa) {                                                                \
             cudaEventRecord(_pb, (e)->stream);                                    \
             (e)->prof_pending.push_back({name, _pa, _pb});                        \
             if ((e)->prof_pending.size() >= 4096) (e)->resolve_profile();         \
@@ -406,7 +414,11 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "file_piece_bytes") e->opt_file_piece = (u64)std::max<int64_t>(4096, value);
     else if (n == "span_bytes") e->opt_span_bytes = value < 4096 ? 4096 : (value > (3ull << 30) ? (3ull << 30) : (u64)value);
     else if (n == "hash_bucket_keys") e->opt_hash_bucket_keys = (u64)std::max<int64_t>(value, 16);
-    else if (n == "profile") { e->resolve_profile(); e->profile = value ? 1 : 0; if (value == 2) e->prof_total.clear(); }
+    else if (n == "profile") {          // 0 off, 1 on, 2 on + totals cleared, 3 = like 2 but only the three long kernels carry events
+        e->resolve_profile();
+        e->profile = value == 3 ? 3 : (value ? 1 : 0);
+        if (value >= 2) e->prof_total.clear();
+    }
     else throw Mc2Error(MC2_ERR_INVALID, "unknown option " + n);
     API_END
 }
