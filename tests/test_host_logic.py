@@ -144,3 +144,18 @@ def test_bind_to_gpu_numa_is_safe_without_a_gpu():
         assert os.sched_getaffinity(0) == before
     else:
         os.sched_setaffinity(0, before)
+
+
+def test_public_header_is_plain_c():
+    """the drop-in boundary must be bindable from C (cgo / ctypes / JNI stubs): the header compiles as C99 and as C++"""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    header = Path(__file__).resolve().parents[1] / "include" / "mercat2_b200.h"
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(header)], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++11", "-fsyntax-only", "-x", "c++", str(header)], check=True)
