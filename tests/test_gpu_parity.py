@@ -792,3 +792,24 @@ def test_bench_json_contract():
     rline = json.loads(ref.stdout.strip().splitlines()[-1])
     assert rline["impl"] == "reference" and rline["metric"] == line["metric"] and rline["unit"] == line["unit"]
     assert rline["cpu_baseline"]["kind"] in ("port", "reference") and rline["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_c_example_end_to_end(tmp_path):
+    """the C client of examples/count_file.c produces the reference's TSV for config 1 (k=3, -c 10) from the .gz file"""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    gcc = shutil.which("gcc")
+    lib = root / "mercat2_b200" / "libmercat2_b200.so"
+    if not gcc:
+        pytest.skip("no gcc")
+    exe = tmp_path / "count_file"
+    subprocess.run([gcc, "-std=c99", f"-I{root / 'include'}", str(root / "examples" / "count_file.c"), f"-L{lib.parent}",
+                    "-lmercat2_b200", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], check=True)
+    src = GOLDEN / "data/fna_gz/DJ.fna.gz"
+    out = tmp_path / "DJ_counts.tsv"
+    run = subprocess.run([str(exe), str(src), "3", "10", "0", str(out)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    want = orc.tsv_bytes("sample", orc.find_kmers(src, 3, 10))
+    assert out.read_bytes() == want and "Significant k-mers: 64" in run.stdout

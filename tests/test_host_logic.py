@@ -159,3 +159,24 @@ def test_public_header_is_plain_c():
     gxx = shutil.which("g++")
     if gxx:
         subprocess.run([gxx, "-std=c++11", "-fsyntax-only", "-x", "c++", str(header)], check=True)
+
+
+def test_c_example_links_against_the_abi(tmp_path):
+    """examples/count_file.c (a plain C99 client) compiles and links against the shared library; without a GPU it
+    must fail loudly at mc2_engine_create (no CPU fallback)"""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    import torch
+    root = Path(__file__).resolve().parents[1]
+    gcc = shutil.which("gcc")
+    lib = root / "mercat2_b200" / "libmercat2_b200.so"
+    if not gcc or not lib.exists():
+        pytest.skip("needs gcc and the built library")
+    exe = tmp_path / "count_file"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", f"-I{root / 'include'}", str(root / "examples" / "count_file.c"),
+                    f"-L{lib.parent}", "-lmercat2_b200", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], check=True)
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe), str(root / "tests/golden/data/fna_gz/DJ.fna.gz"), "3", "10", "0", str(tmp_path / "x.tsv")],
+                             capture_output=True, text=True)
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr and not (tmp_path / "x.tsv").exists()
