@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- input bases/s of the k-mer counting hot path on B200.
 
-Workload (BASELINE.json config 4, the one the metric is quoted on): synthetic 150-bp metagenome reads
-(200 genomes x 5 Mbp, 0.1 % substitutions, FASTA framing '>r%010d\\n' + 150 bases + '\\n' = 164 B per
-read), nucleotide k=31, the reference's default flags -c 10 -s 100.  The 100 Gbp job is sharded over 8
-GPUs: each rank owns reads_per_gpu reads (default 12.5 Gbp, so N=8 is exactly the named 100 Gbp);
-scaling is weak (fixed work per GPU).  A step is one pass of the hot path (chunk -> parse -> extract ->
-count -> per-chunk filter -> sample table) over the rank's shard.
+Headline workload = BASELINE.json config 4 AS WRITTEN (SURVEY 8d run (i)): synthetic 150-bp metagenome reads (200
+genomes x 5 Mbp, 0.1 % substitutions, FASTA framing '>r%010d\\n' + 150 bases + '\\n' = 164 B per read), nucleotide
+k=31, ONE global table: `-s 0 -c 2` (no chunking: the min-count filter sees whole-sample counts).  Every rank owns
+reads_per_gpu reads (default 12.5 Gbp, so N=8 is exactly the named 100 Gbp; weak scaling).  A step is one pass of
+the hot path over the job's reads:
 
-  value  : whole-job bases/s with the FASTA text already resident in HBM
-  e2e    : the same through the C ABI with the text in pinned HOST memory (H2D inside the timed
-           region) and the result table read back (D2H)
-  roofline / cpu_baseline: see DESIGN.md
+  N = 1   text -> packed symbols -> order-preserving 64-bit keys, range-partitioned in HBM -> shared-memory tables ->
+          -c filter -> the sorted table (rows born sorted: nothing is sorted afterwards)
+  N > 1   the same with the key space cut into N slices: every rank partitions the keys of ITS reads by key range,
+          NCCL all-to-all (before the filter) moves each slice to its owner, the owner counts it; rank order = key
+          order, the job's table is the concatenation of the ranks' parts (bin/mercat2.py:119-127's reducer)
 
-`--impl reference` times the CPU reference arm (the oracle port of the reference's Python counter on
-all host cores; /root/reference does not exist on the GPU box) on a bounded sample of the same reads.
+  value      whole-job bases/s with the FASTA text already resident in HBM
+  e2e        the same through the public API with the text in pinned HOST memory (H2D inside the timed region) and
+             the table (64-bit key + count per row) read back into pinned host memory (D2H)
+  roofline   dominant kernel of the timed region against the measured HBM peak; pipeline_* = the whole path against
+             SURVEY 8(d)'s algorithmic bytes
+  phases     per-phase milliseconds of a step (parse / partition / exchange / count / emit)
+  check      table digest on a CPU-sized prefix, engine vs oracle, same pieces and flags
+  secondary  the per-chunk configuration (`-s 100 -c 10`, the reference's defaults) on the same reads
+
+`--impl reference` times the CPU reference arm (the oracle port of the reference's Python counter on all host cores;
+/root/reference does not exist on the GPU box) on a bounded prefix of the same reads.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import multiprocessing
 import os
@@ -36,6 +46,7 @@ READ_LEN = 150
 REC_BYTES = 13 + READ_LEN + 1          # '>r%010d\n' + bases + '\n'
 N_GENOMES, GENOME_LEN = 200, 5_000_000
 SEED = 20240531
+METRIC = "input bases/sec (k-mers counted/sec) per GPU and 8xB200; % of HBM roofline"
 
 
 def parse_args():
@@ -46,12 +57,15 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-gpu", type=int, default=int(os.environ.get("MC2_BENCH_READS", 83_333_334)))
     ap.add_argument("-k", type=int, default=31)
-    ap.add_argument("-c", type=int, default=10)
-    ap.add_argument("-s", type=int, default=100, help="chunk size in MB (reference default 100)")
+    ap.add_argument("-c", type=int, default=2)
+    ap.add_argument("-s", type=int, default=0, help="chunk size in MB (0 = one global table, the headline)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU sample (0 = auto)")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of the 1 Gbp metagenome to synthesise (profiling runs)")
+    ap.add_argument("--groups-per-rank", type=int, default=24, help="N > 1: exchange rounds (key ranges per rank)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
     return ap.parse_args()
 
 
@@ -181,6 +195,8 @@ def cpu_run(files, k, c, pool, out_tsv):
     if total:
         with open(out_tsv, "wb") as out:
             out.write(orc.tsv_bytes("sample", total))
+    elif os.path.exists(out_tsv):
+        os.remove(out_tsv)
     return time.perf_counter() - t0
 
 
@@ -203,6 +219,51 @@ def cpu_reads_auto(cores, k):
     return cores * per_core_bases // READ_LEN
 
 
+def workload_name(k, c, s):
+    kind = "one global table (SURVEY 8d run (i))" if s == 0 else "per-chunk filter (run (ii))"
+    return f"cfg4: synthetic 150-bp metagenome reads, nucleotide k={k} -c {c} -s {s}: {kind}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# roofline accounting
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_step(kernel, windows, text_bytes, rows):
+    """Algorithmic bytes ALL launches of the named kernel move in one step over this rank's reads: what the kernel
+    must read and write once, not what it happens to move.  windows = k-mer windows, rows = surviving rows."""
+    symbols = text_bytes * (READ_LEN + 1) / REC_BYTES            # bases + one separator per read
+    packed = symbols * 0.375                                     # 2-bit codes + 1 validity bit per symbol
+    table = {
+        "fn_parse_kernel<0>": text_bytes, "fn_parse_kernel<2>": text_bytes, "fn_parse_kernel<1>": text_bytes + packed,
+        "fn_hist_kernel": packed, "fn_hist_kernel<level0>": packed,
+        "fn_scatter1_kernel": packed + 8.0 * windows,            # every key written once
+        "hk_hist_kernel": 8.0 * windows, "hk_hist_kernel<level0>": 8.0 * windows,
+        "hk_scatter1_kernel": 16.0 * windows,                    # every key read once and written once
+        "hc_scatter2_kernel": 16.0 * windows,
+        "rc_count_kernel<0>": 8.0 * windows + 16.0 * rows,       # every key read once, every surviving row written once
+        "rc_count_kernel<1>": 8.0 * windows + 16.0 * rows,
+        "rc_gather_kernel": 32.0 * rows,
+        "chunk_has_cr_kernel": text_bytes,
+    }
+    return table.get(kernel)
+
+
+PHASES = (("parse", ("fn_parse", "chunk_", "scan_")), ("partition", ("rp_", "fn_hist", "fn_scatter1", "hk_", "hc_scan", "hc_scatter2")),
+          ("count", ("rc_count",)), ("emit", ("rc_offsets", "rc_gather", "part_ends", "rs_", "seg_", "rle_", "gather_")))
+
+
+def phases_from_profile(profile, steps):
+    out = {name: 0.0 for name, _ in PHASES}
+    out["other"] = 0.0
+    for kern, v in profile.items():
+        for name, prefixes in PHASES:
+            if kern.startswith(prefixes):
+                out[name] += v["us"]
+                break
+        else:
+            out["other"] += v["us"]
+    return {f"{k}_ms": round(v / 1e3 / max(1, steps), 3) for k, v in out.items()}
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -215,9 +276,11 @@ def main():
             return 0
         return reference_arm(args, world)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import mercat2_b200
+    from mercat2_b200 import distributed as mcd
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -237,86 +300,150 @@ def main():
     text = make_reads_text(device, genomes, n_reads, rank * n_reads)
     torch.cuda.synchronize()
     nbytes = text.numel()
-    chunk_bytes = args.s * 1024 * 1024 if (args.s > 0 and nbytes >= args.s * 1024 * 1024) else 0
+    windows = n_reads * (READ_LEN - args.k + 1)
 
     engine = mercat2_b200.Engine(local)
 
-    def merged(table):
-        """N > 1: the ranks hold pieces of ONE sample -- sum their filtered tables on the devices (key-range
-        all-to-all over NCCL); every rank keeps the rows of its own key range."""
-        if world == 1:
-            return table
-        from mercat2_b200 import distributed as mcd
-        part = mcd.merge_table_device(engine, table, dist, device)
-        table.close()
-        return part
+    def count(buf, k, c, s_mb, timings=None):
+        """one pass of the hot path over this rank's reads -> this rank's part of the job's table"""
+        chunk_bytes = s_mb * 1024 * 1024 if (s_mb > 0 and nbytes >= s_mb * 1024 * 1024) else 0
+        if s_mb == 0 and world > 1:
+            # ONE piece whose text is spread over the ranks: keys exchanged before the filter
+            return mcd.count_piece_position_sharded(engine, buf, k, c, dist, device, groups_per_rank=args.groups_per_rank, timings=timings), 1
+        table, offsets = engine.count_sample(buf, k, c, chunk_bytes)
+        if world > 1:                       # whole pieces per rank, filtered per piece: sum the filtered tables by key range
+            part = mcd.merge_table_device(engine, table, dist, device)
+            table.close()
+            table = part
+        return table, len(offsets)
 
-    def step_resident():
-        table, offsets = engine.count_sample(text, args.k, args.c, chunk_bytes)
-        table = merged(table)
+    def step_resident(timings=None):
+        table, n_chunks = count(text, args.k, args.c, args.s, timings)
         rows = table.rows
         table.close()
-        return rows, len(offsets)
+        return rows, n_chunks
+
+    # ---- correctness gate before anything is timed ---------------------------------------------------
+    check = None
+    if not args.no_check:
+        check = run_check(engine, text, args, rank, world, dist if world > 1 else None, device)
 
     for _ in range(args.warmup):
         rows, n_chunks = step_resident()
     launches0 = engine.stat("launches")
-    # CUDA events on the engine's stream around the three long kernels of the path (scatter 1, scatter 2, count) -- the
-    # dominant kernel is one of them; MC2_BENCH_PROFILE=2 times every launch (costs ~6 % of the step)
-    engine.set_option("profile", int(os.environ.get("MC2_BENCH_PROFILE", "3")))
+    # CUDA events on the engine's stream around every kernel of the path (MC2_BENCH_PROFILE=3: only the long ones)
+    engine.set_option("profile", int(os.environ.get("MC2_BENCH_PROFILE", "2")))
     sampler = ClockSampler(local)
     sampler.start()
+    timings = {}
     barrier()
     t0 = time.perf_counter()
-    dev_us = 0.0
     for _ in range(args.steps):
-        rows, n_chunks = step_resident()
-        dev_us += engine.stat("device_us")
+        rows, n_chunks = step_resident(timings if world > 1 and args.s == 0 else None)
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = engine.stat("launches") - launches0
     profile = engine.profile()
     engine.set_option("profile", 0)
+    kernel_us = sum(v["us"] for v in profile.values())
 
-    # ---- e2e: host buffer in, table out, through the same C-ABI call -------------------------------
+    # ---- secondary: the per-chunk configuration on the same reads --------------------------------------
+    secondary = None
+    if not args.no_secondary and args.s == 0:
+        s2, c2 = 100, 10
+        for _ in range(2):
+            t2, nch2 = count(text, args.k, c2, s2)
+            rows2 = t2.rows
+            t2.close()
+        engine.set_option("profile", 2)
+        barrier()
+        t1 = time.perf_counter()
+        sec_steps = max(2, min(args.steps, 3))
+        for _ in range(sec_steps):
+            t2, nch2 = count(text, args.k, c2, s2)
+            rows2 = t2.rows
+            t2.close()
+        barrier()
+        sec_elapsed = time.perf_counter() - t1
+        prof2 = engine.profile()
+        engine.set_option("profile", 0)
+        secondary = {"elapsed": sec_elapsed, "steps": sec_steps, "rows": rows2, "chunks": nch2, "profile": prof2, "s": s2, "c": c2}
+
+    # ---- e2e: host buffer in, table out, through the same public call ----------------------------------
     e2e = None
     if not args.no_e2e:
         import psutil
-        # every rank pins its own shard; the decision is taken once (rank 0) so that all ranks agree
-        fits = [psutil.virtual_memory().available > int(1.25 * nbytes * world) + (16 << 30)]
+        out_rows_cap = int(rows * 1.1) + 1024
+        need = nbytes + 16 * out_rows_cap
+        fits = [psutil.virtual_memory().available > int(1.25 * need * world) + (16 << 30)]
         if world > 1:
             dist.broadcast_object_list(fits, src=0)
         if fits[0]:
             host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             host.copy_(text)
+            out_keys = torch.empty(out_rows_cap, dtype=torch.int64, pin_memory=True)
+            out_counts = torch.empty(out_rows_cap, dtype=torch.int64, pin_memory=True)
             torch.cuda.synchronize()
-            e_steps = max(1, min(args.steps, 3))
+            e_steps = max(1, min(args.steps, 5))
 
             def step_e2e():
-                table, _ = engine.count_sample(host, args.k, args.c, chunk_bytes)
-                table = merged(table)
-                kmers, counts = table.arrays()
+                table, _ = count(host, args.k, args.c, args.s)
+                n = table.rows
+                if n > out_rows_cap:
+                    raise RuntimeError("e2e: more rows than the pinned result buffers hold")
+                got = table.packed_to_host(out_keys.data_ptr(), out_counts.data_ptr(), out_rows_cap)
                 table.close()
-                return kmers.nbytes + counts.nbytes
+                return got * 16
 
             d2h = step_e2e()                   # warm-up
+            times = []
+            for _ in range(e_steps):
+                barrier()
+                t1 = time.perf_counter()
+                d2h = step_e2e()
+                barrier()
+                times.append(time.perf_counter() - t1)
+            # a plain pinned-H2D ceiling measured in the same run (all ranks at once)
+            dst = torch.empty(min(nbytes, 4 << 30), dtype=torch.uint8, device=device)
             barrier()
             t1 = time.perf_counter()
-            for _ in range(e_steps):
-                d2h = step_e2e()
+            for _ in range(3):
+                dst.copy_(host[:dst.numel()], non_blocking=True)
             barrier()
-            e_elapsed = time.perf_counter() - t1
-            e2e = {"steps": e_steps, "elapsed": e_elapsed, "h2d": nbytes, "d2h": d2h}
-            del host
+            h2d_gbs = 3 * dst.numel() / (time.perf_counter() - t1) / 1e9
+            del dst
+            e2e = {"steps": e_steps, "times": times, "h2d": nbytes, "d2h": d2h, "h2d_ceiling_gbs": h2d_gbs}
+            del host, out_keys, out_counts
 
     # ---- max over ranks -------------------------------------------------------------------------------
+    rows_total = rows
     if world > 1:
-        t = torch.tensor([elapsed, e2e["elapsed"] if e2e else 0.0, dev_us], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed, e_el, dev_us = t.tolist()
+        vals = [elapsed, kernel_us, float(rows)] + (e2e["times"] + [e2e["h2d_ceiling_gbs"], float(e2e["d2h"])] if e2e else [])
+        t = torch.tensor(vals, device=device, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed = tmax[0].item()
+        rows_total = int(tsum[2].item())
         if e2e:
-            e2e["elapsed"] = e_el
+            ns = len(e2e["times"])
+            e2e["times"] = tmax[3:3 + ns].tolist()
+            e2e["h2d_ceiling_gbs"] = tsum[3 + ns].item()                    # aggregate over the ranks
+            e2e["d2h"] = int(tsum[4 + ns].item())
+            e2e["h2d"] = nbytes * world
+        if secondary:
+            t2 = torch.tensor([secondary["elapsed"], float(secondary["rows"])], device=device, dtype=torch.float64)
+            t2m = t2.clone()
+            dist.all_reduce(t2m, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            secondary["elapsed"], secondary["rows"] = t2m[0].item(), int(t2[1].item())
+        if timings:
+            keys = sorted(timings)
+            tt = torch.tensor([float(timings[k2]) for k2 in keys], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            timings = dict(zip(keys, tt.tolist()))
 
     out = None
     if rank == 0:
@@ -329,50 +456,85 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel: largest share of the per-kernel event time
-        tot_us = dev_us if dev_us > 0 else (sum(v["us"] for v in profile.values()) or 1.0)   # device time of the timed steps
-        top = max(profile.items(), key=lambda kv: kv[1]["us"]) if profile else ("none", {"launches": 1, "us": 1.0})
-        windows_per_chunk = (bases_per_step * (READ_LEN - args.k + 1) / READ_LEN) / max(1, n_chunks)
-        alg = algorithmic_bytes(top[0], windows_per_chunk, nbytes / max(1, n_chunks), args.k)
-        avg_us = top[1]["us"] / max(1, top[1]["launches"])
-        achieved = alg / (avg_us * 1e-6) / 1e9 if alg else None
-        # the whole path against SURVEY 8(d)'s sparse formula: text read once + every key written once and read
-        # once (8 + 8 B per window) + 12 B per row of the emitted table (rows = survivors of the -c filter)
-        w_total = bases_per_step * (READ_LEN - args.k + 1) / READ_LEN
-        pipeline_alg = nbytes + 16.0 * w_total + 12.0 * rows
-        pipeline_gbs = pipeline_alg * args.steps / (dev_us * 1e-6) / 1e9 if dev_us else None
-        traffic, traffic_src = None, None
+
+        def roofline_of(prof, steps, rows_rank, step_s):
+            """dominant kernel (largest share of the per-kernel event time of rank 0) + the whole path"""
+            tot_us = sum(v["us"] for v in prof.values()) or 1.0
+            top = max(prof.items(), key=lambda kv: kv[1]["us"]) if prof else ("none", {"launches": 1, "us": 1.0})
+            alg_step = algorithmic_bytes_per_step(top[0], windows, nbytes, rows_rank)
+            alg = alg_step * steps / max(1, top[1]["launches"]) if alg_step else None
+            avg_us = top[1]["us"] / max(1, top[1]["launches"])
+            achieved = alg / (avg_us * 1e-6) / 1e9 if alg else None
+            # the whole path against SURVEY 8(d)'s sparse formula: text read once + every key written once and read
+            # once (8 + 8 B per window) + 12 B per row of the emitted table
+            pipeline_alg = nbytes + 16.0 * windows + 12.0 * rows_rank
+            pipeline_gbs = pipeline_alg / step_s / 1e9
+            return top, {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "traffic_unit": "bytes per launch",
+                         "traffic_source": None, "peak_source": peak_src,
+                         "kernel_share_of_step": top[1]["us"] / tot_us,
+                         "algorithmic_bytes_per_launch": alg, "avg_launch_us": avg_us, "launches_per_step": top[1]["launches"] / steps,
+                         "pipeline_bytes_per_base": pipeline_alg / bases_per_step,
+                         "pipeline_achieved": pipeline_gbs, "pipeline_frac": pipeline_gbs / peak,
+                         "kernel_time_share_of_wall": tot_us * 1e-6 / (step_s * steps)}
+
+        top, roof = roofline_of(profile, args.steps, rows, elapsed / args.steps)
         try:                                        # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-            tj = json.loads((Path(__file__).parent / "profiles" / "traffic.json").read_text())
-            if top[0] in tj["kernels"] and n_chunks >= 2:
-                traffic, traffic_src = tj["kernels"][top[0]]["dram_bytes_per_launch"], tj["source"]
+            tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+            if top[0] in tj["kernels"]:
+                roof["traffic"], roof["traffic_source"] = tj["kernels"][top[0]]["dram_bytes_per_launch"], tj["source"]
         except (OSError, ValueError, KeyError):
             pass
+        phases = phases_from_profile(profile, args.steps)
+        if timings:
+            for key, val in timings.items():
+                phases["host_" + key] = round(val / args.steps, 3) if key.endswith("_ms") else val / args.steps
+            sent = timings.get("nvlink_bytes_sent", 0) / args.steps
+            wait_s = timings.get("exchange_wait_ms", 0) / args.steps / 1e3
+            phases["nvlink_bytes_per_rank_per_step"] = sent
+            phases["nvlink_gbs_per_direction_vs_step"] = sent / (elapsed / args.steps) / 1e9
+            phases["nvlink_exposed_wait_s"] = wait_s
+            phases["nvlink_nominal_gbs"] = 900.0
+        limiting = max(((k2, v) for k2, v in phases.items() if k2.endswith("_ms") and not k2.startswith("host_")), key=lambda kv: kv[1])[0]
+        if timings and phases.get("host_exchange_wait_ms", 0) > phases[limiting]:
+            limiting = "host_exchange_wait_ms"
+        parallelism = (f"key-range partition x{world}: NCCL all-to-all of the keys before the filter, {args.groups_per_rank} rounds"
+                       if (world > 1 and args.s == 0) else f"chunk-sharded x{world}" if world > 1 else "single GPU")
         out = {
-            "metric": "input bases/sec (k-mers counted/sec) per GPU and 8xB200; % of HBM roofline",
+            "metric": METRIC,
             "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"cfg4 shard: synthetic 150-bp metagenome reads, nucleotide k={args.k} -c {args.c} -s {args.s}",
+            "config": {"workload": workload_name(args.k, args.c, args.s),
                        "reads_per_gpu": n_reads, "bases_per_gpu_per_step": bases_per_step, "text_bytes_per_gpu": nbytes,
-                       "chunks_per_gpu": n_chunks, "surviving_rows": rows, "parallelism": f"chunk-sharded x{world}" + (" + NCCL key-range all-to-all of the filtered tables" if world > 1 else ""),
+                       "chunks_per_gpu": n_chunks, "surviving_rows": rows_total, "surviving_rows_rank0": rows, "parallelism": parallelism,
                        "numa_bound": numa_bound, "l2_policy": "input per step (>= 1 GB) is larger than L2; no flush needed"},
             "clocks": clocks,
             "gpu_launches": launches,
-            "device_ms_per_step": dev_us / args.steps / 1e3,
-            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_unit": "bytes per launch",
-                         "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel_share_of_step": top[1]["us"] / tot_us,
-                         "algorithmic_bytes_per_launch": alg, "avg_launch_us": avg_us,
-                         "pipeline_bytes_per_base": pipeline_alg / bases_per_step,
-                         "pipeline_achieved": pipeline_gbs, "pipeline_frac": (pipeline_gbs / peak) if pipeline_gbs else None},
+            "launches_per_step": launches / args.steps,
+            "roofline": roof,
+            "phases": phases, "limiting_phase": limiting,
             "kernels": {k2: {"launches": v["launches"], "ms": round(v["us"] / 1e3, 3)} for k2, v in
-                        sorted(profile.items(), key=lambda kv: -kv[1]["us"])[:12]},
+                        sorted(profile.items(), key=lambda kv: -kv[1]["us"])[:14]},
+            "check": check,
         }
+        if secondary:
+            _, roof2 = roofline_of(secondary["profile"], secondary["steps"], secondary["rows"] / world, secondary["elapsed"] / secondary["steps"])
+            out["secondary"] = {"workload": workload_name(args.k, secondary["c"], secondary["s"]),
+                                "value": world * bases_per_step * secondary["steps"] / secondary["elapsed"], "unit": "bases/s",
+                                "ms_per_step": secondary["elapsed"] / secondary["steps"] * 1e3, "steps": secondary["steps"],
+                                "chunks_per_gpu": secondary["chunks"], "surviving_rows": secondary["rows"],
+                                "roofline": {k2: roof2[k2] for k2 in ("kernel", "achieved", "frac", "kernel_share_of_step", "pipeline_frac", "pipeline_achieved")}}
         if e2e:
-            out["e2e"] = {"value": world * bases_per_step * e2e["steps"] / e2e["elapsed"], "unit": "bases/s",
-                          "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+            ts = sorted(e2e["times"])
+            med = ts[len(ts) // 2]
+            total_bases = world * bases_per_step
+            out["e2e"] = {"value": total_bases * len(ts) / sum(ts), "unit": "bases/s",
+                          "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": len(ts),
+                          "min_s": ts[0], "median_s": med, "max_s": ts[-1], "value_at_median": total_bases / med,
+                          "h2d_ceiling_gbs": e2e["h2d_ceiling_gbs"],
+                          "pcie_floor_s": (e2e["h2d"] + e2e["d2h"]) / world / (e2e["h2d_ceiling_gbs"] / world * 1e9),
+                          "note": "pcie_floor_s = (H2D + D2H bytes of one rank) / measured pinned-H2D rate of one rank when all ranks copy at once"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -386,7 +548,7 @@ def main():
         out["cpu_baseline"] = {"value": n_cpu * READ_LEN / secs, "unit": "bases/s", "cores": cores, "kind": "port",
                                "sample": f"first {n_cpu} reads of the same shard ({n_cpu * READ_LEN / 1e6:.1f} Mbp) as "
                                          f"{len(files)} chunk files, one oracle find_kmers task per file on a "
-                                         f"{cores}-process pool, serial merge + sorted TSV; {secs:.1f} s"}
+                                         f"{cores}-process pool (-c {args.c}), serial merge + sorted TSV; {secs:.1f} s"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -394,32 +556,51 @@ def main():
     return 0
 
 
-def algorithmic_bytes(kernel, windows, text_bytes, k):
-    """Algorithmic bytes of ONE launch of the named kernel for one chunk: what the
-    kernel must read and write once, not what it happens to move."""
-    name = kernel.split("<")[0]
-    symbols = text_bytes * (READ_LEN + 1) / REC_BYTES            # bases + one separator per read
-    packed = symbols * 0.375                                     # 2-bit codes + 1 validity bit per symbol
-    table = {
-        "fn_parse_kernel": text_bytes + packed if "true" in kernel else text_bytes,
-        "fn_hist_kernel": packed,
-        "fn_scatter1_kernel": packed + 8.0 * windows,            # every key written once
-        "hc_scatter1_kernel": symbols + 8.0 * windows,
-        "hc_scatter2_kernel": 16.0 * windows,                    # every key read once and written once
-        "hc_count2_kernel": 8.0 * windows,                       # every key read once
-        "hc_count_kernel": 8.0 * windows,
-        "rs_scatter_kernel": 16.0 * windows,
-        "rs_hist_kernel": 8.0 * windows,
-        "extract_keys_kernel": symbols + 8.0 * windows,
-        "chunk_candidates_kernel": text_bytes,
-    }
-    if name in table:
-        return table[name]
-    if name.startswith("parse_"):
-        return text_bytes
-    if name.startswith("dense_"):
-        return symbols
-    return None
+def run_check(engine, text, args, rank, world, dist, device):
+    """Known-answer gate on a CPU-sized prefix of the SAME reads with the SAME flags: the engine's table (through the
+    path the timed steps take) against the oracle's, as TSV digests.  N > 1 additionally runs the key-exchange path on
+    the prefix split over the ranks."""
+    import numpy as np
+    from oracle import mercat2_oracle as orc
+    n_check = min(args.reads_per_gpu, int(os.environ.get("MC2_BENCH_CHECK_READS", 40_000)))
+    pre = text[: n_check * REC_BYTES]
+    res = {"reads": n_check, "flags": f"-k {args.k} -c {args.c} -s 0"}
+    if rank == 0:
+        want = orc.find_kmers_text(pre.cpu().numpy().tobytes().decode(), args.k, args.c)
+        want_tsv = orc.tsv_bytes("sample", want) if want else b""
+        t = engine.count_text(pre, args.k, args.c)
+        got_tsv = t.tsv_bytes("sample") if t.rows else b""
+        t.close()
+        res.update({"oracle_md5": hashlib.md5(want_tsv).hexdigest(), "engine_md5": hashlib.md5(got_tsv).hexdigest(),
+                    "rows": len(want), "ok": got_tsv == want_tsv})
+        # the same prefix forced through the level-0 (very large chunk) machinery the headline uses
+        engine.set_option("hash_bucket_keys", 16)
+        try:
+            t = engine.count_text(pre, args.k, args.c)
+            big_tsv = t.tsv_bytes("sample") if t.rows else b""
+            t.close()
+        finally:
+            engine.set_option("hash_bucket_keys", 3500)
+        res["level0_ok"] = big_tsv == want_tsv
+        res["ok"] = res["ok"] and res["level0_ok"]
+    if world > 1:
+        from mercat2_b200 import distributed as mcd
+        # every rank takes its slice of the prefix (cut at read boundaries); rank parts concatenated must equal the oracle
+        per = n_check // world
+        a = rank * per * REC_BYTES
+        b = n_check * REC_BYTES if rank == world - 1 else (rank + 1) * per * REC_BYTES
+        part = mcd.count_piece_position_sharded(engine, pre[a:b], args.k, args.c, dist, device, groups_per_rank=3)
+        body = part.tsv_body() if part.rows else b""
+        part.close()
+        bodies = [None] * world
+        dist.all_gather_object(bodies, body)
+        if rank == 0:
+            res["sharded_ok"] = (b"k-mer\tsample_Count\n" + b"".join(bodies) if any(bodies) else b"") == want_tsv
+            res["ok"] = res["ok"] and res["sharded_ok"]
+    if rank == 0 and not res["ok"]:
+        print(json.dumps({"error": "bench check failed: engine table differs from the oracle", "check": res}))
+        raise SystemExit(3)
+    return res if rank == 0 else None
 
 
 def reference_arm(args, world):
@@ -457,15 +638,16 @@ def reference_arm(args, world):
     value = n_cpu * READ_LEN * len(times) / elapsed
     out = {
         "impl": "reference",
-        "metric": "input bases/sec (k-mers counted/sec) per GPU and 8xB200; % of HBM roofline",
+        "metric": METRIC,
         "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / len(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"cfg4 shard: synthetic 150-bp metagenome reads, nucleotide k={args.k} -c {args.c} -s {args.s}",
-                   "sample_reads": n_cpu},
+        "config": {"workload": workload_name(args.k, args.c, args.s), "sample_reads": n_cpu,
+                   "note": "the reference runs one find_kmers task per chunk FILE (bin/mercat2.py:120); with -s 0 a single file "
+                           "would be ONE task on ONE core, so the prefix is given to it as 2 x cores chunk files to let it use every core"},
         "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
                          "sample": f"{n_cpu} reads ({n_cpu * READ_LEN / 1e6:.1f} Mbp) per step as {2 * cores} chunk files, "
-                                   f"{cores}-process pool, serial merge + sorted TSV"},
+                                   f"{cores}-process pool, -c {args.c}, serial merge + sorted TSV"},
         "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

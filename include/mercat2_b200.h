@@ -45,7 +45,8 @@ const char* mc2_last_error(void);
 const char* mc2_version(void);
 
 /* Tunables (mostly for tests): "dense_max_bins", "smem_max_bins", "batch_symbols", "force_path"
- * (0 auto, 1 dense, 2 sparse, 3 wide), "force_encoding" (-1 auto, 0 ACGT 2-bit, 1 A-Z 5-bit, 2 byte). */
+ * (0 auto, 1 dense, 2 sparse, 3 wide), "force_encoding" (-1 auto, 0 ACGT 2-bit, 1 A-Z 5-bit, 2 byte), "sparse_algo"
+ * (0/2 range partition + shared-memory tables, 1 radix sort), "count_mode" (-1 auto, 0 / 1 see rangecount.cuh). */
 int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value);
 /* Counters: "launches" (kernels launched so far), "h2d_bytes", "d2h_bytes", "chunks", "device_ms"
  * (CUDA-event time of the last count call, microseconds in "device_us"). */
@@ -132,6 +133,10 @@ int mc2_table_info(const mc2_table* t, int* encoding, int* key_kind, uint64_t* p
 int mc2_table_device_rows(mc2_table* t, const uint64_t** keys, const uint64_t** counts, uint64_t* rows);
 /* cuts[i] = number of packed rows with key < splitters[i] (host arrays) */
 int mc2_table_lower_bound(mc2_table* t, const uint64_t* splitters, uint64_t m, uint64_t* cuts);
+/* The packed rows into HOST memory (pinned memory makes this one DMA per array): keys / counts with room for
+ * `capacity` rows; *rows = rows copied.  This is the table as the device holds it -- 16 bytes per row instead of the
+ * k + 8 bytes of mc2_table_export -- for callers that decode k-mers lazily (decode: mc2_table_info's encoding). */
+int mc2_table_export_packed(mc2_table* t, uint64_t* keys, uint64_t* counts, uint64_t capacity, uint64_t* rows);
 /* the literal-byte rows (host copies): kmers wide_rows*k bytes, counts wide_rows entries */
 int mc2_table_export_wide(mc2_table* t, char* kmers, uint64_t* counts);
 /* Build a table from packed rows (device or host memory; unsorted, equal keys are summed) plus literal-byte rows
@@ -147,18 +152,32 @@ int mc2_table_tsv_body(mc2_table* t, char* buf, uint64_t cap, uint64_t* size);
 int mc2_sample_dense(mc2_sample* s, uint64_t** table, uint64_t* bins, int* encoding);
 int mc2_sample_dense_plan(mc2_sample* s, int encoding);
 /* ---- one piece split across GPUs BEFORE the filter (SURVEY 8e grain 3; `-s 0` on a file larger than one GPU) ----
- * Every rank parses its byte range of the piece (cut at header lines) and partitions the 2-bit packed keys of all
- * its windows into `groups` groups by key hash (mc2_partition_keys: device array grouped by group id + sizes).  The
- * host layer sends group g to its owner rank (NCCL all-to-all on the device array), the owner counts the keys it
- * received as ONE chunk (mc2_sample_add_keys: the -c filter then sees whole-piece counts, exactly like
- * lib/mercat2_kmers.py:73-78 on the unsplit piece).  Windows outside the packed alphabet (N, lower case ...) are
- * counted unfiltered by mc2_count_exceptions so that the caller can sum them across ranks before filtering. */
+ * The reducer this replaces is the dict sum + filter of ONE chunk file (lib/mercat2_kmers.py:56-78) when that chunk's
+ * text lives on several GPUs.  Every rank parses its byte range of the piece (cut at header lines) into 2-bit packed
+ * symbols (mc2_keys_open) and exposes a sampled histogram of its keys' 32-bit prefixes (mc2_keys_sample: device
+ * pointer, summed over the ranks by the caller -- NCCL all-reduce -- so that all ranks cut the key space at the same
+ * keys).  mc2_keys_partition then groups the order-preserving 64-bit keys of all its windows into `groups` ascending,
+ * disjoint key ranges on its GPU (device array grouped by range + sizes + range bounds).  The host layer sends range g
+ * to its owner rank (NCCL all-to-all on the device array); the owner counts what it received for one range with
+ * mc2_sample_add_keys: every occurrence of a key is in that call, so the -c filter sees whole-piece counts exactly
+ * like lib/mercat2_kmers.py:73-78 on the unsplit piece, and the rows of successive ranges follow each other in sorted
+ * order (rank order == key order: the table is the concatenation of the ranks' parts).  Windows outside the packed
+ * alphabet (N, lower case ...) are counted unfiltered by mc2_count_exceptions so that the caller can sum them across
+ * ranks before filtering.  mc2_partition_keys = open + partition with the rank's own sample (single GPU). */
 typedef struct mc2_keys mc2_keys;
+int mc2_keys_open(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, mc2_keys** out);
+/* hist: device pointer to *entries uint32 counters (valid until mc2_keys_partition / mc2_keys_free) */
+int mc2_keys_sample(mc2_keys* ks, uint32_t** hist, uint64_t* entries);
+int mc2_keys_partition(mc2_keys* ks, uint32_t groups);
 int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, uint32_t groups, mc2_keys** out);
-/* keys: device array of *total keys, group g occupying sizes[0]+..+sizes[g-1] onward; sizes: groups entries */
-int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols);
+/* keys: device array of *total keys, range g occupying sizes[0]+..+sizes[g-1] onward; sizes: groups entries;
+ * bounds (optional): groups + 1 entries, range g holds the keys whose 32-bit prefix (the first 16 symbols, left
+ * aligned) lies in [bounds[g], bounds[g+1]) */
+int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols, uint64_t* bounds);
 void mc2_keys_free(mc2_keys* ks);
-int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space);
+/* Count n keys that are ALL occurrences of their key range within the current chunk.  prefix_lo / prefix_hi: the
+ * 32-bit prefix range the keys lie in (from mc2_keys_info's bounds; 0, 0 = unknown: the whole key space). */
+int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space, uint64_t prefix_lo, uint64_t prefix_hi);
 int mc2_count_exceptions(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, mc2_table** out);
 /* Device-to-device copy on the engine's stream, complete at return (moves a reduced table between engine memory and
  * a buffer owned by the communication library). */

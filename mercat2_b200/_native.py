@@ -49,16 +49,20 @@ SYMBOLS = [
     ("mc2_table_info", _INT, [_VP, C.POINTER(_INT), C.POINTER(_INT), _PU64, _PU64]),
     ("mc2_table_device_rows", _INT, [_VP, _PP, _PP, _PU64]),
     ("mc2_table_lower_bound", _INT, [_VP, _VP, _U64, _VP]),
+    ("mc2_table_export_packed", _INT, [_VP, _VP, _VP, _U64, _PU64]),
     ("mc2_table_export_wide", _INT, [_VP, _VP, _VP]),
     ("mc2_table_from_rows", _INT, [_VP, _INT, _INT, _INT, _VP, _VP, _U64, _INT, _VP, _VP, _U64, _PP]),
     ("mc2_table_tsv_body", _INT, [_VP, _VP, _U64, _PU64]),
     ("mc2_sample_dense", _INT, [_VP, _PP, _PU64, C.POINTER(_INT)]),
     ("mc2_sample_dense_plan", _INT, [_VP, _INT]),
     ("mc2_device_copy", _INT, [_VP, _VP, _VP, _U64]),
+    ("mc2_keys_open", _INT, [_VP, _VP, _U64, _INT, _INT, _PP]),
+    ("mc2_keys_sample", _INT, [_VP, _PP, _PU64]),
+    ("mc2_keys_partition", _INT, [_VP, C.c_uint32]),
     ("mc2_partition_keys", _INT, [_VP, _VP, _U64, _INT, _INT, C.c_uint32, _PP]),
-    ("mc2_keys_info", _INT, [_VP, _PP, _VP, _PU64, _PU64]),
+    ("mc2_keys_info", _INT, [_VP, _PP, _VP, _PU64, _PU64, _VP]),
     ("mc2_keys_free", None, [_VP]),
-    ("mc2_sample_add_keys", _INT, [_VP, _VP, _U64, _INT]),
+    ("mc2_sample_add_keys", _INT, [_VP, _VP, _U64, _INT, _U64, _U64]),
     ("mc2_count_exceptions", _INT, [_VP, _VP, _U64, _INT, _INT, _PP]),
     ("mc2_table_from_tsv", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_merge_tables", _INT, [_VP, _VP, C.c_uint32, _PP]),
@@ -202,6 +206,22 @@ class Table:
         lib = self._engine._lib
         _check(lib, lib.mc2_table_device_rows(self._h, C.byref(keys), C.byref(counts), C.byref(n)))
         return keys.value or 0, counts.value or 0, int(n.value)
+
+    def packed_to_host(self, keys_addr: int, counts_addr: int, capacity: int) -> int:
+        """Copy the packed rows (64-bit order-preserving key + count) to host buffers at raw addresses (pinned memory:
+        one DMA per array); returns the rows copied."""
+        n = C.c_uint64(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_export_packed(self._h, keys_addr or None, counts_addr or None, capacity, C.byref(n)))
+        return int(n.value)
+
+    def packed_arrays(self):
+        """(keys uint64[rows], counts uint64[rows]) of the packed rows, sorted by key."""
+        n = self.info()["packed_rows"]
+        keys = np.empty(n, dtype=np.uint64)
+        counts = np.empty(n, dtype=np.uint64)
+        self.packed_to_host(keys.ctypes.data, counts.ctypes.data, n)
+        return keys, counts
 
     def lower_bound(self, splitters) -> list:
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
@@ -372,11 +392,19 @@ class Engine:
         return Matrix(self, out, len(tables))
 
     def partition_keys(self, data, k: int, groups: int) -> "Keys":
-        """2-bit packed keys of every window of a plain nucleotide FASTA text, grouped by key hash into `groups` groups."""
+        """Order-preserving 64-bit keys of every window of a plain nucleotide FASTA text, grouped into `groups`
+        ascending key ranges (boundaries from this text's own key sample)."""
+        keys = self.open_keys(data, k)
+        keys.partition(groups)
+        return keys
+
+    def open_keys(self, data, k: int) -> "Keys":
+        """Parse a plain nucleotide FASTA text into packed symbols and sample its key prefixes; the caller may sum
+        `Keys.sample_ptr` over ranks (all-reduce) before `Keys.partition(groups)`."""
         addr, n, space, keep = _as_buffer(data)
         out = C.c_void_p()
-        _check(self._lib, self._lib.mc2_partition_keys(self._h, addr, n, space, k, groups, C.byref(out)))
-        return Keys(self, out, groups)
+        _check(self._lib, self._lib.mc2_keys_open(self._h, addr, n, space, k, C.byref(out)))
+        return Keys(self, out)
 
     def count_exceptions(self, data, k: int) -> Table:
         """Unfiltered table of the windows that hold a symbol outside ACGT (literal-byte rows)."""
@@ -427,16 +455,26 @@ class Engine:
 
 
 class Keys:
-    """Device array of packed keys grouped by hash (Engine.partition_keys)."""
+    """Packed symbols of one text on the device, then (after partition) its keys grouped by ascending key range."""
 
-    def __init__(self, engine, handle, groups):
-        self._engine, self._h, self.groups = engine, handle, groups
+    def __init__(self, engine, handle):
+        self._engine, self._h, self.groups = engine, handle, 0
+        ptr, n = C.c_void_p(), C.c_uint64(0)
+        lib = engine._lib
+        _check(lib, lib.mc2_keys_sample(handle, C.byref(ptr), C.byref(n)))
+        self.sample_ptr, self.sample_entries = ptr.value or 0, int(n.value)     # uint32[entries] on the device
+
+    def partition(self, groups: int):
+        lib = self._engine._lib
+        _check(lib, lib.mc2_keys_partition(self._h, groups))
+        self.groups = groups
         ptr, total, exc = C.c_void_p(), C.c_uint64(0), C.c_uint64(0)
         sizes = np.zeros(groups, dtype=np.uint64)
-        lib = engine._lib
-        _check(lib, lib.mc2_keys_info(handle, C.byref(ptr), sizes.ctypes.data, C.byref(total), C.byref(exc)))
+        bounds = np.zeros(groups + 1, dtype=np.uint64)
+        _check(lib, lib.mc2_keys_info(self._h, C.byref(ptr), sizes.ctypes.data, C.byref(total), C.byref(exc), bounds.ctypes.data))
         self.ptr, self.total, self.exception_symbols = ptr.value or 0, int(total.value), int(exc.value)
         self.sizes = [int(x) for x in sizes]
+        self.bounds = [int(x) for x in bounds]          # group g holds the keys with 32-bit prefix in [bounds[g], bounds[g+1])
 
     def close(self):
         if getattr(self, "_h", None) and self._engine._h:
@@ -478,10 +516,11 @@ class Sample:
         lib = self._engine._lib
         _check(lib, lib.mc2_sample_add_rows(self._h, kmers.ctypes.data, counts.ctypes.data, len(counts)))
 
-    def add_keys(self, keys_ptr: int, n: int, on_device: bool = True):
-        """Count n packed keys at a raw address as ONE chunk of this sample (min_count applies to their totals)."""
+    def add_keys(self, keys_ptr: int, n: int, on_device: bool = True, prefix_lo: int = 0, prefix_hi: int = 0):
+        """Count n packed keys at a raw address: ALL occurrences of one key range of the current chunk (min_count applies
+        to their totals).  prefix_lo / prefix_hi: the 32-bit prefix range they lie in (Keys.bounds), 0, 0 = unknown."""
         lib = self._engine._lib
-        _check(lib, lib.mc2_sample_add_keys(self._h, keys_ptr or None, n, MC2_DEVICE if on_device else MC2_HOST))
+        _check(lib, lib.mc2_sample_add_keys(self._h, keys_ptr or None, n, MC2_DEVICE if on_device else MC2_HOST, prefix_lo, prefix_hi))
 
     def dense(self):
         """(device address, bins, encoding) of the per-sample dense table; bins == 0 if the sample is not on the dense path."""

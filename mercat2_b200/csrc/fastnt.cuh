@@ -8,15 +8,16 @@
 // (about 11 ALU ops per text byte instead of ~55), and everything downstream works on 2-bit packed
 // symbols: a k-mer is two funnel shifts instead of a 16-step rolling loop.
 //
-// Output of K1f: `codes` (u32, 16 symbols per word, symbol i at bits 2(i%16)) and `bad` (u32, one bit per
-// symbol: record separator or non-ACGT symbol).  A window of k symbols is countable on the fast lane iff
-// none of its bad bits is set.  Keys are extracted in stream order (first symbol in the LOW bits); the
-// hash tables do not care, and surviving rows are converted to the order-preserving big-endian code by
-// fn_canon_kernel.
+// Output of K1f: `codes` (u32, 16 symbols per word, symbol i at bits 30 - 2(i%16): the FIRST symbol of a word is its
+// most significant pair) and `bad` (u32, one bit per symbol, symbol i at bit i%32: record separator or non-ACGT
+// symbol).  A window of k symbols is countable on the fast lane iff none of its bad bits is set.  With this layout
+// two funnel shifts yield the window's 64-bit code with its first symbol most significant, i.e. the
+// order-preserving key itself (numeric order == Python str order of the k-mer): the range partition of
+// rangecount.cuh works on its top 32 bits and no key is ever converted.
 #pragma once
 #include "common.cuh"
 #include "parse.cuh"
-#include "hashcount.cuh"
+#include "rangecount.cuh"
 
 #define FN_THREADS 256
 #define FN_WARPS (FN_THREADS / 32)
@@ -140,6 +141,12 @@ __device__ __forceinline__ u32 fn_compress(u32 src, u32 mask) {
     return out;
 }
 
+// 16 two-bit symbols assembled low-pair-first -> the stored word (first symbol in the top pair)
+__device__ __forceinline__ u32 fn_store_order(u32 x) {
+    x = __brev(x);                                                 // pairs reversed AND swapped inside
+    return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+
 // ---- K1f: count pass and write pass ---------------------------------------------------------------------------
 // MODE 0: count pass with alphabet statistics (first piece of a sample); MODE 1: write pass (also counts the kept
 // non-ACGT bytes); MODE 2: light count pass (line structure only).
@@ -246,7 +253,7 @@ fn_parse_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ tile_stat
         const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;
         u32* gc = codes + (base_sym >> 4);
         for (u32 i = fw + threadIdx.x; i < nw; i += FN_THREADS) {
-            const u32 val = s_c[i];
+            const u32 val = fn_store_order(s_c[i]);
             if (i == fw || i == nw - 1) { if (val) atomicOr(&gc[i], val); }
             else gc[i] = val;
         }
@@ -269,10 +276,13 @@ struct PackedView {
 
 // the three code words that hold the 16 windows starting in word g, and the mask of countable windows
 struct FnWords { u32 w0, w1, w2; };
-__device__ __forceinline__ u64 fn_key(const FnWords& w, int j, u64 mask) {       // j must be a compile-time constant
-    const u32 lo = __funnelshift_r(w.w0, w.w1, 2 * j);
-    const u32 hi = __funnelshift_r(w.w1, w.w2, 2 * j);
-    return (((u64)hi << 32) | lo) & mask;
+// top 32 bits of the left-aligned code of window j (its first 16 symbols); j must be a compile-time constant
+__device__ __forceinline__ u32 fn_hi(const FnWords& w, int j) { return __funnelshift_l(w.w1, w.w0, 2 * j); }
+// the window's key: k symbols, first symbol most significant, right-aligned in 2k bits
+__device__ __forceinline__ u64 fn_key(const FnWords& w, int j, int rshift /*64 - 2k*/) {
+    const u32 hi = __funnelshift_l(w.w1, w.w0, 2 * j);
+    const u32 lo = __funnelshift_l(w.w2, w.w1, 2 * j);
+    return (((u64)hi << 32) | lo) >> rshift;
 }
 __device__ __forceinline__ u32 fn_load_windows(const PackedView& pv, u64 g, int k, FnWords& w) {
     const u64 nwords = (pv.n + 15) >> 4;
@@ -285,27 +295,6 @@ __device__ __forceinline__ u32 fn_load_windows(const PackedView& pv, u64 g, int 
     const u64 bi = g >> 1;
     u64 b = (u64)pv.bad[bi] | ((bi + 1 < nbw ? (u64)pv.bad[bi + 1] : 0xFFFFFFFFull) << 32);
     b >>= (g & 1) * 16;
-    b |= 0xFFFF000000000000ull;
-    const u64 first = g << 4;
-    if (first + 48 > pv.n) b |= ~0ull << (pv.n - first);
-    u64 x = b;
-    int cur = 1;
-    while (cur * 2 <= k) { x |= x >> cur; cur *= 2; }
-    if (cur < k) x |= x >> (k - cur);
-    return ~(u32)x & 0xFFFFu;
-}
-
-// 16 windows starting in code word g: keys (stream order) and the mask of countable windows
-__device__ __forceinline__ u32 fn_windows(const PackedView& pv, u64 g, int k, u64 mask, u64 keys[16]) {
-    const u64 nwords = (pv.n + 15) >> 4;
-    if (g >= nwords) return 0;
-    const u32 w0 = pv.codes[g];
-    const u32 w1 = g + 1 < nwords ? pv.codes[g + 1] : 0u;
-    const u32 w2 = g + 2 < nwords ? pv.codes[g + 2] : 0u;
-    const u64 nbw = (pv.n + 31) >> 5;
-    const u64 bi = g >> 1;
-    u64 b = (u64)pv.bad[bi] | ((bi + 1 < nbw ? (u64)pv.bad[bi + 1] : 0xFFFFFFFFull) << 32);
-    b >>= (g & 1) * 16;
     b |= 0xFFFF000000000000ull;                                  // only 48 bits are real
     const u64 first = g << 4;
     if (first + 48 > pv.n) b |= ~0ull << (pv.n - first);          // symbols past the end stop every window
@@ -314,32 +303,56 @@ __device__ __forceinline__ u32 fn_windows(const PackedView& pv, u64 g, int k, u6
     int cur = 1;
     while (cur * 2 <= k) { x |= x >> cur; cur *= 2; }
     if (cur < k) x |= x >> (k - cur);
-    const u32 valid = ~(u32)x & 0xFFFFu;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const u32 lo = __funnelshift_r(w0, w1, 2 * j);
-        const u32 hi = __funnelshift_r(w1, w2, 2 * j);
-        keys[j] = (((u64)hi << 32) | lo) & mask;
-    }
-    return valid;
+    return ~(u32)x & 0xFFFFu;
 }
+// prefix mask: for k < 16 only the first k symbols of the top word belong to the key
+__device__ __forceinline__ u32 fn_pmask(int k) { return k >= 16 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * k)); }
 
 #define FN_HIST_THREADS 1024
+// prefix histogram of a strided sample of the packed stream (every `stride`-th code word) for rp_plan_kernel
 __global__ void __launch_bounds__(FN_HIST_THREADS)
-fn_hist_kernel(PackedView pv, int k, u32 nb, u32* __restrict__ ghist) {
+rp_sample_packed_kernel(PackedView pv, int k, u64 stride, u32 base, u32 sh, u32* __restrict__ shist) {
+    __shared__ u32 hist[RP_LUT];
+    for (u32 i = threadIdx.x; i < RP_LUT; i += FN_HIST_THREADS) hist[i] = 0;
+    BLOCK_SYNC();
+    const u32 hist32 = (u32)__cvta_generic_to_shared(hist);
+    const u32 pm = fn_pmask(k);
+    const u64 nwords = (pv.n + 15) >> 4;
+    for (u64 g = ((u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x) * stride; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS * stride) {
+        FnWords w;
+        const u32 valid = fn_load_windows(pv, g, k, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            smem_red_inc_if(hist32 + 4u * rp_lut_index(fn_hi(w, j) & pm, base, sh), (valid >> j) & 1u);
+    }
+    BLOCK_SYNC();
+    for (u32 b = threadIdx.x; b < RP_LUT; b += FN_HIST_THREADS) {
+        const u32 c = hist[b];
+        if (c) atomicAdd(&shist[b], c);
+    }
+}
+
+// exact histogram over all sub-buckets (FINE) or over the level-1 buckets only (level-0 partition of a very large chunk)
+template <bool FINE>
+__global__ void __launch_bounds__(FN_HIST_THREADS)
+fn_hist_kernel(PackedView pv, int k, RpView r, u32 nb, u32* __restrict__ ghist) {
     extern __shared__ __align__(16) u8 dyn[];
-    u32* hist = reinterpret_cast<u32*>(dyn);
+    RpShared& rs = *reinterpret_cast<RpShared*>(dyn);
+    u32* hist = reinterpret_cast<u32*>(dyn + sizeof(RpShared));
+    rp_load_shared(r, rs, FINE);
     for (u32 i = threadIdx.x; i < nb; i += FN_HIST_THREADS) hist[i] = 0;
     BLOCK_SYNC();
     const u32 hist32 = (u32)__cvta_generic_to_shared(hist);
-    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const u32 pm = fn_pmask(k);
     const u64 nwords = (pv.n + 15) >> 4;
     for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
-        u64 keys[16];
-        const u32 valid = fn_windows(pv, g, k, mask, keys);
+        FnWords w;
+        const u32 valid = fn_load_windows(pv, g, k, w);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)                       // predicated reduction: no branch per window
-            smem_red_inc_if(hist32 + 4u * hc_bucket(keys[j], nb), (valid >> j) & 1u);
+        for (int j = 0; j < 16; ++j) {                     // predicated reduction: no branch per window
+            const u32 p = fn_hi(w, j) & pm;
+            smem_red_inc_if(hist32 + 4u * (FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)), (valid >> j) & 1u);
+        }
     }
     BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < nb; b += FN_HIST_THREADS) {
@@ -465,7 +478,7 @@ fn_parse_single_kernel(const u8* __restrict__ text, u64 len, u32 ntiles, ull* __
     const u32 fw = rel0 >> 4, nw = (rel0 + total + 15) >> 4;
     u32* gc = codes + (base_sym >> 4);
     for (u32 i = fw + threadIdx.x; i < nw; i += FN_THREADS) {
-        const u32 val = s_c[i];
+        const u32 val = fn_store_order(s_c[i]);
         if (i == fw || i == nw - 1) { if (val) atomicOr(&gc[i], val); }
         else gc[i] = val;
     }
@@ -479,15 +492,9 @@ fn_parse_single_kernel(const u8* __restrict__ text, u64 len, u32 ntiles, ull* __
 }
 
 // ---- dense tables straight from the packed stream (4^k bins, k <= 15) -----------------------------------------
-// Index = the window's code with its first symbol most significant (the layout of the sample table), obtained from
-// the stream-order key by one bit reversal.  SMEM: per-CTA histogram replicated per warp group, flushed once;
-// otherwise reduction atomics on the L2-resident global table.
-__device__ __forceinline__ u32 fn_dense_index(u32 key, int k) {
-    u32 x = __brev(key);                                          // pairs reversed and swapped inside
-    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
-    return x >> (32 - 2 * k);
-}
-
+// Index = the window's code with its first symbol most significant (the layout of the sample table) = the top 2k bits
+// of the window's first code word.  SMEM: per-CTA histogram replicated per warp group, flushed once; otherwise
+// reduction atomics on the L2-resident global table.
 template <bool SMEM>
 __global__ void __launch_bounds__(FN_HIST_THREADS)
 fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ table) {
@@ -499,14 +506,14 @@ fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ tabl
     }
     u32* my = SMEM ? hist + (u32)((threadIdx.x >> 5) % nrep) * bins : table;
     const u32 my32 = SMEM ? (u32)__cvta_generic_to_shared(my) : 0u;
-    const u64 mask = (1ull << (2 * k)) - 1;
+    const int rs = 32 - 2 * k;
     const u64 nwords = (pv.n + 15) >> 4;
     for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
-        u64 keys[16];
-        const u32 valid = fn_windows(pv, g, k, mask, keys);
+        FnWords w;
+        const u32 valid = fn_load_windows(pv, g, k, w);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const u32 idx = fn_dense_index((u32)keys[j], k);
+            const u32 idx = fn_hi(w, j) >> rs;
             if (SMEM) smem_red_inc_if(my32 + 4u * idx, (valid >> j) & 1u);           // predicated: no branch per window
             else if ((valid >> j) & 1u) atomicAdd(&my[idx], 1u);
         }
@@ -521,46 +528,39 @@ fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ tabl
     }
 }
 
-template <bool USE_DST>
+// packed stream -> keys grouped by level-1 bucket (or by level-0 group with 64-bit group bases)
 __global__ void __launch_bounds__(EX_THREADS)
-fn_scatter1_kernel(PackedView pv, int k, u32 nb, u32 nb1, u32* __restrict__ cur1, u64* __restrict__ keys1,
-                   const u64* __restrict__ base64) {
-    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM bytes
+fn_scatter1_kernel(PackedView pv, int k, RpView r, u32* __restrict__ cur1, u64* __restrict__ keys1, const u64* __restrict__ base64) {
+    extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM_LUT bytes
     u64* stage = reinterpret_cast<u64*>(dyn_sc);
-    u32* sdst = reinterpret_cast<u32*>(dyn_sc + HC_SDST_OFFSET);
+    u16* sdig = reinterpret_cast<u16*>(dyn_sc + HC_SDST_OFFSET);
+    u16* s_lut = reinterpret_cast<u16*>(dyn_sc + HC_SCATTER_SMEM16);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
-    for (u32 i = threadIdx.x; i < nb1; i += EX_THREADS) cnt[i] = 0;
+    for (u32 i = threadIdx.x; i < r.nb1; i += EX_THREADS) cnt[i] = 0;
+    for (u32 i = threadIdx.x; i < RP_LUT / 8; i += EX_THREADS) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(r.lut)[i];
     BLOCK_SYNC();
-    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const int rshift = 64 - 2 * k;
+    const u32 pm = fn_pmask(k);
     FnWords w;
     const u32 valid = fn_load_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, w);
-    auto dig = [nb](u64 key) { return hc_bucket(key, nb) >> HC_NB2_LOG2; };
-    // keys are recomputed (two funnel shifts) wherever they are needed instead of living in 32 registers
-    auto key = [&](int i) { return fn_key(w, i, mask); };
-    hc_group_and_write2<USE_DST>(key, key, valid, nb1, dig, stage, sdst, cnt, loff, gbase, sm, cur1, keys1, base64);
-}
-
-// stream-order key (first symbol in the low bits) -> big-endian code (first symbol most significant)
-__global__ void fn_canon_kernel(u64* __restrict__ keys, u64 n, int k) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u64 x = __brevll(keys[i]);                                    // reverses bits: pairs reversed AND swapped inside
-    x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
-    keys[i] = 2 * k >= 64 ? x : (x >> (64 - 2 * k));
+    // keys and digits are recomputed (funnel shifts) wherever they are needed instead of living in 32 registers
+    auto key = [&](int i) { return fn_key(w, i, rshift); };
+    auto dig = [&](int i) { return (u32)s_lut[rp_lut_index(fn_hi(w, i) & pm, r.base, r.sh)]; };
+    hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
 }
 
 // debug: order-independent checksum of all countable windows of the packed stream
 __global__ void fn_checksum_kernel(PackedView pv, int k, ull* __restrict__ out /*[0]=sum, [1]=xor, [2]=count*/) {
-    const u64 mask = 2 * k >= 64 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const int rshift = 64 - 2 * k;
     const u64 nwords = (pv.n + 15) >> 4;
     ull sum = 0, x = 0, cnt = 0;
     for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < nwords; g += (u64)gridDim.x * blockDim.x) {
-        u64 keys[16];
-        const u32 valid = fn_windows(pv, g, k, mask, keys);
+        FnWords w;
+        const u32 valid = fn_load_windows(pv, g, k, w);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if ((valid >> j) & 1u) { sum += keys[j] * 0x9E3779B97F4A7C15ull; x ^= keys[j]; cnt++; }
+            if ((valid >> j) & 1u) { const u64 key = fn_key(w, j, rshift); sum += key * 0x9E3779B97F4A7C15ull; x ^= key; cnt++; }
     }
     atomicAdd(&out[0], sum); atomicXor(&out[1], x); atomicAdd(&out[2], cnt);
 }

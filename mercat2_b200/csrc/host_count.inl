@@ -9,10 +9,9 @@ static void dense_batch(mc2_engine* e, const Plan& plan, SymView v, u64 s0, u64 
     if (plan.smem) {
         auto kern = dense_smem_kernel<ENC>;
         const size_t smem = (size_t)plan.bins * plan.nrep * 4;
-        static thread_local bool attr_set[3] = {false, false, false};
-        if (!attr_set[ENC]) {
+        if (!e->dense_attrs_set[ENC]) {          // (function attributes are per device: remembered per engine, not per thread)
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[ENC] = true;
+            e->dense_attrs_set[ENC] = true;
         }
         int per_sm = 1;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, smem));
@@ -25,7 +24,7 @@ static void dense_batch(mc2_engine* e, const Plan& plan, SymView v, u64 s0, u64 
     }
 }
 
-// sort + RLE of an already materialised key range (fallback for overflowed hash buckets)
+// sort + RLE of an already materialised key range (fallback for overflowed sub-buckets)
 static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys, u64 m, int kb) {
     if (!m) return;
     DBuf<u64> k0(e, m), k1(e, m);
@@ -44,137 +43,179 @@ static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys
     s->fast.push_back(std::move(part));
 }
 
-// hash-partition + shared-memory tables (hashcount.cuh); the chunk must fit one batch.  Keys come either from
-// the byte symbol stream `v` (encoding ENC) or, when `pv` is given, from the packed nucleotide stream.
 static void prefetch_next_count_pass(mc2_engine* e, mc2_sample* s);
 
-struct KeySpan {               // keys already extracted (one level-0 group of a very large chunk)
+struct KeySpan {               // keys already extracted (one level-0 group of a very large chunk, or keys received from other ranks)
     const u64* keys;
     u64 n;
-    bool stream_order;         // keys come from the packed lane (first symbol in the low bits)
+    u64 p_lo, p_hi;            // the keys' 32-bit prefixes lie in [p_lo, p_hi)   (p_hi <= 2^32)
 };
 
+// One level of the range partition on the device (rangecount.cuh): LUT + level-1 descriptors.
+struct RpPlan {
+    DBuf<u16> lut;
+    DBuf<uint2> l1;
+    u32 base = 0, sh = 0, nb1 = 1, nidx = 1, down = 0, up = 0;
+    RpView view() const { return RpView{lut.p, l1.p, base, sh, nb1, down, up}; }
+};
+static void plan_geometry(RpPlan& pl, int kb, u32 nb1, u64 p_lo, u64 p_hi) {
+    pl.nb1 = nb1;
+    pl.down = kb >= 32 ? (u32)(kb - 32) : 0u;
+    pl.up = kb >= 32 ? 0u : (u32)(32 - kb);
+    pl.base = (u32)p_lo;
+    const u64 span = std::max<u64>(1, p_hi - p_lo);
+    pl.sh = 0;
+    while (((span - 1) >> pl.sh) >= RP_LUT) ++pl.sh;
+    pl.nidx = (u32)((span - 1) >> pl.sh) + 1;
+}
+static const u64 RP_SAMPLE_WINDOWS = 1ull << 21;     // keys whose prefixes shape a level's LUT
+
+// set the attributes of every kernel that needs more than 48 KB of dynamic shared memory (once per device)
 template <int ENC>
-static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr) {
+static void range_kernel_attrs_enc() {
+    CUDA_CHECK(cudaFuncSetAttribute(hc_hist_kernel<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(hc_scatter1_kernel<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM_LUT));
+}
+static void range_kernel_attrs(mc2_engine* e) {
+    if (e->range_attrs_set) return;
+    range_kernel_attrs_enc<ENC_NT2>();
+    range_kernel_attrs_enc<ENC_AA5>();
+    range_kernel_attrs_enc<ENC_BYTE>();
+    CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(hc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HC_MAX_NB1 * HC_NB2 * 4)));
+    CUDA_CHECK(cudaFuncSetAttribute(hk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM_LUT));
+    CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM_LUT));
+    CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM16));
+    CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    e->range_attrs_set = true;
+}
+
+// sampled prefix histogram of the source (packed streams, a key array, or a byte-symbol stream) -> plan tables
+template <int ENC>
+static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, SymView v, u64 cap, RpPlan& pl,
+                       const u32* shist_given = nullptr) {
+    pl.lut.alloc(e, RP_LUT);
+    pl.l1.alloc(e, pl.nb1);
+    DBuf<u32> shist;
+    const u32* sh_p = shist_given;
+    if (!sh_p) {
+        shist.alloc(e, RP_LUT);
+        shist.zero();
+        if (ks) {
+            const u64 stride = std::max<u64>(1, ks->n / RP_SAMPLE_WINDOWS);
+            const u64 grid = std::min<u64>(div_up(div_up(ks->n, stride), HK_HIST_THREADS), (u64)e->num_sms * 2);
+            if (ks->n) LAUNCH(e, rp_sample_keys_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, 0, ks->keys, ks->n, stride, pl.down, pl.up, pl.base, pl.sh, shist.p);
+        } else if (!pvs.empty()) {
+            const u64 stride = std::max<u64>(1, cap / RP_SAMPLE_WINDOWS);
+            for (auto& pv : pvs) {
+                const u64 nwords = div_up(pv.n, 16);
+                const u64 grid = std::min<u64>(div_up(div_up(nwords, stride), FN_HIST_THREADS), (u64)e->num_sms * 2);
+                if (nwords) LAUNCH(e, rp_sample_packed_kernel, (unsigned)std::max<u64>(grid, 1), FN_HIST_THREADS, 0, pv, k, stride, pl.base, pl.sh, shist.p);
+            }
+        } else {
+            const u64 ntiles = div_up(v.n, EX_TILE);
+            const u64 stride = std::max<u64>(1, cap / RP_SAMPLE_WINDOWS);
+            const u64 grid = std::min<u64>(div_up(ntiles, stride), (u64)e->num_sms * 4);
+            auto kern = rp_sample_sym_kernel<ENC>;
+            if (ntiles) LAUNCHN(e, "rp_sample_sym_kernel", kern, (unsigned)std::max<u64>(grid, 1), EX_THREADS, 0, v, k, stride, pl.down, pl.up, pl.base, pl.sh, shist.p);
+        }
+        sh_p = shist.p;
+    }
+    LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.lut.p, pl.l1.p);
+}
+
+// keys one two-level partition can take (beyond it: level-0 partition first)
+static u64 range_batch_max(const mc2_engine* e, const mc2_sample* s) {
+    const double fill = s->c < 2 ? 0.7 : 1.0;                    // min_count 1 keeps every distinct key in the table
+    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * fill), e->opt_batch_symbols);
+}
+
+// Range partition + shared-memory tables (rangecount.cuh); the chunk must fit one batch.  Keys come from the byte
+// symbol stream `v` (encoding ENC), from the packed nucleotide stream `pv`, or from a key array `ks`.  The surviving
+// rows are appended to the sample as ONE part that is already sorted by key.
+template <int ENC>
+static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr) {
+    range_kernel_attrs(e);
     const int k = s->k;
     const int kb = k * EncTraits<ENC>::BITS;
     const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
-    const u64 mult = ks ? HC_MULT2 : HC_MULT1;
-    const bool stream_order = pv || (ks && ks->stream_order);
+    if (cap == 0) return;
+    const u32 c = (u32)std::min<u64>(s->c, 0xFFFFFFFFull);
+    // MODE 0 keeps every distinct key of a sub-bucket in the table, MODE 1 only the repeated ones
+    const int mode = c < 2 ? 0 : e->opt_count_mode >= 0 ? (e->opt_count_mode ? 1 : 0) : (s->dup_rich ? 0 : 1);
     // (`cap` of a symbol stream counts ~25 % more positions than windows; a key array is exact, so aim lower there to
-    // keep the same head room below the 4096 keys a bucket may hold)
-    const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * (ks ? 0.8 : 1.0)));
+    // keep the same head room below the keys a table may hold)
+    const double fill = (ks ? 0.8 : 1.0) * (mode == 0 && c < 2 ? 0.7 : 1.0);
+    const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * fill));
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
-    struct Tail { ull total, out_n; u32 ovf_n, pad; };
+    RpPlan pl;
+    plan_geometry(pl, kb, nb1, ks ? ks->p_lo : 0, ks ? ks->p_hi : (1ull << 32));
+    std::vector<PackedView> pvs;
+    if (pv) pvs.push_back(*pv);
+    build_plan<ENC>(e, k, pvs, ks, v, cap, pl);
+    const RpView rv = pl.view();
+    struct Tail { ull total, rows; u32 ovf_n, pad; };
     // (the bucket histogram and the result counters share one allocation: one memset per chunk instead of two)
-    DBuf<u32> ghist(e, nb + sizeof(Tail) / 4), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb);
+    DBuf<u32> ghist(e, nb + sizeof(Tail) / 4), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb), rows(e, nb);
+    DBuf<u64> row_off(e, nb);
     struct { Tail* p; } tail{reinterpret_cast<Tail*>(ghist.p + nb)};       // nb is a multiple of 128: 8-byte aligned
     ghist.zero();
-    const size_t hist_smem = (size_t)nb * 4;
+    const size_t hist_smem = sizeof(RpShared) + (size_t)nb * 4;
     if (ks) {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute(hk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            attr_set = true;
-        }
-        int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hk_hist_kernel, HK_HIST_THREADS, hist_smem));
-        const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms * std::max(per_sm, 1));
-        LAUNCH(e, hk_hist_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, nb, mult, ghist.p);
+        const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms);
+        LAUNCHN(e, "hk_hist_kernel", hk_hist_kernel<true>, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, rv, nb, ghist.p);
     } else if (pv) {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            attr_set = true;
-        }
-        int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
         const u64 nwords = div_up(cap, 16);
-        const u64 grid = std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
-        LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, *pv, k, nb, ghist.p);
+        const u64 grid = std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms);
+        LAUNCHN(e, "fn_hist_kernel", fn_hist_kernel<true>, (unsigned)grid, FN_HIST_THREADS, hist_smem, *pv, k, rv, nb, ghist.p);
     } else {
         auto kern = hc_hist_kernel<ENC>;
-        static thread_local bool attr_set[3] = {false, false, false};
-        if (!attr_set[ENC]) {
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            attr_set[ENC] = true;
-        }
         int per_sm = 1;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, hist_smem));
         const u64 grid = std::min<u64>(div_up(cap, EX_TILE), (u64)e->num_sms * std::max(per_sm, 1));
-        LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, hist_smem, v, (u64)0, v.n, k, nb, ghist.p);
-    }
-    {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HC_MAX_NB1 * HC_NB2 * 4)));
-            attr_set = true;
-        }
+        LAUNCHN(e, "hc_hist_kernel", kern, (unsigned)grid, EX_THREADS, hist_smem, v, (u64)0, v.n, k, rv, nb, ghist.p);
     }
     LAUNCH(e, hc_scan_kernel, 1, 1024, (size_t)nb * 4, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
-    DBuf<u64> keys1(e, cap), keys2(e, cap);
+    // keys1 also serves as the survivors' slot array (16-byte rows at slot sub_base[b] / c) once scatter 2 has read it:
+    // for c >= 2 the slots of cap keys need 16 * (cap / c + 1) <= 8 * cap + 16 bytes
+    DBuf<u64> keys1(e, cap + 8), keys2(e, cap);
+    DBuf<RcRow> slots1;
+    RcRow* slots = reinterpret_cast<RcRow*>(keys1.p);
+    if (c < 2) { slots1.alloc(e, cap + 2); slots = slots1.p; }
     const bool dbg = getenv("MC2_DEBUG_HASH") != nullptr;
     if (dbg) {
         CUDA_CHECK(cudaMemsetAsync(keys1.p, 0xEE, cap * 8, e->stream));
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
-    const bool use_dst = (e->opt_scatter_variant & 1) && !ks;
-    const size_t sc_smem = use_dst ? HC_SCATTER_SMEM : HC_SCATTER_SMEM16;
-    {
-        static thread_local int attr_variant = -1;
-        if (attr_variant != e->opt_scatter_variant) {
-            const int carve = (e->opt_scatter_variant & 2) ? 100 : -1;
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            const int carve1 = (e->opt_scatter_variant & 4) ? 85 : carve;
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
-            CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_scatter2_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            attr_variant = e->opt_scatter_variant;
-        }
-    }
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, HC_SCATTER_SMEM16, ks->keys, ks->n, nb, nb1, mult, cur1.p, keys1.p,
-               (const u64*)nullptr);
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else if (pv) {
-        if (use_dst) LAUNCH(e, fn_scatter1_kernel<true>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
-        else LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, sc_smem, *pv, k, nb, nb1, cur1.p, keys1.p, (const u64*)nullptr);
+        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, HC_SCATTER_SMEM_LUT, *pv, k, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else {
         auto kern = hc_scatter1_kernel<ENC>;
-        static thread_local bool attr_set[3] = {false, false, false};
-        if (!attr_set[ENC]) {
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-            attr_set[ENC] = true;
-        }
-        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, HC_SCATTER_SMEM, v, (u64)0, v.n, k, nb, nb1, cur1.p, keys1.p);
+        LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, v, (u64)0, v.n, k, rv, cur1.p, keys1.p);
     }
-    if (use_dst)
-        LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<true, false>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
-    else if (e->opt_scatter_variant & 8)
-        LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<false, true>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
-    else
-        LAUNCHN(e, "hc_scatter2_kernel", (hc_scatter2_kernel<false, false>), (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, sc_smem, (const u64*)keys1.p, (const u32*)sub_base.p,
-               (const u32*)tile_pref.p, nb, nb1, (u32)HC_NB2, cur2.p, keys2.p, mult);
+    LAUNCH(e, hc_scatter2_kernel, (unsigned)(div_up(cap, HC_TILE) + nb1), EX_THREADS, HC_SCATTER_SMEM16, (const u64*)keys1.p, (const u32*)sub_base.p,
+           (const u32*)tile_pref.p, nb, (u32)HC_NB2, rv, cur2.p, keys2.p);
     if (dbg) {
         DBuf<ull> badc(e, 2);
         badc.zero();
         const u64 total = (u64)read_scalar<ull>(e, &tail.p->total);
         if (total) {
-            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys1.p, (const u32*)sub_base.p, nb, (u32)HC_NB2, (u32)total, badc.p, mult);
-            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys2.p, (const u32*)sub_base.p, nb, 1u, (u32)total, badc.p + 1, mult);
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys1.p, (const u32*)sub_base.p, nb, (u32)HC_NB2, (u32)total, badc.p, rv);
+            LAUNCH(e, hc_verify_kernel, (unsigned)div_up(total, 256), 256, 0, (const u64*)keys2.p, (const u32*)sub_base.p, nb, 1u, (u32)total, badc.p + 1, rv);
         }
         const ull b1 = read_scalar<ull>(e, badc.p), b2 = read_scalar<ull>(e, badc.p + 1);
-        fprintf(stderr, "[hash] cap=%llu total=%llu nb1=%u nb=%u packed=%d misplaced level1=%llu level2=%llu\n", (ull)cap, (ull)total, nb1, nb,
-                pv ? 1 : 0, b1, b2);
+        fprintf(stderr, "[range] cap=%llu total=%llu nb1=%u nb=%u packed=%d mode=%d misplaced level1=%llu level2=%llu\n", (ull)cap, (ull)total, nb1, nb,
+                pv ? 1 : 0, mode, b1, b2);
         DBuf<ull> cs(e, 9);
         cs.zero();
         if (pv) LAUNCH(e, fn_checksum_kernel, 256, 256, 0, *pv, k, cs.p);
@@ -182,102 +223,51 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
         LAUNCH(e, key_checksum_kernel, 256, 256, 0, (const u64*)keys2.p, total, cs.p + 6);
         ull h[9];
         d2h(e, h, cs.p, 9);
-        fprintf(stderr, "[hash] checksum stream (%llx %llx %llu) keys1 (%llx %llx %llu) keys2 (%llx %llx %llu)%s\n", h[0], h[1], h[2], h[3],
-                h[4], h[5], h[6], h[7], h[8], (pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) ? "  MISMATCH" : "");
+        fprintf(stderr, "[range] checksum stream (%llx %llx %llu) keys1 (%llx %llx %llu) keys2 (%llx %llx %llu)%s\n", h[0], h[1], h[2], h[3],
+                h[4], h[5], h[6], h[7], h[8], ((pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) || b1 || b2) ? "  MISMATCH" : "");
     }
-    const u64 out_cap = cap / s->c + 2;
-    FastPart part;
-    part.keys.alloc(e, out_cap);
-    part.counts.alloc(e, out_cap);
-    unsigned cgrid = (unsigned)std::min<u64>(nb, (u64)e->num_sms);
-    if (s->c >= 2 && (e->opt_count_variant & 15) == 3) {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hc_count3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC3_SMEM));
-            attr_set = true;
-        }
-        LAUNCH(e, hc_count3_kernel, cgrid, HC3_THREADS, HC3_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
-    } else if (s->c >= 2) {                                        // (count_variant bits >= 4: timing experiments)
-        cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hc_count2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC2_SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute(hc_count2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr_set = true;
-        }
-        LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n, (ull*)nullptr,
-               (u32)(e->opt_count_variant >> 4));
-        if (dbg) {                                                // stress: repeat on the same keys, results must not vary
-            DBuf<ull> dc(e, 8 + (u64)cgrid * 64);
-            DBuf<Tail> t2(e, 1);
-            DBuf<u64> ok2(e, out_cap), oc2(e, out_cap);
-            for (int rep = 0; rep < 40; ++rep) {
-                dc.zero();
-                t2.zero();
-                LAUNCH(e, hc_count2_kernel, cgrid, HC2_THREADS, HC2_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-                       ok2.p, oc2.p, &t2.p->out_n, out_cap, ovf_list.p, &t2.p->ovf_n, dc.p, 0u);
-                ull h[4];
-                d2h(e, h, dc.p, 4);
-                if (cgrid == nb) {                                 // one bucket per CTA: barrier timestamps are meaningful
-                    std::vector<ull> ts((u64)cgrid * 64);
-                    d2h(e, ts.data(), dc.p + 8, (u64)cgrid * 64);
-                    int leaks1 = 0, leaks2 = 0;
-                    for (unsigned cta = 0; cta < cgrid; ++cta) {
-                        ull max_end1 = 0, min_beg2 = ~0ull, max_end2 = 0, min_beg3 = ~0ull;
-                        for (int w = 0; w < 16; ++w) {
-                            const ull* q = &ts[((u64)cta * 16 + w) * 4];
-                            max_end1 = std::max(max_end1, q[0]); min_beg2 = std::min(min_beg2, q[1]);
-                            max_end2 = std::max(max_end2, q[2]); min_beg3 = std::min(min_beg3, q[3]);
-                        }
-                        if (min_beg2 < max_end1) leaks1++;
-                        if (min_beg3 < max_end2) leaks2++;
-                    }
-                    if (leaks1 || leaks2) fprintf(stderr, "[hash] BARRIER LEAK rep %d: %d CTAs passed the pass1|pass2 barrier early, %d the pass2|emit barrier\n", rep, leaks1, leaks2);
-                }
-                const Tail tt = read_scalar<Tail>(e, t2.p);
-                static ull first_out = 0, first_hits = 0, first_claims = 0;
-                if (rep == 0) { first_out = tt.out_n; first_hits = h[0]; first_claims = h[2]; }
-                if (h[0] != h[1] || tt.out_n != first_out || h[0] != first_hits || h[2] != first_claims || h[3])
-                    fprintf(stderr, "[hash] STRESS rep %d: pass2 hits %llu, counts read back %llu, claims %llu (first %llu), empty-key slots %llu, survivors %llu (first %llu)\n",
-                            rep, h[0], h[1], h[2], first_claims, h[3], (ull)tt.out_n, first_out);
-            }
-        }
-    } else {
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(hc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_COUNT_SMEM));
-            attr_set = true;
-        }
-        LAUNCH(e, hc_count_kernel, cgrid, HC_THREADS, HC_COUNT_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, s->c,
-               part.keys.p, part.counts.p, &tail.p->out_n, out_cap, ovf_list.p, &tail.p->ovf_n);
-    }
+    const unsigned cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
+    if (mode == 1)
+        LAUNCHN(e, "rc_count_kernel<1>", rc_count_kernel<1>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,
+                ovf_list.p, &tail.p->ovf_n);
+    else
+        LAUNCHN(e, "rc_count_kernel<0>", rc_count_kernel<0>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,
+                ovf_list.p, &tail.p->ovf_n);
+    LAUNCH(e, rc_offsets_kernel, 1, 1024, 0, (const u32*)rows.p, nb, row_off.p, (ull*)nullptr, &tail.p->rows, 0);
     if (pv && !ks) prefetch_next_count_pass(e, s);               // rides on the synchronisation below
     const Tail t = read_scalar<Tail>(e, tail.p);
-    if (t.out_n > out_cap) throw Mc2Error(MC2_ERR_LIMIT, "hash path: survivor buffer overflow (internal error)");
+    if (t.rows > cap / c + 1) throw Mc2Error(MC2_ERR_LIMIT, "range path: more survivors than slots (internal error)");
     if (ks && getenv("MC2_DEBUG_PHASES"))
-        fprintf(stderr, "[phase]   group: %llu keys, %u buckets, %llu survivors, %u overflowed buckets\n", (ull)cap, nb, (ull)t.out_n, t.ovf_n);
+        fprintf(stderr, "[phase]   group: %llu keys, %u buckets, mode %d, %llu survivors, %u overflowed buckets\n", (ull)cap, nb, mode, (ull)t.rows, t.ovf_n);
+    if (t.rows) {
+        FastPart part;
+        part.n = t.rows;
+        part.sorted = true;
+        part.keys.alloc(e, t.rows);
+        part.counts.alloc(e, t.rows);
+        LAUNCH(e, rc_gather_kernel, (unsigned)std::min<u64>(div_up(nb, 8), (u64)e->num_sms * 8), 256, 0, (const RcRow*)slots, (const u32*)sub_base.p,
+               (const u32*)rows.p, (const u64*)row_off.p, nb, c, part.keys.p, part.counts.p, (RcRow*)nullptr);
+        s->fast.push_back(std::move(part));
+    }
     if (dbg) {                                                    // the sort path on the same keys must agree
         mc2_sample tmp;
         tmp.e = e; tmp.k = k; tmp.c = s->c;
         count_key_range_sorted(e, &tmp, keys2.p, t.total, 64);
         u64 ref_rows = 0;
         for (auto& p : tmp.fast) ref_rows += p.n;
-        fprintf(stderr, "[hash] survivors: tables %llu (+%u overflowed buckets) sort %llu%s\n", (ull)t.out_n, t.ovf_n, (ull)ref_rows,
-                (!t.ovf_n && ref_rows != t.out_n) ? "  MISMATCH" : "");
+        fprintf(stderr, "[range] survivors: tables %llu (+%u overflowed buckets) sort %llu%s\n", (ull)t.rows, t.ovf_n, (ull)ref_rows,
+                (!t.ovf_n && ref_rows != t.rows) ? "  MISMATCH" : "");
     }
-    if (t.out_n) {
-        if (stream_order) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(t.out_n, 256), 256, 0, part.keys.p, (u64)t.out_n, k);
-        part.n = t.out_n;
-        part.sorted = false;
-        s->fast.push_back(std::move(part));
+    // duplicate-rich data (survivors carry a quarter of the keys or more): the following chunks / groups of the sample
+    // skip the bitmap pre-filter.  If that makes tables overflow, go back.
+    if (c >= 2) {
+        if (mode == 1 && t.rows * (u64)c * 4 >= t.total && t.total >= 65536) s->dup_rich = true;
+        if (mode == 0 && (u64)t.ovf_n * 50 > nb) s->dup_rich = false;
     }
     if (t.ovf_n) {
-        // Buckets the tables could not take (more keys than the prefetch registers hold, or too many distinct
-        // repeats): their keys are gathered into ONE array and counted by a single sort + run-length pass (buckets
-        // hold disjoint key sets).  Heavily duplicated data makes bucket sizes spread (sigma ~ sqrt(size * copies)),
-        // so the overflow rate also steers the bucket size of the sample's next chunks.
+        // Sub-buckets whose distinct (MODE 0) or repeated (MODE 1) keys do not fit the table: their keys are gathered
+        // into ONE array and counted by a single sort + run-length pass (sub-buckets hold disjoint key sets).  The
+        // overflow rate also steers the bucket size of the sample's next chunks.
         std::vector<u32> ovf(t.ovf_n), base(nb + 1);
         d2h(e, ovf.data(), ovf_list.p, t.ovf_n);
         d2h(e, base.data(), sub_base.p, nb + 1);
@@ -294,7 +284,6 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
             CUDA_CHECK(cudaMemcpyAsync(dof.p, dst_off.data(), t.ovf_n * 8ull, cudaMemcpyHostToDevice, e->stream));
             LAUNCH(e, gather_ranges_kernel, (unsigned)std::min<u64>(div_up(m, 256), 65535), 256, 0, (const u64*)keys2.p, (const u64*)so.p,
                    (const u64*)dof.p, t.ovf_n, m, gathered.p);
-            if (stream_order) LAUNCH(e, fn_canon_kernel, (unsigned)div_up(m, 256), 256, 0, gathered.p, m, k);
             CUDA_CHECK(cudaStreamSynchronize(e->stream));          // (host vectors were the sources of async copies)
             count_key_range_sorted(e, s, gathered.p, m, kb);
         }
@@ -306,10 +295,9 @@ static void sparse_chunk_hash(mc2_engine* e, mc2_sample* s, SymView v, const Pac
 template <int ENC>
 static void sparse_chunk(mc2_engine* e, mc2_sample* s, SymView v) {
     {
-        const u64 hash_max = (u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys;
-        const bool want_hash = e->opt_sparse_algo == 2 || (e->opt_sparse_algo == 0 && s->c >= 2);
-        if (want_hash && v.n <= std::min<u64>(hash_max, e->opt_batch_symbols) && v.n < (1ull << 32)) {
-            sparse_chunk_hash<ENC>(e, s, v);
+        const bool want_range = e->opt_sparse_algo != 1;
+        if (want_range && v.n <= range_batch_max(e, s) && v.n < (1ull << 32)) {
+            sparse_chunk_range<ENC>(e, s, v);
             return;
         }
     }
@@ -451,8 +439,8 @@ static FnStats fn_count_pass(mc2_engine* e, FnSpan& sp, bool with_stats, DBuf<Fn
 
 static void prefetch_next_count_pass(mc2_engine* e, mc2_sample* s) {
     if (!s->next_len || s->pre.valid || !e->opt_prefetch_pass) return;
-    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
-    const bool ok = e->opt_fast_nt && !e->opt_parse_single && s->k <= 32 && s->c >= 2 && e->opt_sparse_algo != 1 &&
+    const u64 hash_max = range_batch_max(e, s);
+    const bool ok = e->opt_fast_nt && !e->opt_parse_single && s->k <= 32 && e->opt_sparse_algo != 1 &&
                     s->plan.enc == ENC_NT2 && s->plan.path == PATH_SPARSE && e->opt_force_enc <= 0 && e->opt_force_path != PATH_WIDE &&
                     s->next_len <= std::min<u64>(e->opt_span_bytes, hash_max);
     if (!ok) { s->next_len = 0; return; }
@@ -509,11 +497,7 @@ static void fn_dense_span(mc2_engine* e, mc2_sample* s, const PackedView& pv) {
     const u64 nwords = div_up(pv.n, 16);
     if (plan.smem) {
         const size_t smem = (size_t)plan.bins * plan.nrep * 4;
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        range_kernel_attrs(e);
         const unsigned grid = (unsigned)std::min<u64>(div_up(nwords, FN_HIST_THREADS), (u64)e->num_sms * (smem <= 96 * 1024 ? 2 : 1));
         LAUNCHN(e, "fn_dense_kernel<smem>", fn_dense_kernel<true>, grid, FN_HIST_THREADS, smem, pv, s->k, plan.bins, plan.nrep, s->dense_chunk.p);
     } else {
@@ -522,57 +506,53 @@ static void fn_dense_span(mc2_engine* e, mc2_sample* s, const PackedView& pv) {
     }
 }
 
-// A chunk with more windows than one hash batch holds (-s 0 on a large file): a level-0 partition of ALL its keys by an
-// independent hash into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then
-// the usual two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact
-// for the whole chunk.  Returns false (nothing counted) when the keys do not fit in free device memory.
-// Level-0 partition of key sources into g0 groups by hash `mult`: keys0 (grouped, exact offsets in gbase[g0 + 1]).
-// Sources: packed symbol streams (their windows) or one key array.  Returns false if the result does not fit in
-// free device memory (`extra` = bytes the caller still needs afterwards) or a group would exceed `group_max` keys.
+// Level-0 partition of key sources into g0 groups of ascending, disjoint key ranges: keys0 (grouped, exact offsets in
+// gbase[g0 + 1]; bounds[g] = first 32-bit prefix of group g, bounds[g0] = end of the partitioned range).  Sources:
+// packed symbol streams (their windows) or one key array.  The group boundaries come from a sampled prefix histogram
+// (`shist_given`: a histogram the caller already holds, e.g. summed over all ranks so that every rank cuts at the same
+// keys).  Returns false if the result does not fit in free device memory (`extra` = bytes the caller still needs
+// afterwards) or a group would exceed `group_max` keys.
 struct Level0 {
     DBuf<u64> keys0;
     std::vector<u64> gbase;
+    std::vector<u64> bounds;
     u64 gmax = 0;
 };
-static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, u32 g0, u64 mult,
-                             u64 group_max, u64 extra, Level0& out) {
-    const u32 nb0 = g0 * HC_NB2;
-    DBuf<u32> ghist(e, nb0);
+static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, u32 g0, u64 group_max, u64 extra,
+                             Level0& out, const u32* shist_given = nullptr) {
+    range_kernel_attrs(e);
+    u64 cap = ks ? ks->n : 0;
+    for (auto& pv : pvs) cap += pv.n;
+    RpPlan pl;
+    const u64 p_lo = ks ? ks->p_lo : 0, p_hi = ks ? ks->p_hi : (1ull << 32);
+    plan_geometry(pl, 2 * k, g0, p_lo, p_hi);
+    build_plan<ENC_NT2>(e, k, pvs, ks, SymView{nullptr, 0}, cap, pl, shist_given);
+    const RpView rv = pl.view();
+    DBuf<u32> ghist(e, g0);
     ghist.zero();
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(fn_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(hk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(fn_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(hk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SCATTER_SMEM));
-        attr_set = true;
-    }
-    const size_t hist_smem = (size_t)nb0 * 4;
+    const size_t hist_smem = sizeof(RpShared) + (size_t)g0 * 4;
     PhaseTimer pt(e);
     if (ks) {
-        int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hk_hist_kernel, HK_HIST_THREADS, hist_smem));
-        const u64 grid = std::min<u64>(div_up(ks->n, HK_HIST_THREADS * 8), (u64)e->num_sms * std::max(per_sm, 1));
-        if (ks->n) LAUNCH(e, hk_hist_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, nb0, mult, ghist.p);
+        const u64 grid = std::min<u64>(div_up(ks->n, HK_HIST_THREADS * 8), (u64)e->num_sms * 2);
+        if (ks->n) LAUNCHN(e, "hk_hist_kernel<level0>", hk_hist_kernel<false>, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, rv, g0, ghist.p);
     } else {
-        if (mult != HC_MULT1) throw Mc2Error(MC2_ERR_INVALID, "level-0 partition of packed streams uses the first hash (internal error)");
-        int per_sm = 1;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn_hist_kernel, FN_HIST_THREADS, hist_smem));
         for (auto& pv : pvs) {
-            const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * std::max(per_sm, 1));
-            if (grid) LAUNCH(e, fn_hist_kernel, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, nb0, ghist.p);
+            const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), FN_HIST_THREADS), (u64)e->num_sms * 2);
+            if (grid) LAUNCHN(e, "fn_hist_kernel<level0>", fn_hist_kernel<false>, (unsigned)grid, FN_HIST_THREADS, hist_smem, pv, k, rv, g0, ghist.p);
         }
     }
-    std::vector<u32> h(nb0);
-    d2h(e, h.data(), (const u32*)ghist.p, nb0);
+    std::vector<u32> h(g0);
+    std::vector<uint2> l1(g0);
+    d2h(e, h.data(), (const u32*)ghist.p, g0);
+    d2h(e, l1.data(), (const uint2*)pl.l1.p, g0);
     pt.mark("level-0 histogram");
     out.gbase.assign(g0 + 1, 0);
+    out.bounds.assign(g0 + 1, p_hi);
     out.gmax = 0;
     for (u32 g = 0; g < g0; ++g) {
-        u64 n = 0;
-        for (u32 j = 0; j < HC_NB2; ++j) n += h[(u64)g * HC_NB2 + j];
-        out.gbase[g + 1] = out.gbase[g] + n;
-        out.gmax = std::max(out.gmax, n);
+        out.gbase[g + 1] = out.gbase[g] + h[g];
+        out.gmax = std::max<u64>(out.gmax, h[g]);
+        out.bounds[g] = g == 0 ? p_lo : std::max<u64>(out.bounds[g - 1], std::min<u64>(l1[g].x, p_hi));
     }
     const u64 total = out.gbase[g0];
     if (total == 0) return true;
@@ -596,13 +576,12 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     pt.mark("level-0 allocation");
     CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM16, ks->keys, ks->n, nb0, g0, mult, cur0.p,
-               out.keys0.p, (const u64*)gbase_dev.p);
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur0.p, out.keys0.p,
+               (const u64*)gbase_dev.p);
     } else {
         for (auto& pv : pvs) {
             const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
-            if (grid) LAUNCH(e, fn_scatter1_kernel<false>, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM16, pv, k, nb0, g0, cur0.p, out.keys0.p,
-                             (const u64*)gbase_dev.p);
+            if (grid) LAUNCH(e, fn_scatter1_kernel, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM_LUT, pv, k, rv, cur0.p, out.keys0.p, (const u64*)gbase_dev.p);
         }
     }
     CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // (host vector was the source of an async copy)
@@ -614,23 +593,24 @@ static u32 level0_groups(u64 cap, u64 hash_max) {
     return (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(2, div_up(cap, std::max<u64>(1, hash_max / 2))));
 }
 
-// A chunk with more windows than one hash batch holds (-s 0 on a large file): a level-0 partition of ALL its keys by an
-// independent hash into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then
-// the usual two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact
-// for the whole chunk.  Returns false (nothing counted) when the keys do not fit in free device memory.
-static bool sparse_chunk_hash_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, const KeySpan* ks, u64 hash_max) {
+// A chunk with more windows than one batch holds (-s 0 on a large file): a level-0 partition of ALL its keys by key
+// range into groups that fit, written once to HBM (8 B per window -- sized for the 180 GB of a B200), then the usual
+// two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact for the
+// whole chunk, and the groups' sorted rows follow each other in key order.  Returns false (nothing counted) when the
+// keys do not fit in free device memory.
+static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, const KeySpan* ks, u64 hash_max) {
     u64 cap = ks ? ks->n : 0;
     for (auto& pv : pvs) cap += pv.n;
     const u32 g0 = level0_groups(cap, hash_max);
     if (div_up(cap, g0) > hash_max) return false;
     Level0 l0;
-    if (!level0_partition(e, s->k, pvs, ks, g0, ks ? HC_MULT3 : HC_MULT1, hash_max, 3 * 8 * div_up(cap, g0) * 2, l0)) return false;
+    if (!level0_partition(e, s->k, pvs, ks, g0, hash_max, 3 * 8 * div_up(cap, g0) * 2, l0)) return false;
     PhaseTimer pt(e);
     for (u32 g = 0; g < g0; ++g) {
         const u64 n = l0.gbase[g + 1] - l0.gbase[g];
         if (!n) continue;
-        KeySpan span{l0.keys0.p + l0.gbase[g], n, true};
-        sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
+        KeySpan span{l0.keys0.p + l0.gbase[g], n, l0.bounds[g], std::max<u64>(l0.bounds[g + 1], l0.bounds[g] + 1)};
+        sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
     }
     pt.mark("groups");
     return true;
@@ -661,12 +641,12 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     *need_exceptions = false;
     if (!e->opt_fast_nt || s->k > 32 || len == 0) return false;
     if (e->opt_force_enc > 0 || e->opt_force_path == PATH_WIDE) return false;
-    const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
-    // which plans the packed lane serves: 2-bit sparse keys through the hash tables (min_count >= 2), and dense 4^k tables
+    const u64 hash_max = range_batch_max(e, s);
+    // which plans the packed lane serves: 2-bit sparse keys through the range partition, and dense 4^k tables
     auto served = [&](const Plan& pl) {
         if (pl.enc != ENC_NT2) return false;
         if (pl.path == PATH_DENSE) return s->k <= 15;
-        if (pl.path != PATH_SPARSE || s->c < 2 || e->opt_sparse_algo == 1) return false;
+        if (pl.path != PATH_SPARSE || e->opt_sparse_algo == 1) return false;
         return len <= hash_max || e->opt_big_chunks != 0;
     };
     if (s->plan.path != PATH_UNSET && !served(s->plan)) return false;
@@ -757,7 +737,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
         e->ride_len = sizeof(FnStats);
         e->ride_done = false;
         try {
-            sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
+            sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, &pv);
         } catch (...) {
             e->ride_dev = nullptr;
             throw;
@@ -772,7 +752,7 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     std::vector<PackedView> pvs;
     for (auto& sp : spans)
         if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
-    if (!sparse_chunk_hash_big(e, s, pvs, nullptr, hash_max)) return false;
+    if (!sparse_chunk_big(e, s, pvs, nullptr, hash_max)) return false;
     const FnStats fs3 = read_scalar<FnStats>(e, st.p);
     *need_exceptions = (fs3.packed2 >> 32) != 0;
     return true;

@@ -116,6 +116,44 @@ static u64 seg_reduce(mc2_engine* e, Acc acc, u64 m, const u64* w_sorted, u64 c,
     return ns;
 }
 
+// Parts that are each sorted and whose key ranges follow each other without overlap (the groups of a range-partitioned
+// chunk, in group order): the merged table is their concatenation.  Returns false when the parts are not of that kind.
+static bool concat_sorted_parts(mc2_engine* e, std::vector<FastPart>& parts, u64 M, FastPart& out) {
+    std::vector<const u64*> ptrs;
+    std::vector<u64> ns;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        if (!p.sorted) return false;
+        ptrs.push_back(p.keys.p);
+        ns.push_back(p.n);
+    }
+    const u32 np = (u32)ptrs.size();
+    DBuf<const u64*> dptr(e, np);
+    DBuf<u64> dn(e, np), dends(e, 2ull * np);
+    CUDA_CHECK(cudaMemcpyAsync(dptr.p, ptrs.data(), np * sizeof(u64*), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dn.p, ns.data(), np * 8ull, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, part_ends_kernel, (unsigned)div_up(np, 128), 128, 0, (const u64* const*)dptr.p, (const u64*)dn.p, np, dends.p);
+    std::vector<u64> ends(2ull * np);
+    d2h(e, ends.data(), (const u64*)dends.p, 2ull * np);
+    for (u32 i = 1; i < np; ++i)
+        if (ends[2 * i] <= ends[2 * i - 1]) return false;              // first key of part i must exceed the last key of part i-1
+    out.n = M;
+    out.sorted = true;
+    out.keys.alloc(e, M);
+    out.counts.alloc(e, M);
+    u64 at = 0;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(out.keys.p + at, p.keys.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(out.counts.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += p.n;
+        p.keys.release();
+        p.counts.release();
+        p.n = 0;
+    }
+    return true;
+}
+
 // merge several (key, count) parts: concat, sort pairs, sum equal keys, keep sums >= c
 static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int key_bits, u64 c, FastPart& out) {
     u64 M = 0;
@@ -127,6 +165,7 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
         int nonempty = 0;
         for (auto& p : parts) if (p.n) { only = &p; nonempty++; }
         if (nonempty == 1 && only->sorted) { out = std::move(*only); return; }
+        if (nonempty > 1 && concat_sorted_parts(e, parts, M, out)) return;
     }
     DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
     u64 at = 0;

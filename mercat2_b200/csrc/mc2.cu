@@ -16,7 +16,7 @@
 #include "radix.cuh"
 #include "wide.cuh"
 #include "chunker.cuh"
-#include "hashcount.cuh"
+#include "rangecount.cuh"
 #include "fastnt.cuh"
 #include "metrics.cuh"
 #include "tsv.cuh"
@@ -44,10 +44,11 @@ struct mc2_engine {
     int opt_parse_single = 0;              // packed lane: 1 = one pass over the text with chained look-back (measured slower: 0.39 vs 0.28 ms per 100 MiB)
     u64 opt_file_piece = 32ull << 20;      // bytes per piece of the streaming file reader
     u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
-    int opt_count_variant = 2;             // min_count >= 2: 2 = bitmap pre-filter (faster as measured), 3 = 16-bit counter pre-filter
-    int opt_scatter_variant = 0;           // bit0: stage destination indices, bit1: max shared-memory carveout
-    int opt_sparse_algo = 0;               // 0 auto (hash tables when min_count >= 2), 1 radix sort, 2 hash tables
+    int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)
+    int opt_sparse_algo = 0;               // 0 auto (range partition + shared-memory tables), 1 radix sort, 2 range partition
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
+    bool range_attrs_set = false;          // kernel attributes (dynamic shared memory opt-in) are per device: set once per engine
+    bool dense_attrs_set[3] = {false, false, false};
     // stats
     u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0, ovf_buckets = 0;
     double device_us = 0;
@@ -95,7 +96,7 @@ struct mc2_engine {
 static inline bool prof_on(const mc2_engine* e, const char* name) {
     if (!e->profile) return false;
     if (e->profile != 3) return true;
-    return !strncmp(name, "hc_scatter2", 11) || !strncmp(name, "fn_scatter1", 11) || !strncmp(name, "hc_count2", 9);
+    return !strncmp(name, "hc_scatter2", 11) || !strncmp(name, "fn_scatter1", 11) || !strncmp(name, "hk_scatter1", 11) || !strncmp(name, "rc_count", 8);
 }
 
 #define LAUNCHN(e, name, kern, grid, block, smem, ...)                            \
@@ -299,7 +300,8 @@ struct mc2_sample {
     std::vector<FastPart> fast;
     std::vector<WidePart> wide;
     u64 n_chunks = 0;
-    double bucket_scale = 1.0;             // shrinks when many hash buckets overflow (heavily duplicated keys)
+    double bucket_scale = 1.0;             // shrinks when many sub-buckets overflow their table
+    bool dup_rich = false;                 // most keys repeat (seen on an earlier chunk / group): count without the bitmap pre-filter
     PrePass pre;
     const u8* next_text = nullptr;         // the chunk that follows the one being counted (resident text), for PrePass
     u64 next_len = 0;
@@ -406,8 +408,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "force_encoding") e->opt_force_enc = (int)value;
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
-    else if (n == "scatter_variant") e->opt_scatter_variant = (int)value;
-    else if (n == "count_variant") e->opt_count_variant = (int)value;
+    else if (n == "count_mode") e->opt_count_mode = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
     else if (n == "parse_single") e->opt_parse_single = (int)value;
     else if (n == "prefetch_pass") e->opt_prefetch_pass = (int)value;
@@ -558,6 +559,24 @@ int mc2_table_lower_bound(mc2_table* t, const uint64_t* splitters, uint64_t m, u
     API_END
 }
 
+int mc2_table_export_packed(mc2_table* t, uint64_t* keys, uint64_t* counts, uint64_t capacity, uint64_t* rows) {
+    API_BEGIN
+    if (!t || !rows) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    const u64 n = t->fast.n;
+    if (n && (!keys || !counts)) throw Mc2Error(MC2_ERR_INVALID, "NULL buffer");
+    if (n > capacity) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+    mc2_engine* e = t->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(keys, t->fast.keys.p, n * 8, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(counts, t->fast.counts.p, n * 8, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->d2h_bytes += n * 16;
+    }
+    *rows = n;
+    API_END
+}
+
 int mc2_table_export_wide(mc2_table* t, char* kmers, uint64_t* counts) {
     API_BEGIN
     if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
@@ -681,33 +700,38 @@ struct mc2_keys {
     mc2_engine* e = nullptr;
     int k = 0;
     u32 groups = 0;
+    // open state: the packed text and its sampled prefix histogram (mc2_keys_open), until mc2_keys_partition ran
+    DBuf<u8> holder;
+    std::vector<FnSpan> spans;
+    std::vector<PackedView> pvs;
+    DBuf<u32> shist;
+    bool partitioned = false;
     Level0 l0;
     u64 exception_symbols = 0;
+    u64 windows = 0;
 };
 
-int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, uint32_t groups, mc2_keys** out) {
+int mc2_keys_open(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, mc2_keys** out) {
     API_BEGIN
     check_count_args(e, text, nbytes, k);
     if (!out) throw Mc2Error(MC2_ERR_INVALID, "out is NULL");
     if (k > 32) throw Mc2Error(MC2_ERR_LIMIT, "key partition needs k <= 32 (2-bit packed keys)");
-    if (groups < 1 || groups > HC_MAX_NB1) throw Mc2Error(MC2_ERR_INVALID, "groups must be in [1, 400]");
     CUDA_CHECK(cudaSetDevice(e->device));
+    range_kernel_attrs(e);
     std::unique_ptr<mc2_keys> ks(new mc2_keys);
     ks->e = e;
     ks->k = k;
-    ks->groups = groups;
-    ks->l0.gbase.assign(groups + 1, 0);
+    ks->shist.alloc(e, RP_LUT);
+    ks->shist.zero();
     if (nbytes) {
-        DBuf<u8> holder;
-        const u8* d = to_device(e, text, nbytes, space, holder);
+        const u8* d = to_device(e, text, nbytes, space, ks->holder);
         std::vector<u64> cuts;
         if (!fn_span_cuts(e, d, nbytes, cuts)) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text cannot be cut into spans at header lines");
         DBuf<FnStats> st(e, 1);
         st.zero();
-        std::vector<FnSpan> spans(cuts.size() - 1);
-        std::vector<PackedView> pvs;
+        ks->spans.resize(cuts.size() - 1);
         for (size_t i = 0; i + 1 < cuts.size(); ++i) {
-            FnSpan& sp = spans[i];
+            FnSpan& sp = ks->spans[i];
             sp.text = d + cuts[i];
             sp.len = cuts[i + 1] - cuts[i];
             const bool single = e->opt_parse_single != 0;
@@ -715,24 +739,74 @@ int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int spa
             if (fs.complex) throw Mc2Error(MC2_ERR_LIMIT, "key partition: text is not plain FASTA (whitespace, '*' or non-ASCII bytes in sequence lines)");
             if (!sp.nsym) continue;
             if (!single) fn_write_pass(e, sp, st);
-            pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
+            ks->pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
+            ks->windows += sp.nsym;
         }
-        if (!level0_partition(e, k, pvs, nullptr, groups, HC_MULT1, (1ull << 32) - 1, 0, ks->l0))
-            throw Mc2Error(MC2_ERR_LIMIT, "key partition: the keys do not fit in free device memory");
         const FnStats fs2 = read_scalar<FnStats>(e, st.p);
         ks->exception_symbols = fs2.packed2 >> 32;
+        ks->holder.release();                                    // the packed codes are all that is needed from here on
+        // sampled prefix histogram over the whole key space (the caller may sum it over ranks before partitioning)
+        const u64 stride = std::max<u64>(1, ks->windows / RP_SAMPLE_WINDOWS);
+        for (auto& pv : ks->pvs) {
+            const u64 nwords = div_up(pv.n, 16);
+            const u64 grid = std::min<u64>(div_up(div_up(nwords, stride), FN_HIST_THREADS), (u64)e->num_sms * 2);
+            LAUNCH(e, rp_sample_packed_kernel, (unsigned)std::max<u64>(grid, 1), FN_HIST_THREADS, 0, pv, k, stride, 0u, 32u - RP_LUT_LOG2, ks->shist.p);
+        }
     }
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     *out = ks.release();
     API_END
 }
 
-int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols) {
+int mc2_keys_sample(mc2_keys* ks, uint32_t** hist, uint64_t* entries) {
+    API_BEGIN
+    if (!ks || !hist || !entries) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    *hist = ks->shist.p;
+    *entries = RP_LUT;
+    API_END
+}
+
+int mc2_keys_partition(mc2_keys* ks, uint32_t groups) {
     API_BEGIN
     if (!ks) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (ks->partitioned) throw Mc2Error(MC2_ERR_INVALID, "the keys are already partitioned");
+    if (groups < 1 || groups > HC_MAX_NB1) throw Mc2Error(MC2_ERR_INVALID, "groups must be in [1, 384]");
+    mc2_engine* e = ks->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    ks->groups = groups;
+    ks->l0.gbase.assign(groups + 1, 0);
+    ks->l0.bounds.assign(groups + 1, 1ull << 32);
+    ks->l0.bounds[0] = 0;
+    if (!level0_partition(e, ks->k, ks->pvs, nullptr, groups, (1ull << 32) - 1, 0, ks->l0, ks->shist.p))
+        throw Mc2Error(MC2_ERR_LIMIT, "key partition: the keys do not fit in free device memory");
+    ks->pvs.clear();
+    ks->spans.clear();
+    ks->partitioned = true;
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    API_END
+}
+
+int mc2_partition_keys(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, uint32_t groups, mc2_keys** out) {
+    if (!out) { g_err = "out is NULL"; return MC2_ERR_INVALID; }
+    if (groups < 1 || groups > HC_MAX_NB1) { g_err = "groups must be in [1, 384]"; return MC2_ERR_INVALID; }
+    mc2_keys* ks = nullptr;
+    int st = mc2_keys_open(e, text, nbytes, space, k, &ks);
+    if (st < 0) return st;
+    st = mc2_keys_partition(ks, groups);
+    if (st < 0) { mc2_keys_free(ks); return st; }
+    *out = ks;
+    return MC2_OK;
+}
+
+int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t* total, uint64_t* exception_symbols, uint64_t* bounds) {
+    API_BEGIN
+    if (!ks) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (!ks->partitioned) throw Mc2Error(MC2_ERR_INVALID, "mc2_keys_partition has not run");
     if (keys) *keys = (const uint64_t*)ks->l0.keys0.p;
     if (sizes)
         for (u32 g = 0; g < ks->groups; ++g) sizes[g] = ks->l0.gbase[g + 1] - ks->l0.gbase[g];
+    if (bounds)
+        for (u32 g = 0; g <= ks->groups; ++g) bounds[g] = ks->l0.bounds[g];
     if (total) *total = ks->l0.gbase[ks->groups];
     if (exception_symbols) *exception_symbols = ks->exception_symbols;
     API_END
@@ -744,12 +818,13 @@ void mc2_keys_free(mc2_keys* ks) {
     delete ks;
 }
 
-int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space) {
+int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int space, uint64_t prefix_lo, uint64_t prefix_hi) {
     API_BEGIN
     if (!s || (n && !keys)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
     mc2_engine* e = s->e;
     CUDA_CHECK(cudaSetDevice(e->device));
     if (s->k > 32) throw Mc2Error(MC2_ERR_LIMIT, "packed keys need k <= 32");
+    if (prefix_hi > (1ull << 32) || (prefix_hi && prefix_lo >= prefix_hi)) throw Mc2Error(MC2_ERR_INVALID, "bad prefix range");
     if (s->plan.path == PATH_UNSET) {
         s->plan.enc = ENC_NT2;
         s->plan.path = PATH_SPARSE;
@@ -767,10 +842,10 @@ int mc2_sample_add_keys(mc2_sample* s, const uint64_t* keys, uint64_t n, int spa
             e->h2d_bytes += n * 8;
             d = holder.p;
         }
-        const u64 hash_max = std::min<u64>((u64)HC_MAX_NB1 * HC_NB2 * e->opt_hash_bucket_keys, e->opt_batch_symbols);
-        KeySpan span{d, n, true};
-        if (n <= hash_max) sparse_chunk_hash<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
-        else if (!sparse_chunk_hash_big(e, s, std::vector<PackedView>(), &span, hash_max))
+        const u64 hash_max = range_batch_max(e, s);
+        KeySpan span{d, n, prefix_hi ? prefix_lo : 0ull, prefix_hi ? prefix_hi : (1ull << 32)};
+        if (n <= hash_max) sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
+        else if (!sparse_chunk_big(e, s, std::vector<PackedView>(), &span, hash_max))
             throw Mc2Error(MC2_ERR_LIMIT, "add_keys: the keys do not fit in free device memory");
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
     }

@@ -272,6 +272,11 @@ seg_compact_kernel(const u64* __restrict__ seg_start, const u64* __restrict__ se
 }
 
 // small gathers
+// first and last key of every part (ends[2i], ends[2i+1]); parts are non-empty
+__global__ void part_ends_kernel(const u64* const* __restrict__ ptrs, const u64* __restrict__ ns, u32 np, u64* __restrict__ ends) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) { ends[2 * i] = ptrs[i][0]; ends[2 * i + 1] = ptrs[i][ns[i] - 1]; }
+}
 __global__ void gather_u64_kernel(const u64* __restrict__ src, const u64* __restrict__ idx, u64 n, u64* __restrict__ dst) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];

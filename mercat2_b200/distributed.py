@@ -151,14 +151,21 @@ ENC_NT2, ENC_AA5, ENC_BYTE = 0, 1, 2
 KEY_CODE, KEY_DENSE_AA = 0, 1
 
 
-def _to_tensor(engine, ptr: int, n: int, device):
-    """n int64 words of engine memory as a tensor the communication library owns (one device-to-device copy)."""
+class _DeviceMemory:
+    """n elements of engine-owned device memory, exposed through the CUDA array interface (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _to_tensor(engine, ptr: int, n: int, device, typestr: str = "<i8"):
+    """n words of engine memory as a torch tensor VIEW (no copy): NCCL reads and writes the engine's own buffers.  The
+    engine's calls are synchronous at return, so the memory is ready; the tensor must not outlive the engine object
+    that owns the memory."""
     import torch
-    t = torch.empty(n, dtype=torch.int64, device=device)
-    if n and ptr:
-        torch.cuda.synchronize(device)
-        engine.device_copy(t.data_ptr(), ptr, n * 8)
-    return t
+    if not n or not ptr:
+        return torch.empty(0, dtype=torch.int64 if typestr == "<i8" else torch.int32, device=device)
+    return torch.as_tensor(_DeviceMemory(ptr, n, typestr), device=device)
 
 
 def decode_key(key: int, k: int, encoding: int, key_kind: int) -> bytes:
@@ -258,11 +265,9 @@ def reduce_dense_sample(engine, sample, dist, device, root: int = 0) -> bool:
         if bins != dense[0][0]:
             raise RuntimeError("dense plan mismatch between ranks")
     if dist.get_world_size() > 1:
-        t = _to_tensor(engine, ptr, bins, device)
+        t = _to_tensor(engine, ptr, bins, device)                 # a view: NCCL reduces the engine's table in place
         dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize(device)
-        if dist.get_rank() == root:
-            engine.device_copy(ptr, t.data_ptr(), bins * 8)
     return True
 
 
@@ -362,64 +367,125 @@ def _sum_rows(parts_k, parts_c, k):
     return np.frombuffer(uniq.tobytes(), dtype=np.uint8).reshape(-1, k), sums
 
 
+def _prefix_text(p: int, n: int) -> bytes:
+    """The first n (<= 16) symbols of the 32-bit key prefix p as text."""
+    return bytes(b"ACGT"[(p >> (30 - 2 * j)) & 3] for j in range(n))
+
+
 def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, device, out_path=None,
-                                 basename: str = "sample", groups_per_rank: int = 4):
+                                 basename: str = "sample", groups_per_rank: int = 16, timings: dict | None = None):
     """ONE piece (chunk) whose text is split by position over the ranks (each part starts at a header line).  The
-    `-c` filter must see whole-piece counts, so keys are exchanged BEFORE counting: every rank partitions the packed
-    keys of its windows by hash into world * groups_per_rank groups on its GPU, one NCCL all-to-all moves each group
-    to its owner, the owner counts what it received as one chunk.  The (few) windows outside ACGT are counted
-    unfiltered, summed across ranks and filtered on rank 0.  The surviving rows are then re-partitioned by key range
-    (merge_table_device) so that rank order = sorted order, and the TSV is written by byte ranges.
-    Returns this rank's part of the final table."""
-    import os
+    `-c` filter must see whole-piece counts (lib/mercat2_kmers.py:73-78 on the unsplit piece), so keys are exchanged
+    BEFORE counting:
+
+    1. every rank packs its text and samples its keys' prefixes; the samples are summed with one NCCL all-reduce (on the
+       engine's buffer) so that all ranks cut the key space at the same world * groups_per_rank boundaries;
+    2. every rank groups the order-preserving 64-bit keys of all its windows by key range on its GPU;
+    3. in groups_per_rank rounds, round j moves range (r, j) to rank r with one NCCL all-to-all straight out of the
+       engine's key array; the receiver counts round j (all occurrences of that range: the filter is exact) while round
+       j + 1 is already in flight;
+    4. rank r ends up with the sorted rows of the r-th slice of the key space: rank order == key order, the table is the
+       concatenation of the ranks' parts and nothing is sorted or merged afterwards.
+
+    The (few) windows outside ACGT are counted unfiltered, summed across ranks, filtered, and each row joins the rank
+    whose key range it sorts into.  Returns this rank's part of the final table.  `timings` (optional dict) receives
+    per-phase milliseconds and the bytes this rank sent / received."""
     import time
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    trace = os.environ.get("MC2_DEBUG_PHASES") and rank == 0
+    m = groups_per_rank
+    groups = world * m
     t_last = [time.perf_counter()]
 
     def mark(what):
-        if trace:
+        if timings is not None:
             torch.cuda.synchronize(device)
             now = time.perf_counter()
-            print(f"[phase] sharded: {what:<24s} {(now - t_last[0]) * 1e3:9.3f} ms", flush=True)
+            timings[what] = timings.get(what, 0.0) + (now - t_last[0]) * 1e3
             t_last[0] = now
 
-    groups = world * groups_per_rank
-    keys = engine.partition_keys(my_text, k, groups)
-    mark("partition_keys")
-    send = [sum(keys.sizes[r * groups_per_rank:(r + 1) * groups_per_rank]) for r in range(world)]
-    matrix = _agree(dist, (send, keys.exception_symbols))
-    recv = [matrix[src][0][rank] for src in range(world)]
-    send_t = _to_tensor(engine, keys.ptr, keys.total, device)
-    keys.close()
-    recv_t = torch.empty(sum(recv), dtype=torch.int64, device=device)
+    keys = engine.open_keys(my_text, k)
+    mark("parse_ms")
     if world > 1:
-        dist.all_to_all_single(recv_t, send_t, recv, send)
+        hist = _to_tensor(engine, keys.sample_ptr, keys.sample_entries, device, "<i4")
+        dist.all_reduce(hist)
+        torch.cuda.synchronize(device)
+    keys.partition(groups)
+    mark("partition_ms")
+    sizes = torch.tensor(keys.sizes, dtype=torch.int64, device=device)
+    if world > 1:
+        all_sizes = torch.empty((world, groups), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_sizes, sizes)
+        exc = torch.tensor([keys.exception_symbols], dtype=torch.int64, device=device)
+        dist.all_reduce(exc)
+        any_exceptions = int(exc.item()) > 0
     else:
-        recv_t.copy_(send_t)
-    del send_t
-    torch.cuda.synchronize(device)
-    mark("all_to_all")
+        all_sizes = sizes.view(1, groups)
+        any_exceptions = keys.exception_symbols > 0
+    all_sizes = all_sizes.cpu().tolist()
+    offsets = [0]
+    for n in keys.sizes:
+        offsets.append(offsets[-1] + n)
+    send_all = _to_tensor(engine, keys.ptr, keys.total, device)
     sample = engine.sample(k, min_count)
-    sample.add_keys(recv_t.data_ptr(), int(recv_t.numel()))
-    del recv_t
-    mark("add_keys")
-    if any(m[1] > 0 for m in matrix):                    # literal-byte windows: unfiltered local tables -> sum -> filter
+    recv_max = max(sum(all_sizes[src][rank * m + j] for src in range(world)) for j in range(m))
+    bufs = [torch.empty(max(recv_max, 1), dtype=torch.int64, device=device) for _ in range(2 if world > 1 else 0)]
+    sent = received = 0
+
+    def start_round(j):
+        """all-to-all of range (r, j) -> rank r; returns (work, tensor holding this rank's range, its key count)"""
+        n_in = [all_sizes[src][rank * m + j] for src in range(world)]
+        if world == 1:
+            g = rank * m + j
+            return None, send_all[offsets[g]:offsets[g + 1]], n_in[0]
+        buf = bufs[j & 1]
+        outs, at = [], 0
+        for n in n_in:
+            outs.append(buf[at:at + n])
+            at += n
+        ins = [send_all[offsets[r * m + j]:offsets[r * m + j + 1]] for r in range(world)]
+        work = dist.all_to_all(outs, ins, async_op=True)
+        return work, buf[:at], at
+
+    pending = start_round(0)
+    for j in range(m):
+        work, part, n = pending
+        if work is not None:
+            work.wait()
+            torch.cuda.current_stream(device).synchronize()
+        mark("exchange_wait_ms")
+        if j + 1 < m:
+            pending = start_round(j + 1)          # in flight while round j is counted
+        g = rank * m + j
+        sent += sum(keys.sizes[r * m + j] for r in range(world) if r != rank) * 8
+        received += sum(all_sizes[src][g] for src in range(world) if src != rank) * 8
+        if n:
+            sample.add_keys(part.data_ptr(), n, True, keys.bounds[g], max(keys.bounds[g + 1], keys.bounds[g] + 1))
+        mark("count_ms")
+    bounds = keys.bounds
+    del send_all
+    keys.close()
+    if any_exceptions:                               # literal-byte windows: unfiltered local tables -> sum -> filter -> owner
         t = engine.count_exceptions(my_text, k)
         wk, wc = t.wide_arrays()
         t.close()
-        gathered = _agree(dist, (wk, wc))
-        if rank == 0:
-            sk, sc = _sum_rows([g[0] for g in gathered], [g[1] for g in gathered], k)
-            keep = sc >= np.uint64(max(1, min_count))
-            if keep.any():
-                sample.add_rows(sk[keep], sc[keep])
+        gathered = _agree(dist, (wk, wc)) if world > 1 else [(wk, wc)]
+        sk, sc = _sum_rows([g[0] for g in gathered], [g[1] for g in gathered], k)
+        keep = sc >= np.uint64(max(1, min_count))
+        sk, sc = sk[keep], sc[keep]
+        if len(sc):
+            kk = min(k, 16)
+            cut_text = np.array([_prefix_text(bounds[r * m], kk) for r in range(1, world)], dtype=f"S{kk}")
+            heads = _as_keys(np.ascontiguousarray(sk[:, :kk]), kk)
+            dest = np.searchsorted(cut_text, heads, side="right") if world > 1 else np.zeros(len(sc), np.int64)
+            mine = dest == rank
+            if mine.any():
+                sample.add_rows(sk[mine], sc[mine])
     table = sample.finish()
-    mark("finish")
-    part = merge_table_device(engine, table, dist, device)
-    table.close()
-    mark("key-range merge")
+    mark("finish_ms")
+    if timings is not None:
+        timings["nvlink_bytes_sent"] = timings.get("nvlink_bytes_sent", 0) + sent
+        timings["nvlink_bytes_received"] = timings.get("nvlink_bytes_received", 0) + received
     if out_path:
-        write_tsv_sharded(part, out_path, basename, dist)
-    return part
+        write_tsv_sharded(table, out_path, basename, dist)
+    return table

@@ -38,6 +38,7 @@ def reset(engine):
     engine.set_option("fast_nt", 1)
     engine.set_option("hash_bucket_keys", 3500)
     engine.set_option("parse_single", 0)
+    engine.set_option("count_mode", -1)
 
 
 def diff_msg(got, want):
@@ -74,8 +75,8 @@ def test_edge_cases_forced_paths(engine, edge_cases, path):
 
 @pytest.mark.parametrize("algo,fast_nt", [(1, 0), (2, 0), (2, 1)])
 def test_edge_cases_sparse_algorithms(engine, edge_cases, algo, fast_nt):
-    """force the sparse path with the radix-sort (1) and the hash-table (2) counting kernels, the latter
-    with and without the SWAR/packed nucleotide lane"""
+    """force the sparse path with the radix-sort (1) and the range-partition + shared-memory-table (2) counting
+    kernels, the latter with and without the SWAR/packed nucleotide lane"""
     reset(engine)
     engine.set_option("force_path", 2)
     engine.set_option("sparse_algo", algo)
@@ -586,7 +587,7 @@ def test_big_chunk_level0_partition(engine, k, c):
     reset(engine)
     text = synth_reads(5000, 150, seed=31, n_rate=0.002, lower_rate=0.0, genome_len=30000)
     want = orc.find_kmers_text(text.decode(), k, c)
-    engine.set_option("hash_bucket_keys", 4)          # one hash batch = 400 * 128 * 4 = 204 800 keys
+    engine.set_option("hash_bucket_keys", 4)          # one batch = 384 * 128 * 4 = 196 608 keys
     engine.set_option("span_bytes", 64 << 10)
     engine.set_option("force_path", 2)
     try:
@@ -739,8 +740,7 @@ def test_merge_tsv_vs_reference(engine, tmp_path, label):
     assert out3.read_bytes() == b"k-mer\ta\tb\nAAC\t5\t2\nACN\t7\t0\nGGG\t0\t123456789012\nTTT\t1\t0\n"
 
 
-@pytest.mark.parametrize("option,value", [("count_variant", 3), ("scatter_variant", 1), ("scatter_variant", 8), ("parse_single", 1),
-                                          ("prefetch_pass", 0)])
+@pytest.mark.parametrize("option,value", [("count_mode", 0), ("count_mode", 1), ("parse_single", 1), ("prefetch_pass", 0)])
 def test_experiment_variants_stay_exact(engine, option, value):
     """the kernel variants kept behind engine options (measured, not the default -- DESIGN.md §4) count the same tables"""
     reset(engine)
@@ -754,7 +754,7 @@ def test_experiment_variants_stay_exact(engine, option, value):
             table, offs = engine.count_sample(text, 25, 2, len(text) // pieces)
             got = table.to_dict()
         finally:
-            defaults = {"count_variant": 2, "scatter_variant": 0, "parse_single": 0, "prefetch_pass": 1}
+            defaults = {"count_mode": -1, "parse_single": 0, "prefetch_pass": 1}
             engine.set_option(option, defaults[option])
         if want is None:
             want = got
@@ -813,3 +813,115 @@ def test_c_example_end_to_end(tmp_path):
     assert run.returncode == 0, run.stderr
     want = orc.tsv_bytes("sample", orc.find_kmers(src, 3, 10))
     assert out.read_bytes() == want and "Significant k-mers: 64" in run.stdout
+
+
+# ---- full-piece known answers on the range path (no oracle: numpy computes every count) ---------------------------
+def numpy_piece(n_reads, genome_len, seed, dup_every=0, dup_copies=3):
+    """(FASTA text bytes, codes uint8[n, 150]) of 150-bp error-free reads; every dup_every-th read is repeated
+    dup_copies times in a row (planted multiplicities)."""
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, genome_len, dtype=np.uint8)
+    starts = rng.integers(0, genome_len - 150, n_reads)
+    if dup_every:
+        src = np.arange(n_reads)
+        for j in range(1, dup_copies):
+            src[j::dup_every] = src[0::dup_every][: len(src[j::dup_every])]
+        starts = starts[src]
+    codes = genome[starts[:, None] + np.arange(150)[None, :]]
+    rec = np.empty((n_reads, 164), dtype=np.uint8)
+    rec[:, 0] = ord(">")
+    rec[:, 1] = ord("r")
+    ids = np.arange(n_reads, dtype=np.int64)
+    for j in range(10):
+        rec[:, 2 + j] = (ids // 10 ** (9 - j)) % 10 + 48
+    rec[:, 12] = 10
+    rec[:, 13:163] = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    rec[:, 163] = 10
+    return rec.reshape(-1), codes
+
+
+def numpy_table(codes, k, c):
+    """sorted (keys, counts) of all k-mers with count >= c -- keys are the engine's order-preserving 2-bit codes"""
+    n, L = codes.shape
+    w = L - k + 1
+    keys = np.zeros((n, w), dtype=np.uint64)
+    for j in range(k):
+        keys <<= np.uint64(2)
+        keys |= codes[:, j:j + w]
+    uniq, cnt = np.unique(keys.reshape(-1), return_counts=True)
+    keep = cnt >= c
+    return uniq[keep], cnt[keep].astype(np.uint64)
+
+
+@pytest.mark.parametrize("genome_len,dup_every,c", [(200_000_000, 5, 2), (2_000_000, 0, 2), (200_000_000, 5, 1), (20_000_000, 7, 3)])
+def test_full_piece_known_answer(engine, genome_len, dup_every, c):
+    """one 100 MiB piece (640 k reads, 76.8 M windows) through the default path: packed lane -> two-level range partition
+    -> shared-memory tables; the table (every key, every count) must equal numpy's sort/unique of the same windows.
+    Sparse data with planted repeats (bitmap pre-filter + exact second pass), 48x coverage (duplicate-rich mode),
+    min_count 1 (every distinct key is a row)."""
+    import torch
+    reset(engine)
+    n_reads = 640_000
+    text, codes = numpy_piece(n_reads, genome_len, seed=genome_len % 1000 + dup_every, dup_every=dup_every)
+    want_k, want_c = numpy_table(codes, 31, c)
+    assert len(want_k) > 1000
+    dev = torch.from_numpy(text).cuda()
+    for mode in (-1, 0, 1) if c >= 2 else (-1,):
+        engine.set_option("count_mode", mode)
+        try:
+            ovf0 = engine.stat("overflow_buckets")
+            table = engine.count_text(dev, 31, c)
+            info = table.info()
+            got_k, got_c = table.packed_arrays()
+            table.close()
+        finally:
+            reset(engine)
+        assert info["wide_rows"] == 0 and len(got_k) == len(want_k), (mode, len(got_k), len(want_k))
+        assert np.array_equal(got_k, want_k), f"mode {mode}: keys differ at row {int(np.argmax(got_k != want_k))}"
+        assert np.array_equal(got_c, want_c), f"mode {mode}: {int((got_c != want_c).sum())} counts differ"
+        if mode == -1 and genome_len >= 20_000_000:
+            assert engine.stat("overflow_buckets") == ovf0          # the common case never needs the sort fallback
+
+
+def test_full_piece_determinism(engine):
+    """the same 100 MiB piece counted 20 times at -c 2 (both counting modes): identical digests every time -- the
+    stress harness of tools/stress_hash.sh as a test (a lost count under any interleaving changes the digest)"""
+    import torch
+    reset(engine)
+    text, codes = numpy_piece(640_000, 300_000_000, seed=99, dup_every=3, dup_copies=2)
+    want_k, want_c = numpy_table(codes, 31, 2)
+    want = hashlib.md5(want_k.tobytes() + want_c.tobytes()).hexdigest()
+    dev = torch.from_numpy(text).cuda()
+    for mode in (1, 0):
+        engine.set_option("count_mode", mode)
+        try:
+            for rep in range(20 if mode == 1 else 5):
+                table = engine.count_text(dev, 31, 2)
+                got_k, got_c = table.packed_arrays()
+                table.close()
+                assert hashlib.md5(got_k.tobytes() + got_c.tobytes()).hexdigest() == want, f"mode {mode} repetition {rep}"
+        finally:
+            reset(engine)
+
+
+def test_oversized_buckets_take_rounds(engine):
+    """sub-buckets far beyond one register round (4096 keys): the counting kernel walks them in rounds from global
+    memory in both passes; repeated 10 times -- the variant of round 1 that did this lost counts in a timing-dependent
+    way, so this is its regression test"""
+    import torch
+    reset(engine)
+    text, codes = numpy_piece(60_000, 500_000, seed=5)           # 7.2 M windows, ~14x coverage: few distinct keys per bucket
+    dev = torch.from_numpy(text).cuda()
+    for c in (1, 2, 4):
+        want_k, want_c = numpy_table(codes, 31, c)
+        for bucket_keys, mode in ((20000, 0), (20000, 1), (60000, 0), (9000, 1)):
+            engine.set_option("hash_bucket_keys", bucket_keys)
+            engine.set_option("count_mode", mode)
+            try:
+                for rep in range(10):
+                    table = engine.count_text(dev, 31, c)
+                    got_k, got_c = table.packed_arrays()
+                    table.close()
+                    assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c), (c, bucket_keys, mode, rep)
+            finally:
+                reset(engine)
