@@ -100,7 +100,8 @@ int mc2_sample_add_file(mc2_sample* s, const char* path, int gunzip, uint64_t ch
                         uint64_t* text_bytes);
 /* Add already counted rows (rows*k bytes of k-mer text + rows counts, host memory) to the sample: the serial dict
  * merge of bin/mercat2.py:121-127 for tables that were counted elsewhere (another GPU / rank).  Equal k-mers are
- * summed by mc2_sample_finish on the device. */
+ * summed by mc2_sample_finish on the device -- also with the k-mers the sample counted itself (add_text / add_file /
+ * add_keys before or after this call): rows that fit the sample's packed alphabet join its packed rows. */
 int mc2_sample_add_rows(mc2_sample* s, const char* kmers, const uint64_t* counts, uint64_t rows);
 int mc2_sample_finish(mc2_sample* s, mc2_table** out);   /* consumes s */
 void mc2_sample_abort(mc2_sample* s);

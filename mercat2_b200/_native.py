@@ -133,7 +133,7 @@ def _as_buffer(data):
         a = np.ascontiguousarray(data).view(np.uint8)
         return a.ctypes.data, a.size, MC2_HOST, a
     if isinstance(data, str):
-        data = data.encode("ascii", errors="surrogateescape")
+        data = data.encode("utf-8", errors="surrogateescape")       # (non-ASCII is fine inside header lines only)
     mv = memoryview(data)
     a = np.frombuffer(mv, dtype=np.uint8)
     return a.ctypes.data, a.size, MC2_HOST, (mv, a)

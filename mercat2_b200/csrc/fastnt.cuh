@@ -3,8 +3,8 @@
 // Same semantics as parse.cuh (reference parser lib/mercat2_kmers.py:47-63) restricted to "simple" FASTA
 // text: line ends '\n', '\r\n' or '\r', 7-bit ASCII, and outside header lines no other whitespace/control
 // byte and no '*' (header lines may say anything: their bytes are dropped).  Any other
-// byte raises the `complex` flag and the chunk is redone by the general parser, so results never
-// depend on this lane.  What it buys: the byte-granular work is done once, with SWAR on 32-bit words
+// byte -- including a byte >= 0x80 outside a header line -- raises the `complex` flag and the chunk is redone by the
+// general parser, so results never depend on this lane.  What it buys: the byte-granular work is done once, with SWAR on 32-bit words
 // (about 11 ALU ops per text byte instead of ~55), and everything downstream works on 2-bit packed
 // symbols: a k-mer is two funnel shifts instead of a 16-step rolling loop.
 //
@@ -40,7 +40,7 @@ struct FnMasks {
     u32 nl, gt, acgt;   // 16-bit masks over the thread's 16 bytes
     u32 codes;          // 2-bit code of every byte (garbage where the byte is not ACGT)
     u32 cx;             // 16-bit mask: whitespace/control bytes and '*' (not simple unless inside a header line)
-    u32 hi;             // != 0: a byte >= 0x80 (never simple: the reference decodes text)
+    u32 hi;             // 16-bit mask: bytes >= 0x80 (simple only inside a header line, whose text is dropped)
 };
 
 template <bool CODES>
@@ -53,7 +53,7 @@ __device__ __forceinline__ FnMasks fn_classify(const u32 w[4]) {
         const u32 mnl = fn_eq(x, 0x0A0A0A0Au) | fn_eq(x, 0x0D0D0D0Du);
         const u32 mgt = fn_eq(x, 0x3E3E3E3Eu);
         m.cx |= fn_movemask((fn_lt21(x) & ~mnl) | fn_eq(x, 0x2A2A2A2Au)) << (4 * q);
-        m.hi |= x & 0x80808080u;
+        m.hi |= fn_movemask(x & 0x80808080u) << (4 * q);
         m.nl |= fn_movemask(mnl) << (4 * q);
         m.gt |= fn_movemask(mgt) << (4 * q);
         if (!CODES) continue;
@@ -96,7 +96,7 @@ __device__ __forceinline__ FnEmit fn_emit_masks(const FnMasks& m, u32 state) {
     e.hs = hs;
     e.emit = e.keep | hs;
     e.bad = hs | (e.keep & ~m.acgt);
-    e.cx = (m.cx & ~hdr) | m.hi;
+    e.cx = (m.cx | m.hi) & ~hdr;
     return e;
 }
 

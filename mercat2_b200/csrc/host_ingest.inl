@@ -175,6 +175,43 @@ static void sample_add(mc2_sample* s, const void* text, u64 nbytes, int space, u
 
 #include "filestream.inl"
 
+// Literal rows added with mc2_sample_add_rows (tables counted elsewhere) that the sample's packed alphabet can express
+// are the same k-mers as its packed rows / dense bins: move them there so that equal k-mers are summed.
+static void fold_added_rows(mc2_sample* s) {
+    mc2_engine* e = s->e;
+    const int enc = s->plan.enc;
+    if (enc < 0 || (s->plan.path != PATH_DENSE && s->plan.path != PATH_SPARSE) || s->k * enc_bits(enc) > 64) return;
+    for (auto& part : s->wide) {
+        if (!part.added || !part.n) continue;
+        const u64 n = part.n;
+        DBuf<u32> flag(e, n);
+        DBuf<u64> pos(e, n);
+        DBuf<ull> total(e, 1);
+        LAUNCH(e, rows_flag_kernel, (unsigned)div_up(n, 256), 256, 0, (const u8*)part.rows.p, n, s->k, enc, flag.p);
+        dev_exclusive_scan<u32, u64>(e, flag.p, pos.p, n, total.p);
+        const u64 nf = (u64)read_scalar<ull>(e, total.p);
+        if (!nf) continue;
+        const bool dense = s->plan.path == PATH_DENSE;
+        FastPart fp;
+        if (!dense) {
+            fp.n = nf;
+            fp.sorted = false;
+            fp.keys.alloc(e, nf);
+            fp.counts.alloc(e, nf);
+        }
+        WidePart rest;
+        rest.n = n - nf;
+        rest.sorted = false;
+        rest.rows.alloc(e, std::max<u64>(1, rest.n * (u64)s->k));
+        rest.counts.alloc(e, std::max<u64>(1, rest.n));
+        LAUNCH(e, rows_split_kernel, (unsigned)div_up(n, 256), 256, 0, (const u8*)part.rows.p, (const u64*)part.counts.p, n, s->k, enc,
+               (const u32*)flag.p, (const u64*)pos.p, fp.keys.p, fp.counts.p, dense ? (unsigned long long*)s->dense_sample.p : nullptr,
+               rest.rows.p, rest.counts.p);
+        if (!dense) s->fast.push_back(std::move(fp));
+        part = std::move(rest);
+    }
+}
+
 static mc2_table* sample_finish(mc2_sample* s) {
     mc2_engine* e = s->e;
     PhaseTimer pt(e);
@@ -182,6 +219,7 @@ static mc2_table* sample_finish(mc2_sample* s) {
     t->e = e;
     t->k = s->k;
     t->enc = s->plan.enc < 0 ? ENC_NT2 : s->plan.enc;
+    fold_added_rows(s);
     if (s->plan.path == PATH_DENSE) {
         const u32 bins = s->plan.bins;
         const u64 ntiles = div_up(bins, 256);

@@ -249,6 +249,7 @@ struct WidePart {          // unique k-byte rows
     DBuf<u64> counts;
     u64 n = 0;
     bool sorted = true;
+    bool added = false;    // rows handed in by mc2_sample_add_rows: may duplicate k-mers the packed rows hold (see fold_added_rows)
 };
 
 enum : int { PATH_UNSET = 0, PATH_DENSE = 1, PATH_SPARSE = 2, PATH_WIDE = 3 };
@@ -516,6 +517,7 @@ int mc2_sample_add_rows(mc2_sample* s, const char* kmers, const uint64_t* counts
         WidePart part;
         part.n = rows;
         part.sorted = false;
+        part.added = true;
         part.rows.alloc(e, rows * (u64)s->k);
         part.counts.alloc(e, rows);
         CUDA_CHECK(cudaMemcpyAsync(part.rows.p, kmers, rows * (u64)s->k, cudaMemcpyHostToDevice, e->stream));

@@ -32,7 +32,7 @@ struct ParseStats {
     ull n_upper;    // emitted symbols in 'A'..'Z'
     ull n_ascii;    // all emitted non-separator symbols
     ull n_sep;      // separators emitted
-    ull n_bad;      // bytes >= 0x80 seen anywhere in the text (unsupported -> error)
+    ull n_bad;      // bytes >= 0x80 that would become symbols (anywhere outside header lines: unsupported -> error)
     ull n_sym;      // total bytes of `sym` (set by the offsets scan)
 };
 
@@ -100,13 +100,16 @@ __device__ __forceinline__ void load16(const ParseTileView& v, u64 p0, u32 w[4])
 __device__ __forceinline__ u32 byte_of(const u32 w[4], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
 
 // classes of 16 bytes packed 4 bits each; also the thread's forward and reverse summaries
-__device__ __forceinline__ u64 classify16(const u32 w[4], u32& fwd, u32& rev, u32& nbad) {
+// (badmask: bit i = byte i is >= 0x80; such a byte acts like any other non-blank byte in the line automaton.  Inside a
+// header line it is dropped with the rest of the header -- the reference decodes UTF-8 there and never looks at it
+// (lib/mercat2_kmers.py:52) -- anywhere else it would become a symbol and the text is rejected.)
+__device__ __forceinline__ u64 classify16(const u32 w[4], u32& fwd, u32& rev, u32& badmask) {
     u64 cls = 0;
     u32 e = ST_S0, hn = 0, r = R_NONE, bad = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         u32 c = byte_class(byte_of(w, i));
-        if (c == CL_BAD) { bad++; c = CL_X; }
+        if (c == CL_BAD) { bad |= 1u << i; c = CL_X; }
         cls |= (u64)c << (4 * i);
         if (c == CL_NL) { e = ST_S0; hn = 4u; }
         else if (e == ST_S0 && c != CL_W) e = (c == CL_GT) ? ST_H : ST_Q;
@@ -114,7 +117,7 @@ __device__ __forceinline__ u64 classify16(const u32 w[4], u32& fwd, u32& rev, u3
     }
     fwd = e | hn;
     rev = r;
-    nbad = bad;
+    badmask = bad;
     return cls;
 }
 
@@ -163,14 +166,13 @@ parse_summarize_kernel(const u8* __restrict__ text, u64 len, u8* __restrict__ ti
     const u32 first_lane = nn ? (u32)(__ffs(nn) - 1) : 0u;
     const u32 wf = __shfl_sync(0xffffffffu, rev, first_lane);
     if (lane == 0) sm2[warp] = nn ? wf : R_NONE;
-    const u32 anybad = block_count(nbad != 0);
+    BLOCK_SYNC();
     if (threadIdx.x == 0) {
         u32 r = R_NONE;
         for (int i = 0; i < PARSE_WARPS; ++i) if (sm2[i] != R_NONE) { r = sm2[i]; break; }
         tile_fwd[blockIdx.x] = (u8)total;
         tile_rev[blockIdx.x] = (u8)r;
     }
-    if (anybad && nbad) atomicAdd(&stats->n_bad, (ull)nbad);
 }
 
 // ---- K1b: grid-level scans of the tile summaries (single CTA) ------------------------------------
@@ -236,7 +238,7 @@ parse_emit_kernel(const u8* __restrict__ text, u64 len, const u8* __restrict__ t
     }
     // forward pass: emit
     u64 out_lo = 0, out_hi = 0;
-    u32 cnt = 0, n_acgt = 0, n_upper = 0, n_sep = 0;
+    u32 cnt = 0, n_acgt = 0, n_upper = 0, n_sep = 0, n_hi = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const u32 c = (u32)(cls >> (4 * i)) & 15u;
@@ -250,6 +252,7 @@ parse_emit_kernel(const u8* __restrict__ text, u64 len, const u8* __restrict__ t
             emit = (c == CL_X) || (c == CL_GT) || (c == CL_W && !((trail >> i) & 1u));
         }
         if (emit) {
+            if ((nbad >> i) & 1u) n_hi++;                      // a byte >= 0x80 outside a header line
             if (b != MC2_SEP) {
                 if (toupper && b >= 'a' && b <= 'z') b -= 32;
                 n_upper += (b >= 'A' && b <= 'Z');
@@ -268,6 +271,7 @@ parse_emit_kernel(const u8* __restrict__ text, u64 len, const u8* __restrict__ t
         block_exclusive_scan<OpAdd, PARSE_WARPS>(n_acgt, sm, &t_acgt);
         block_exclusive_scan<OpAdd, PARSE_WARPS>(n_upper, sm, &t_upper);
         block_exclusive_scan<OpAdd, PARSE_WARPS>(n_sep, sm, &t_sep);
+        if (n_hi) atomicAdd(&stats->n_bad, (ull)n_hi);
         if (threadIdx.x == 0 && total) {
             atomicAdd(&stats->n_acgt, (ull)t_acgt);
             atomicAdd(&stats->n_upper, (ull)t_upper);

@@ -16,7 +16,8 @@
 // 16 symbols) and is monotone in the key:
 //     b1 = lut[(p - base) >> sh]                 RP_LUT entries, built from a sampled prefix histogram so that
 //                                                level-1 buckets hold equal shares of the sample (rp_plan_kernel)
-//     b2 = min(127, (p - l1[b1].x) >> l1[b1].y)  linear inside the bucket
+//     b2 = ((p - l1[b1].x) * l1[b1].y) >> 32     linear inside the bucket: .y = 2^39 / (prefixes the bucket spans), so
+//                                                the 128 sub-buckets tile the bucket's range exactly
 // Offsets are exact (a histogram pass over all keys), so skew can never overflow memory; it only makes sub-buckets
 // uneven.  A sub-bucket whose repeated keys do not fit the table is listed and redone by the sort path.
 //
@@ -45,7 +46,7 @@
 // One level of the partition as the kernels see it (all pointers: device memory).
 struct RpView {
     const u16* lut;        // RP_LUT entries
-    const uint2* l1;       // nb1 entries: .x = first prefix of the bucket, .y = shift of its linear sub-buckets
+    const uint2* l1;       // nb1 entries: .x = first prefix of the bucket, .y = scale of its linear sub-buckets (2^39 / span)
     u32 base, sh, nb1;
     u32 down, up;          // prefix of a right-aligned key of kb bits: (u32)(key >> down) << up   (kb >= 32: down = kb - 32)
 };
@@ -89,7 +90,10 @@ __device__ __forceinline__ void rp_load_shared(const RpView& r, RpShared& s, boo
         for (u32 i = threadIdx.x; i < r.nb1; i += blockDim.x) s.l1[i] = r.l1[i];
 }
 __device__ __forceinline__ u32 rp_b1(const RpShared& s, const RpView& r, u32 p) { return s.lut[rp_lut_index(p, r.base, r.sh)]; }
-__device__ __forceinline__ u32 rp_b2(uint2 d, u32 p) { return min((p - d.x) >> d.y, HC_NB2 - 1u); }
+// (< 128 by construction of .y for every prefix of the bucket; the clamp only guards a caller that passed wrong bounds)
+__device__ __forceinline__ u32 rp_b2(uint2 d, u32 p) { return min(__umulhi(p - d.x, d.y), HC_NB2 - 1u); }
+// ordering digit inside a sub-bucket: the next RC_FINE_LOG2 bits of the same product (monotone in p within the sub-bucket)
+__device__ __forceinline__ u32 rp_fine(uint2 d, u32 p, u32 bits) { return (u32)(((u64)(p - d.x) * d.y) >> (32 - bits)) & ((1u << bits) - 1u); }
 __device__ __forceinline__ u32 rp_sub(const RpShared& s, const RpView& r, u32 p) {
     const u32 b1 = rp_b1(s, r, p);
     return b1 * HC_NB2 + rp_b2(s.l1[b1], p);
@@ -132,9 +136,9 @@ rp_plan_kernel(const u32* __restrict__ shist, u32 nb1, u32 base, u32 sh, u32 nid
     for (u32 b = threadIdx.x; b < nb1; b += 1024) {
         const u64 lo = (u64)base + ((u64)first[b] << sh);
         const u64 span = (u64)(first[b + 1] - first[b]) << sh;             // prefix values the bucket covers
-        u32 s2 = 0;
-        while (span && ((span - 1) >> s2) >= HC_NB2) ++s2;
-        l1[b] = make_uint2((u32)min(lo, (u64)0xFFFFFFFFull), s2);
+        // x in [0, span)  ->  (x * scale) >> 32 in [0, 128): scale = floor(2^39 / span)   (tiny spans: one prefix per sub-bucket)
+        const u64 scale = span >= HC_NB2 ? min((u64)0xFFFFFFFFull, (u64)((1ull << (32 + HC_NB2_LOG2)) / span)) : 0xFFFFFFFFull;
+        l1[b] = make_uint2((u32)min(lo, (u64)0xFFFFFFFFull), (u32)scale);
     }
 }
 
@@ -446,7 +450,8 @@ hc_scatter2_kernel(const u64* __restrict__ keys1, const u32* __restrict__ sub_ba
 #define RC_PREFETCH 8
 #define RC_ROUND (RC_PREFETCH * RC_THREADS)
 #define RC_FLIST 1024u                           // flagged keys queued per round before the dense insert step
-#define RC_FINE 1024u                            // ordering bins
+#define RC_FINE_LOG2 10
+#define RC_FINE (1u << RC_FINE_LOG2)             // ordering bins
 #define RC_STAGE_ROWS RC_CLAIM_CAP
 // region A: bitmap (pass 1) | staged survivors (keys 8 B + counts 4 B); region B: flagged-key queue | ordering bins
 #define RC_A_BYTES ((size_t)RC_STAGE_ROWS * 12 > (size_t)RC_BM_WORDS * 4 ? (size_t)RC_STAGE_ROWS * 12 : (size_t)RC_BM_WORDS * 4)
@@ -614,11 +619,8 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         // ---- ordered emit ----
         const u32 n_empty = exact ? scal[4] : 0u;
         const bool emit = exact && !ovf;                          // (block-uniform)
-        const u32 b1 = b >> HC_NB2_LOG2, b2 = b & (HC_NB2 - 1u);
-        const uint2 d1 = r.l1[b1];
-        const u32 p_lo = d1.x + (b2 << d1.y);
-        const u32 dsh = d1.y > 10u ? d1.y - 10u : 0u;             // RC_FINE = 2^10 bins over the sub-bucket's 2^d1.y prefixes
-        auto fine = [&](ull key) { return min((rp_prefix(key, r.down, r.up) - p_lo) >> dsh, RC_FINE - 1u); };
+        const uint2 d1 = r.l1[b >> HC_NB2_LOG2];
+        auto fine = [&](ull key) { return rp_fine(d1, rp_prefix(key, r.down, r.up), RC_FINE_LOG2); };
         u32 nsurv = 0;
         if (emit && nd) {
             for (u32 i = threadIdx.x; i < RC_FINE; i += RC_THREADS) bins[i] = 0;      // (the queue of pass 1 lived here)

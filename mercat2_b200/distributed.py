@@ -259,11 +259,13 @@ def reduce_dense_sample(engine, sample, dist, device, root: int = 0) -> bool:
         return False
     if any(m[0] == 0 and m[1] >= 0 for m in metas):          # some rank counted its pieces on a non-dense path
         return False
+    mismatch = False
     if bins == 0:                                   # this rank saw no text: contribute zeros
         sample.dense_plan(dense[0][1])
         ptr, bins, enc = sample.dense()
-        if bins != dense[0][0]:
-            raise RuntimeError("dense plan mismatch between ranks")
+        mismatch = bins != dense[0][0]
+    if any(_agree(dist, mismatch)):                 # (decided together: no rank may leave before the collective)
+        raise RuntimeError("dense plan mismatch between ranks")
     if dist.get_world_size() > 1:
         t = _to_tensor(engine, ptr, bins, device)                 # a view: NCCL reduces the engine's table in place
         dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
@@ -301,9 +303,17 @@ def count_sample_sharded(engine, pieces, k: int, min_count: int, dist, device, o
     """One sample whose pieces (FASTA texts, each filtered on its own like a chunk file) are spread over the ranks:
     count the local pieces, merge across GPUs on the device, optionally write the TSV.  Returns the rank's table part
     (sparse: its key range; dense: the full table on rank 0, None elsewhere)."""
-    sample = engine.sample(k, min_count)
-    for text in pieces:
-        sample.add_text(text, chunk_bytes)
+    # every rank picks the sample's encoding (and with it dense / sparse / literal counting) from its OWN first piece;
+    # soft-masked or N-rich stretches could make ranks disagree, so the decision is taken once for all ranks from the
+    # summed alphabet statistics of every rank's first piece and forced on the engine while the sample is counted
+    enc = agree_encoding(pieces[0] if len(pieces) else b"", dist)
+    engine.set_option("force_encoding", enc)
+    try:
+        sample = engine.sample(k, min_count)
+        for text in pieces:
+            sample.add_text(text, chunk_bytes)
+    finally:
+        engine.set_option("force_encoding", -1)
     if reduce_dense_sample(engine, sample, dist, device):
         # rank 0 now holds the summed dense table; the literal-byte rows (windows outside the alphabet) of the other
         # ranks are few and follow through the object collective
@@ -340,6 +350,27 @@ def count_sample_sharded(engine, pieces, k: int, min_count: int, dist, device, o
 # =====================================================================================================
 # One piece split across GPUs before the filter (SURVEY.md 8e grain 3)
 # =====================================================================================================
+def alphabet_stats(text, limit: int = 1 << 20) -> tuple:
+    """(sequence bytes, of them ACGT, of them 'A'..'Z') over the first `limit` bytes of a FASTA text (header lines
+    skipped) -- the statistics the engine's own plan uses (csrc/host_reduce.inl make_plan)."""
+    if hasattr(text, "is_cuda"):
+        text = bytes(text[:limit].cpu().numpy().tobytes())
+    head = bytes(memoryview(text)[:limit]) if not isinstance(text, (bytes, bytearray)) else bytes(text[:limit])
+    body = b"".join(line for line in head.splitlines() if not line.lstrip().startswith(b">"))
+    a = np.frombuffer(body.replace(b"*", b""), dtype=np.uint8)
+    counts = np.bincount(a, minlength=256)
+    return int(len(a)), int(counts[[65, 67, 71, 84]].sum()), int(counts[65:91].sum())
+
+
+def agree_encoding(first_piece, dist) -> int:
+    """One encoding for all ranks (0 = 2-bit ACGT, 1 = 5-bit A-Z, 2 = byte), by the engine's rule on the summed statistics."""
+    stats = _agree(dist, alphabet_stats(first_piece))
+    n, acgt, upper = (sum(s[i] for s in stats) for i in range(3))
+    if n == 0 or acgt * 10 >= n * 9:
+        return ENC_NT2
+    return ENC_AA5 if upper * 2 >= n else ENC_BYTE
+
+
 def split_at_headers(text: bytes, world: int) -> list:
     """Cut one FASTA text into `world` byte ranges of similar size, each starting at a header line (so that no
     window crosses a cut).  Host helper for callers that hold the whole text; ranks that read their own byte range
@@ -348,7 +379,10 @@ def split_at_headers(text: bytes, world: int) -> list:
     cuts = [0]
     for r in range(1, world):
         at = max(cuts[-1], (n * r) // world)
-        pos = 0 if at == 0 else text.find(b"\n>", at - 1)
+        if at == 0:                                  # (tiny text: nothing to cut before the first byte)
+            cuts.append(0)
+            continue
+        pos = text.find(b"\n>", at - 1)
         cuts.append(n if pos < 0 else pos + 1)
     cuts.append(n)
     return [text[cuts[i]:cuts[i + 1]] for i in range(world)]

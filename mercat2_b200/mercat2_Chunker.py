@@ -10,37 +10,30 @@ from __future__ import annotations
 
 import glob
 import os
+import re
 from pathlib import Path
 
 from . import _native
 from .mercat2_kmers import read_text_bytes
 
-_UNITS = {
-    "customary": ("B", "K", "M", "G", "T", "P", "E", "Z", "Y"),
-    "customary_ext": ("byte", "kilo", "mega", "giga", "tera", "peta", "exa", "zetta", "iotta"),
-    "iec": ("Bi", "Ki", "Mi", "Gi", "Ti", "Pi", "Ei", "Zi", "Yi"),
-    "iec_ext": ("byte", "kibi", "mebi", "gibi", "tebi", "pebi", "exbi", "zebi", "yobi"),
-}
+# unit spelling -> power of 1024 (the four symbol families of lib/mercat2_Chunker.py:110-117, plus 'k' as an alias of 'K')
+_POWER = {unit: power
+          for family in ("B K M G T P E Z Y", "byte kilo mega giga tera peta exa zetta iotta",
+                         "Bi Ki Mi Gi Ti Pi Ei Zi Yi", "byte kibi mebi gibi tebi pebi exbi zebi yobi")
+          for power, unit in enumerate(family.split())}
+_POWER["k"] = 1
+_SIZE = re.compile(r"([0-9.]*)(.*)", re.DOTALL)
 
 
 def human2bytes(s: str) -> int:
-    """'100M' -> 104857600, '0.5kilo' -> 512, '1 Gi' -> 2**30 (lib/mercat2_Chunker.py:82-139);
-    raises ValueError for an unknown unit."""
-    text = s
-    digits = ""
-    while text and text[0:1].isdigit() or text[0:1] == ".":
-        digits += text[0]
-        text = text[1:]
-    number = float(digits)
-    unit = text.strip()
-    for symbols in _UNITS.values():
-        if unit in symbols:
-            break
-    else:
-        if unit != "k":
-            raise ValueError("can't interpret %r" % s)
-        symbols, unit = _UNITS["customary"], "K"
-    return int(number * (1 << (10 * symbols.index(unit))))
+    """'100M' -> 104857600, '0.5kilo' -> 512, '1 Gi' -> 2**30: a leading run of digits and dots, then a unit
+    (same grammar and errors as lib/mercat2_Chunker.py:82-139: ValueError for a malformed number or an unknown unit)."""
+    number, unit = _SIZE.fullmatch(s).groups()
+    value = float(number)
+    try:
+        return int(value * (1 << (10 * _POWER[unit.strip()])))
+    except KeyError:
+        raise ValueError("can't interpret %r" % s) from None
 
 
 def piece_name(path, index: int) -> str:

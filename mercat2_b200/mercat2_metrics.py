@@ -60,7 +60,7 @@ def file_metrics_text(data: bytes, engine=None):
     rows = {}
     for i in range(len(res["length"])):
         off, ln = int(res["header_off"][i]), int(res["header_len"][i])
-        name = data[off:off + ln].decode("ascii")
+        name = data[off:off + ln].decode("utf-8", errors="replace")      # headers may carry UTF-8 (the reference reads text)
         status = int(res["status"][i])
         if status == 2:
             raise KeyError(name)

@@ -90,6 +90,8 @@ EDGE_TEXTS = {
     "multi_line_wrapped": (">g\n" + "\n".join(["ACGTTGCA" * 10] * 7 + ["ACG"]) + "\n", [(5, 1), (12, 2), (31, 1)]),
     "header_with_gt_in_desc": (">r1 a>b >c\nACGT\n>r2 >\nACGT\n", [(4, 1)]),
     "line_is_only_stars": (">p\nAB\n***\nCD\n", [(2, 1), (4, 1)]),
+    # header lines may carry any UTF-8 text (the reference reads text mode and drops them, lib/mercat2_kmers.py:52)
+    "utf8_in_header": (">r1 \u03b2-lactamase \u00b5 na\u00efve\nACGTACGT\n>r2 \u2603\nACGA\nTT\n", [(3, 1), (4, 1)]),
 }
 
 
@@ -98,7 +100,7 @@ def build_edge_cases(ref):
     with tempfile.TemporaryDirectory() as tmp:
         for name, (text, ks) in EDGE_TEXTS.items():
             path = Path(tmp, name + ".fa")
-            with open(path, "w", newline="") as out:      # keep \r bytes as written
+            with open(path, "w", newline="", encoding="utf-8") as out:      # keep \r bytes as written
                 out.write(text)
             for k, c in ks:
                 expected = ref["mercat2_kmers"].find_kmers(path, k, c)

@@ -925,3 +925,28 @@ def test_oversized_buckets_take_rounds(engine):
                     assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c), (c, bucket_keys, mode, rep)
             finally:
                 reset(engine)
+
+
+def test_add_rows_sums_with_counted_text(engine):
+    """mc2_sample_add_rows on a sample that also counted text itself (the dict merge of bin/mercat2.py:121-127 for a
+    table counted on another rank): a k-mer present on both sides must come out as ONE summed row -- on the sparse,
+    the dense (nucleotide and protein) and the literal-byte paths, rows added before or after the text"""
+    reset(engine)
+    text = synth_reads(3000, 150, seed=77, n_rate=0.003, lower_rate=0.02, genome_len=40000)
+    reads = [b">" + r for r in text.split(b">") if r]
+    halves = [b"".join(reads[0::2]), b"".join(reads[1::2])]
+    prot = (b">p1\nMKVLAAGIVGLLLAQWERTYIPASDFGHKLCVNMX*\n>p2\nMKVLAAGIVBZUOMKVLAAG*\n" * 40, b">q\nMKVLAAGIVGLLWERTYIPASMKVLAAGXB*\n" * 30)
+    for data, k, c in ((halves, 21, 2), (halves, 4, 5), (halves, 33, 2), (halves, 12, 1), (prot, 3, 2), (prot, 6, 1)):
+        want = orc.merge_counts(orc.find_kmers_text(h.decode(), k, c) for h in data)
+        other = engine.count_text(data[1], k, c)
+        ok, oc = other.arrays()
+        other.close()
+        for rows_first in (False, True):
+            sample = engine.sample(k, c)
+            if rows_first:
+                sample.add_rows(ok, oc)
+            sample.add_text(data[0])
+            if not rows_first:
+                sample.add_rows(ok, oc)
+            got = sample.finish().to_dict()
+            assert got == want, f"k={k} c={c} rows_first={rows_first}: {diff_msg(got, want)}"
