@@ -200,6 +200,12 @@ int mc2_matrix_k(const mc2_matrix* m);
 int mc2_matrix_export(mc2_matrix* m, char* kmers, uint64_t* counts);
 int mc2_matrix_write_tsv(mc2_matrix* m, const char* path, const char* corner, const char* const* names, int transposed);
 void mc2_matrix_free(mc2_matrix* m);
+/* merge_tsv byte for byte as the reference writes it (lib/mercat2_report.py:98-160: a k-way cursor walk whose row label
+ * is the smallest next k-mer among the files that advanced on the previous line -- with differing k-mer sets labels
+ * repeat / appear out of order and some rows are dropped; identical to the sorted union when all samples hold the same
+ * k-mers).  tables in column order, names = column labels, corner = first header cell. */
+int mc2_merge_tables_reference(mc2_engine* e, mc2_table* const* tables, uint32_t n, const char* path, const char* corner,
+                               const char* const* names);
 
 /* ---- protein metrics ----------------------------------------------------------------------------
  * Replaces the numeric part of plot_sample_metrics (lib/mercat2_figures.py:157-183) and

@@ -71,6 +71,7 @@ SYMBOLS = [
     ("mc2_matrix_export", _INT, [_VP, _VP, _VP]),
     ("mc2_matrix_write_tsv", _INT, [_VP, C.c_char_p, C.c_char_p, _VP, _INT]),
     ("mc2_matrix_free", None, [_VP]),
+    ("mc2_merge_tables_reference", _INT, [_VP, _VP, C.c_uint32, C.c_char_p, C.c_char_p, _VP]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -390,6 +391,16 @@ class Engine:
         out = C.c_void_p()
         _check(self._lib, self._lib.mc2_merge_tables(self._h, arr, len(tables), C.byref(out)))
         return Matrix(self, out, len(tables))
+
+    def merge_tables_reference(self, tables, path, corner: str, names):
+        """Write merge_tsv's combined table exactly as the reference does (lib/mercat2_report.py:98-160)."""
+        tables = list(tables)
+        names = [str(n).encode() for n in names]
+        if len(names) != len(tables):
+            raise ValueError("one name per table")
+        arr = (C.c_void_p * len(tables))(*[t._h for t in tables])
+        narr = (C.c_char_p * len(names))(*names)
+        _check(self._lib, self._lib.mc2_merge_tables_reference(self._h, arr, len(tables), os.fsencode(str(path)), corner.encode(), narr))
 
     def partition_keys(self, data, k: int, groups: int) -> "Keys":
         """Order-preserving 64-bit keys of every window of a plain nucleotide FASTA text, grouped into `groups`

@@ -51,13 +51,17 @@ struct KeySpan {               // keys already extracted (one level-0 group of a
     u64 p_lo, p_hi;            // the keys' 32-bit prefixes lie in [p_lo, p_hi)   (p_hi <= 2^32)
 };
 
-// One level of the range partition on the device (rangecount.cuh): LUT + level-1 descriptors.
+// One level of the range partition on the device (rangecount.cuh): LUT + level-1 descriptors (workspace memory).
 struct RpPlan {
-    DBuf<u16> lut;
-    DBuf<uint2> l1;
+    u16* lut = nullptr;
+    uint2* l1 = nullptr;
     u32 base = 0, sh = 0, nb1 = 1, nidx = 1, down = 0, up = 0;
-    RpView view() const { return RpView{lut.p, l1.p, base, sh, nb1, down, up}; }
+    RpView view() const { return RpView{lut, l1, base, sh, nb1, down, up}; }
 };
+static RangeWork& range_work(mc2_engine* e) {
+    if (!e->work) e->work = new RangeWork;
+    return *e->work;
+}
 static void plan_geometry(RpPlan& pl, int kb, u32 nb1, u64 p_lo, u64 p_hi) {
     pl.nb1 = nb1;
     pl.down = kb >= 32 ? (u32)(kb - 32) : 0u;
@@ -100,14 +104,15 @@ static void range_kernel_attrs(mc2_engine* e) {
 // sampled prefix histogram of the source (packed streams, a key array, or a byte-symbol stream) -> plan tables
 template <int ENC>
 static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, SymView v, u64 cap, RpPlan& pl,
-                       const u32* shist_given = nullptr) {
-    pl.lut.alloc(e, RP_LUT);
-    pl.l1.alloc(e, pl.nb1);
-    DBuf<u32> shist;
+                       int level, const u32* shist_given = nullptr) {
+    RangeWork& w = range_work(e);
+    pl.lut = w.lut[level].get(e, RP_LUT);
+    pl.l1 = w.l1[level].get(e, HC_MAX_NB1);
+    struct { u32* p; } shist{nullptr};
     const u32* sh_p = shist_given;
     if (!sh_p) {
-        shist.alloc(e, RP_LUT);
-        shist.zero();
+        shist.p = w.shist.get(e, RP_LUT);
+        CUDA_CHECK(cudaMemsetAsync(shist.p, 0, RP_LUT * 4, e->stream));
         if (ks) {
             const u64 stride = std::max<u64>(1, ks->n / RP_SAMPLE_WINDOWS);
             const u64 grid = std::min<u64>(div_up(div_up(ks->n, stride), HK_HIST_THREADS), (u64)e->num_sms * 2);
@@ -128,7 +133,7 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
         }
         sh_p = shist.p;
     }
-    LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.lut.p, pl.l1.p);
+    LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.lut, pl.l1);
 }
 
 // keys one two-level partition can take (beyond it: level-0 partition first)
@@ -160,14 +165,16 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     plan_geometry(pl, kb, nb1, ks ? ks->p_lo : 0, ks ? ks->p_hi : (1ull << 32));
     std::vector<PackedView> pvs;
     if (pv) pvs.push_back(*pv);
-    build_plan<ENC>(e, k, pvs, ks, v, cap, pl);
+    build_plan<ENC>(e, k, pvs, ks, v, cap, pl, 1);
     const RpView rv = pl.view();
     struct Tail { ull total, rows; u32 ovf_n, pad; };
     // (the bucket histogram and the result counters share one allocation: one memset per chunk instead of two)
-    DBuf<u32> ghist(e, nb + sizeof(Tail) / 4), sub_base(e, nb + 1), cur1(e, nb1), cur2(e, nb), tile_pref(e, nb1 + 1), ovf_list(e, nb), rows(e, nb);
-    DBuf<u64> row_off(e, nb);
+    RangeWork& w = range_work(e);
+    struct { u32* p; } ghist{w.ghist.get(e, nb + sizeof(Tail) / 4)}, sub_base{w.sub_base.get(e, nb + 1)}, cur1{w.cur1.get(e, nb1)}, cur2{w.cur2.get(e, nb)},
+        tile_pref{w.tile_pref.get(e, nb1 + 1)}, ovf_list{w.ovf_list.get(e, nb)}, rows{w.rows.get(e, nb)};
+    struct { u64* p; } row_off{w.row_off.get(e, nb)};
     struct { Tail* p; } tail{reinterpret_cast<Tail*>(ghist.p + nb)};       // nb is a multiple of 128: 8-byte aligned
-    ghist.zero();
+    CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)nb * 4 + sizeof(Tail), e->stream));
     const size_t hist_smem = sizeof(RpShared) + (size_t)nb * 4;
     if (ks) {
         const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms);
@@ -186,10 +193,9 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     LAUNCH(e, hc_scan_kernel, 1, 1024, (size_t)nb * 4, (const u32*)ghist.p, nb, nb1, (u32)HC_NB2, sub_base.p, cur1.p, cur2.p, tile_pref.p, &tail.p->total);
     // keys1 also serves as the survivors' slot array (16-byte rows at slot sub_base[b] / c) once scatter 2 has read it:
     // for c >= 2 the slots of cap keys need 16 * (cap / c + 1) <= 8 * cap + 16 bytes
-    DBuf<u64> keys1(e, cap + 8), keys2(e, cap);
-    DBuf<RcRow> slots1;
+    struct { u64* p; } keys1{w.keys1.get(e, cap + 8)}, keys2{w.keys2.get(e, cap)};
     RcRow* slots = reinterpret_cast<RcRow*>(keys1.p);
-    if (c < 2) { slots1.alloc(e, cap + 2); slots = slots1.p; }
+    if (c < 2) slots = reinterpret_cast<RcRow*>(w.slots1.get(e, (cap + 2) * sizeof(RcRow)));
     const bool dbg = getenv("MC2_DEBUG_HASH") != nullptr;
     if (dbg) {
         CUDA_CHECK(cudaMemsetAsync(keys1.p, 0xEE, cap * 8, e->stream));
@@ -526,7 +532,7 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     RpPlan pl;
     const u64 p_lo = ks ? ks->p_lo : 0, p_hi = ks ? ks->p_hi : (1ull << 32);
     plan_geometry(pl, 2 * k, g0, p_lo, p_hi);
-    build_plan<ENC_NT2>(e, k, pvs, ks, SymView{nullptr, 0}, cap, pl, shist_given);
+    build_plan<ENC_NT2>(e, k, pvs, ks, SymView{nullptr, 0}, cap, pl, 0, shist_given);
     const RpView rv = pl.view();
     DBuf<u32> ghist(e, g0);
     ghist.zero();
@@ -544,7 +550,7 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     std::vector<u32> h(g0);
     std::vector<uint2> l1(g0);
     d2h(e, h.data(), (const u32*)ghist.p, g0);
-    d2h(e, l1.data(), (const uint2*)pl.l1.p, g0);
+    d2h(e, l1.data(), (const uint2*)pl.l1, g0);
     pt.mark("level-0 histogram");
     out.gbase.assign(g0 + 1, 0);
     out.bounds.assign(g0 + 1, p_hi);

@@ -27,8 +27,10 @@ static thread_local std::string g_err;
 // =====================================================================================================
 // engine
 // =====================================================================================================
+struct RangeWork;
 struct mc2_engine {
     int device = 0;
+    RangeWork* work = nullptr;             // device workspace of the range-partition path, grown on demand and reused by every chunk
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int num_sms = 148;
@@ -147,6 +149,27 @@ struct DBuf {
         n = 0;
     }
     ~DBuf() { release(); }
+};
+
+// grow-only device buffer: get(n) returns room for n elements, reallocating (with head room) only when it must
+template <typename T>
+struct WBuf {
+    DBuf<T> b;
+    T* get(mc2_engine* e, u64 n) {
+        if (!b.p || b.n < n) b.alloc(e, n + n / 16 + 64);
+        return b.p;
+    }
+};
+// Workspace of one range-partitioned chunk / group (rangecount.cuh).  Chunks of a sample and groups of a very large
+// chunk follow each other on one stream and differ a little in size; allocating their buffers afresh each time made
+// the stream-ordered pool grow and fragment (a freed 536 MB block does not serve a 540 MB request) and cost more host
+// time than the kernels took.  One set of buffers, sized for the largest request so far, serves them all.
+struct RangeWork {
+    WBuf<u64> keys1, keys2, row_off;
+    WBuf<u32> ghist, sub_base, cur1, cur2, tile_pref, ovf_list, rows, shist;
+    WBuf<u8> slots1;                       // RcRow slots when min_count == 1 (otherwise the slots overlay keys1)
+    WBuf<u16> lut[2];                      // level-0 plan and group / chunk plan are alive at the same time
+    WBuf<uint2> l1[2];
 };
 
 template <typename T>
@@ -393,6 +416,7 @@ void mc2_engine_destroy(mc2_engine* e) {
     if (e->pin_small) cudaFreeHost(e->pin_small);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e->work;
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -1067,6 +1091,73 @@ int mc2_matrix_write_tsv(mc2_matrix* m, const char* path, const char* corner, co
             else ok = ok && fputc('\n', f) != EOF;
         }
     }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
+    API_END
+}
+
+// merge_tsv exactly as the reference writes it (lib/mercat2_report.py:98-160), for tables still on the device.  The
+// reference walks the per-sample TSVs with one cursor per file; the label of an output line is the smallest NEXT k-mer
+// among the files that advanced on the previous line (all files at the start), a file prints its count and advances
+// when its current k-mer is <= the label and prints 0 otherwise, and the walk ends when no file that advanced has a
+// row left.  With identical k-mer sets this is the sorted union; with differing sets a pending smaller k-mer is
+// printed under a larger label, labels repeat, and rows of files that never advance again are dropped -- downstream
+// consumers of the reference's combined table see exactly that, so this entry point reproduces it byte for byte
+// (the sorted union is mc2_merge_tables + mc2_matrix_write_tsv).  The cursor walk is inherently serial and runs on the
+// host over the tables' exported rows; the device did the parse / count / sort that produced them.
+int mc2_merge_tables_reference(mc2_engine* e, mc2_table* const* tables, uint32_t n, const char* path, const char* corner,
+                               const char* const* names) {
+    API_BEGIN
+    if (!e || !path || !corner || (n && (!tables || !names))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    for (u32 i = 0; i < n; ++i) {
+        if (!tables[i]) throw Mc2Error(MC2_ERR_INVALID, "NULL table");
+        ensure_host(tables[i]);
+        if (tables[i]->counts.empty()) throw Mc2Error(MC2_ERR_INVALID, "merge: a table without rows (the reference fails on a TSV without rows)");
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) throw Mc2Error(MC2_ERR_IO, std::string("cannot open ") + path);
+    std::string buf = corner;
+    for (u32 i = 0; i < n; ++i) { buf += '\t'; buf += names[i]; }
+    buf += '\n';
+    bool ok = true;
+    struct Key { const char* p; size_t len; };
+    auto less = [](const Key& a, const Key& b) {                   // Python str order of ASCII text
+        const int d = memcmp(a.p, b.p, std::min(a.len, b.len));
+        return d < 0 || (d == 0 && a.len < b.len);
+    };
+    auto key_of = [&](u32 i, u64 row) { return Key{tables[i]->kmers.data() + row * (u64)tables[i]->k, (size_t)tables[i]->k}; };
+    std::vector<u64> cur(n, 0);
+    bool have = false;
+    Key label{nullptr, 0};
+    for (u32 i = 0; i < n; ++i) {
+        const Key k0 = key_of(i, 0);
+        if (!have || less(k0, label)) { label = k0; have = true; }
+    }
+    char num[24];
+    while (have) {
+        buf.append(label.p, label.len);
+        bool next_have = false;
+        Key next{nullptr, 0};
+        for (u32 i = 0; i < n; ++i) {
+            const u64 rows = tables[i]->counts.size();
+            if (cur[i] >= rows || less(label, key_of(i, cur[i]))) {
+                buf += "\t0";
+            } else {
+                const int len = snprintf(num, sizeof num, "\t%llu", (ull)tables[i]->counts[cur[i]]);
+                buf.append(num, len);
+                if (++cur[i] < rows) {
+                    const Key k1 = key_of(i, cur[i]);
+                    if (!next_have || less(k1, next)) { next = k1; next_have = true; }
+                }
+            }
+        }
+        buf += '\n';
+        if (buf.size() >= (8u << 20)) { ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+        have = next_have;
+        label = next;
+    }
+    ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
     ok = (fclose(f) == 0) && ok;
     if (!ok) throw Mc2Error(MC2_ERR_IO, std::string("short write to ") + path);
     API_END

@@ -168,9 +168,22 @@ hk_hist_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32 nb, u32* __res
     rp_load_shared(r, rs, FINE);
     for (u32 i = threadIdx.x; i < nb; i += HK_HIST_THREADS) hist[i] = 0;
     BLOCK_SYNC();
-    for (u64 i = (u64)blockIdx.x * HK_HIST_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * HK_HIST_THREADS) {
+    // four independent loads in flight per thread (one per iteration left the kernel latency-bound: 0.24 ms per 65 M keys)
+    const u64 stride = (u64)gridDim.x * HK_HIST_THREADS;
+    u64 i = (u64)blockIdx.x * HK_HIST_THREADS + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        u64 kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) kk[j] = keys[i + j * stride];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const u32 p = rp_prefix(kk[j], r.down, r.up);
+            smem_red_inc(&hist[FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)]);
+        }
+    }
+    for (; i < n; i += stride) {
         const u32 p = rp_prefix(keys[i], r.down, r.up);
-        atomicAdd(&hist[FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)], 1u);
+        smem_red_inc(&hist[FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)]);
     }
     BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < nb; b += HK_HIST_THREADS) {
@@ -513,6 +526,24 @@ __device__ __forceinline__ void rc_pass2(ull key, const ull* tkeys, u32* tcnt, u
 
 struct RcRow { ull key, count; };
 
+// MODE 0 insert: no claim log, no distinct counter (the emit pass walks the whole table); a probe sequence that does not
+// end within RC_PROBE_LIMIT slots means the table is (nearly) full: the bucket is flagged and redone by sorting.
+#define RC_PROBE_LIMIT 512u
+__device__ __forceinline__ void rc_insert0(ull key, ull* tkeys, u32* tcnt, u32* scal) {
+    u32 p = rc_slot(rc_hash(key));
+#pragma unroll 1
+    for (u32 probes = 0; probes < RC_PROBE_LIMIT; ++probes) {
+        ull cur = tkeys[p];
+        if (cur == HC_EMPTY) {
+            cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+            if (cur == HC_EMPTY) cur = key;
+        }
+        if (cur == key) { smem_red_inc(&tcnt[p]); return; }
+        p = (p + 1) & (RC_SLOTS - 1);
+    }
+    scal[2] = 1;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(RC_THREADS, 2)
 rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u32 c, RpView r,
@@ -530,6 +561,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
     __shared__ u32 s_warp[RC_THREADS / 32 + 1];
     for (u32 i = threadIdx.x; i < RC_SLOTS; i += RC_THREADS) { tkeys[i] = HC_EMPTY; tcnt[i] = 0; }
     if (MODE == 1) for (u32 i = threadIdx.x; i < RC_BM_WORDS; i += RC_THREADS) bm[i] = 0;
+    if (MODE == 0) for (u32 i = threadIdx.x; i < RC_FINE; i += RC_THREADS) bins[i] = 0;
     if (threadIdx.x < 16) (&s_scal[0][0])[threadIdx.x] = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 need_at = c - 1;                                 // flagged occurrences at which a key may reach min_count
@@ -550,6 +582,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
     for (; b < nb; b += gridDim.x, par ^= 1u) {
         u32* scal = s_scal[par];
         const u32 n = n_n, lo = lo_n;
+        const uint2 d1 = __ldg(&r.l1[b >> HC_NB2_LOG2]);           // (used by the emit pass: fetched here so that its latency is hidden)
         ull kcur[RC_PREFETCH];
 #pragma unroll
         for (int j = 0; j < RC_PREFETCH; ++j) kcur[j] = knext[j];
@@ -574,7 +607,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                     const ull key = rd == 0 ? kcur[j] : keys2[lo + i];
                     if (MODE == 1) rc_pass1(key, bm, tkeys, tcnt, claimed, flist, scal, need_at);
                     else if (key == HC_EMPTY) smem_red_inc(&scal[4]);
-                    else rc_insert(key, rc_hash(key), tkeys, tcnt, claimed, scal);
+                    else rc_insert0(key, tkeys, tcnt, scal);
                 }
             }
             if (MODE == 1) {
@@ -593,14 +626,15 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
             }
         }
         BLOCK_SYNC();
-        const bool ovf = scal[2] != 0;
-        const u32 nd = min(scal[1], (u32)RC_CLAIM_CAP);
+        bool ovf = scal[2] != 0;
+        const u32 nd = MODE == 1 ? min(scal[1], (u32)RC_CLAIM_CAP) : RC_SLOTS;      // table slots the emit pass visits
         bool exact = MODE == 0;
         if (MODE == 1) {
             const bool need2 = !ovf && scal[3];
             // exact counts are needed only if some key may reach min_count: clear the flagged-occurrence counters ...
             if (need2) {
                 for (u32 i = threadIdx.x; i < nd; i += RC_THREADS) tcnt[claimed[i]] = 0;
+                for (u32 i = threadIdx.x; i < RC_FINE; i += RC_THREADS) bins[i] = 0;      // (the queue of pass 1 lived here)
                 BLOCK_SYNC();
                 // ... and pass 2 counts every occurrence of the keys that have a slot
                 for (u32 rd = 0; rd < nrounds; ++rd) {
@@ -615,26 +649,20 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                 exact = true;
             }
         }
-        if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
         // ---- ordered emit ----
-        const u32 n_empty = exact ? scal[4] : 0u;
-        const bool emit = exact && !ovf;                          // (block-uniform)
-        const uint2 d1 = r.l1[b >> HC_NB2_LOG2];
+        // slot visited by step i of the emit loops: MODE 1 walks the claim log, MODE 0 the whole table
+        auto slot_of = [&](u32 i) { return MODE == 1 ? (u32)claimed[i] : i; };
         auto fine = [&](ull key) { return rp_fine(d1, rp_prefix(key, r.down, r.up), RC_FINE_LOG2); };
+        const u32 n_empty = exact ? scal[4] : 0u;
         u32 nsurv = 0;
-        if (emit && nd) {
-            for (u32 i = threadIdx.x; i < RC_FINE; i += RC_THREADS) bins[i] = 0;      // (the queue of pass 1 lived here)
-            BLOCK_SYNC();
-            // A: survivors per ordering bin
+        if (exact && !ovf) {                                       // (block-uniform)
+            // A: survivors per ordering bin (bins are zero here)
             for (u32 i = threadIdx.x; i < nd; i += RC_THREADS) {
-                const u32 p = claimed[i];
-                if (tcnt[p] >= c) { smem_red_inc(&bins[fine(tkeys[p])]); smem_red_inc(&scal[6]); }
+                const u32 p = slot_of(i);
+                if (tcnt[p] >= c) smem_red_inc(&bins[fine(tkeys[p])]);
             }
             BLOCK_SYNC();
-            nsurv = scal[6];
-        }
-        if (nsurv) {                                               // (block-uniform)
-            // exclusive scan of the bins (2 per thread), in place: bins[d] = first staging row of bin d
+            // exclusive scan of the bins (2 per thread), in place: bins[d] = first staging row of bin d; total = survivors
             const u32 c0 = bins[2 * threadIdx.x], c1 = bins[2 * threadIdx.x + 1];
             __syncwarp();
             u32 incl = c0 + c1;
@@ -654,17 +682,24 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
                     if (lane >= d) wi += y;
                 }
                 if (lane < RC_THREADS / 32) s_warp[lane] = wi - w;
+                if (lane == RC_THREADS / 32 - 1) s_warp[RC_THREADS / 32] = wi;
             }
             BLOCK_SYNC();
+            nsurv = s_warp[RC_THREADS / 32];
             const u32 ex = s_warp[warp] + incl - (c0 + c1);
             bins[2 * threadIdx.x] = ex;
             bins[2 * threadIdx.x + 1] = ex + c0;
+            if (nsurv > RC_STAGE_ROWS) { ovf = true; nsurv = 0; }    // (MODE 0, min_count 1, table almost full of distinct keys)
             BLOCK_SYNC();
+        }
+        if (ovf && threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = b;
+        if (nsurv) {                                               // (block-uniform)
             // B: place (after this pass bins[d] = END of bin d); the table slots are released here
             for (u32 i = threadIdx.x; i < nd; i += RC_THREADS) {
-                const u32 p = claimed[i];
-                const ull key = tkeys[p];
+                const u32 p = slot_of(i);
                 const u32 cnt = tcnt[p];
+                if (MODE == 0 && cnt == 0) continue;              // (an empty slot of the table)
+                const ull key = tkeys[p];
                 tkeys[p] = HC_EMPTY;
                 tcnt[p] = 0;
                 if (cnt >= c) {
@@ -697,12 +732,13 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         } else {
             // nothing to order: release the table slots
             for (u32 i = threadIdx.x; i < nd; i += RC_THREADS) {
-                const u32 p = claimed[i];
+                const u32 p = slot_of(i);
+                if (MODE == 0 && tcnt[p] == 0) continue;
                 tkeys[p] = HC_EMPTY;
                 tcnt[p] = 0;
             }
             if (threadIdx.x == 0) {
-                const bool one = emit && n_empty >= c && n_empty > 0;
+                const bool one = exact && !ovf && n_empty >= c && n_empty > 0;
                 if (one) {
                     RcRow row;
                     row.key = HC_EMPTY;
@@ -713,10 +749,12 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
             }
         }
         BLOCK_SYNC();
-        {   // region A: staging -> bitmap again (MODE 1, all of it: the staging area overlays it); region B: bins -> queue
+        {   // region A: staging -> bitmap again (MODE 1, all of it: the staging area overlays it); region B: bins -> zero / queue
             if (MODE == 1) {
                 uint4* bm4 = reinterpret_cast<uint4*>(bm);
                 for (u32 i = threadIdx.x; i < RC_BM_WORDS / 4; i += RC_THREADS) bm4[i] = make_uint4(0, 0, 0, 0);
+            } else {
+                for (u32 i = threadIdx.x; i < RC_FINE; i += RC_THREADS) bins[i] = 0;
             }
             if (threadIdx.x < 8) s_scal[par ^ 1u][threadIdx.x] = 0;
         }

@@ -1,6 +1,12 @@
 """merge_tsv / merge_tsv_T of the reference's lib/mercat2_report.py (:98-160, :164-194) on the engine: the per-sample
-tables are parsed (or taken as they are, still on the device), their k-mers united and sorted, and the sample x k-mer
-matrix is formatted on the GPU.  Same names and arguments as the reference (``tsv_list``: {sample name: TSV path})."""
+tables are parsed on the device (or taken as they are, still on the device).  Same names and arguments as the reference
+(``tsv_list``: {sample name: TSV path}).
+
+``merge_tsv`` writes the reference's table BYTE FOR BYTE by default.  The reference's k-way merge takes the label of a
+row from the files that advanced on the previous line only, so with differing k-mer sets its table has repeated /
+out-of-order labels and drops some rows; everything downstream of the reference (PCA, diversity) consumes that table, so
+the drop-in reproduces it.  ``union=True`` writes what the merge is meant to be -- one row per k-mer of the sorted union,
+'0' where a sample lacks it -- formatted on the GPU; the two are identical whenever all samples hold the same k-mers."""
 from __future__ import annotations
 
 import os
@@ -20,15 +26,23 @@ def _tables(tsv_list: dict, engine):
     return names, header, tables
 
 
-def merge_tsv(tsv_list: dict, out_file: os.PathLike, engine=None):
-    """One row per k-mer of the sorted union, one column per sample (sorted by name), '0' where a sample lacks it."""
+def merge_tsv(tsv_list: dict, out_file: os.PathLike, engine=None, union: bool = False):
+    """One column per sample (sorted by name); rows as the reference's merge_tsv writes them (default) or the sorted
+    union of the k-mers (``union=True``)."""
     engine = engine or _native.default_engine()
     names, header, tables = _tables(tsv_list, engine)
-    matrix = engine.merge_tables(tables)
-    matrix.write_tsv(out_file, header, names, transposed=False)
-    matrix.close()
+    _write(engine, tables, names, out_file, header, union)
     for t in tables:
         t.close()
+
+
+def _write(engine, tables, names, out_file, header, union):
+    if union:
+        matrix = engine.merge_tables(tables)
+        matrix.write_tsv(out_file, header, names, transposed=False)
+        matrix.close()
+    else:
+        engine.merge_tables_reference(tables, out_file, header, names)
 
 
 def merge_tsv_T(tsv_list: dict, out_file: os.PathLike, engine=None):
@@ -43,10 +57,8 @@ def merge_tsv_T(tsv_list: dict, out_file: os.PathLike, engine=None):
         t.close()
 
 
-def merge_tables(tables: dict, out_file: os.PathLike, header: str = "k-mer", engine=None):
+def merge_tables(tables: dict, out_file: os.PathLike, header: str = "k-mer", engine=None, union: bool = False):
     """merge_tsv for tables that are still on the device ({sample name: Table}): no TSV is re-read."""
     engine = engine or _native.default_engine()
     names = sorted(tables.keys())
-    matrix = engine.merge_tables([tables[n] for n in names])
-    matrix.write_tsv(out_file, header, names, transposed=False)
-    matrix.close()
+    _write(engine, [tables[n] for n in names], names, out_file, header, union)

@@ -706,8 +706,9 @@ def test_merge_tsv_vs_reference(engine, tmp_path, label):
         dst = tmp_path / f"{name}_counts.tsv"
         dst.write_bytes(read_maybe_gz(f))
         tsv_list[name] = str(dst)
-    # the engine writes the sorted union; the reference's own k-way merge equals it when all samples hold the same
-    # k-mers (nucleotide k=3) and is scrambled otherwise (see oracle.merge_tsv) -- then the clean union is the target
+    # default: the reference's own table byte for byte (its k-way merge repeats / reorders labels when the samples' k-mer
+    # sets differ: protein k=3); union=True: the sorted union, equal to the reference's table when all samples hold the
+    # same k-mers (nucleotide k=3)
     ref = gzip.open(GOLDEN / f"merged_{label}.tsv.gz", "rb").read()
     union = tmp_path / "union.tsv"
     orc.merge_tsv_union(tsv_list, union)
@@ -715,6 +716,8 @@ def test_merge_tsv_vs_reference(engine, tmp_path, label):
     assert (want == ref) == (label == "nucleotide_k3")
     out = tmp_path / "combined.tsv"
     mercat2_report.merge_tsv(tsv_list, out, engine)
+    assert out.read_bytes() == ref
+    mercat2_report.merge_tsv(tsv_list, out, engine, union=True)
     assert out.read_bytes() == want
     out_t = tmp_path / "combined_T.tsv"
     mercat2_report.merge_tsv_T(tsv_list, out_t, engine)
@@ -731,13 +734,19 @@ def test_merge_tsv_vs_reference(engine, tmp_path, label):
     if label == "protein_k3":                              # (the nucleotide goldens were counted on removeN-cleaned files)
         out2 = tmp_path / "combined_resident.tsv"
         mercat2_report.merge_tables(tables, out2, "k-mer", engine)
+        assert out2.read_bytes() == ref
+        mercat2_report.merge_tables(tables, out2, "k-mer", engine, union=True)
         assert out2.read_bytes() == want
     # a k-mer missing from some samples, literal-byte rows, a file without trailing newline
     a = tmp_path / "a.tsv"; a.write_bytes(b"k-mer\ta_Count\nAAC\t5\nACN\t7\nTTT\t1")
     b = tmp_path / "b.tsv"; b.write_bytes(b"k-mer\tb_Count\nAAC\t2\nGGG\t123456789012\n")
     out3 = tmp_path / "ab.tsv"
-    mercat2_report.merge_tsv({"b": str(b), "a": str(a)}, out3, engine)
+    mercat2_report.merge_tsv({"b": str(b), "a": str(a)}, out3, engine, union=True)
     assert out3.read_bytes() == b"k-mer\ta\tb\nAAC\t5\t2\nACN\t7\t0\nGGG\t0\t123456789012\nTTT\t1\t0\n"
+    mercat2_report.merge_tsv({"b": str(b), "a": str(a)}, out3, engine)          # the reference's walk: label = next key of the files that advanced
+    ref3 = tmp_path / "ab_ref.tsv"
+    orc.merge_tsv({"b": str(b), "a": str(a)}, ref3)
+    assert out3.read_bytes() == ref3.read_bytes()
 
 
 @pytest.mark.parametrize("option,value", [("count_mode", 0), ("count_mode", 1), ("parse_single", 1), ("prefetch_pass", 0)])

@@ -1,25 +1,44 @@
 #!/usr/bin/env python
-"""Top source lines by warp-stall samples: tools/ncu_lines.py <rep> <kernel regex> [n]"""
-import csv, subprocess, sys
+"""Per-source-line hot spots of one kernel from a full ncu capture (compiled with -lineinfo, captured with --import-source on):
+python tools/ncu_lines.py <report.ncu-rep> <kernel regex> [top N]"""
+import re
+import subprocess
+import sys
+
 rep, kern = sys.argv[1], sys.argv[2]
-n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern],
-                     capture_output=True, text=True).stdout
-hdr, agg, launches = None, {}, 0
-for x in csv.reader(raw.splitlines()):
-    if x and x[0] == "Line No":
-        hdr = x
-        launches += 1
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kern}", "--launch-count", "1"]
+raw = subprocess.run(cmd, capture_output=True, text=True).stdout
+# (the Source column holds unescaped quotes, so the csv module cannot split these rows: CUDA-line rows look like
+#  "<line>","<source text>","-","-","<all samples>","<not issued>","<# samples>","<inst executed>","<thread inst>",...)
+fname, out = "", []
+for line in raw.splitlines():
+    if line.startswith('"File Path"'):
+        fname = line.split('","')[1].rstrip('"').split("/")[-1]
         continue
-    if hdr and len(x) > 10 and x[0].isdigit():
-        key = (x[0], x[1][:130])
-        smp = int(x[4]) if x[4].isdigit() else 0
-        ins = int(x[7]) if x[7].isdigit() else 0
-        a = agg.setdefault(key, [0, 0])
-        a[0] += smp
-        a[1] += ins
-tot = sum(a[0] for a in agg.values()) or 1
-toti = sum(a[1] for a in agg.values()) or 1
-print(f"{launches} launches, {tot} samples, {toti} warp instructions")
-for (ln, src), (smp, ins) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:n]:
-    print(f"{100*smp/tot:5.1f}%  inst {100*ins/toti:5.1f}%  L{ln}: {src}")
+    m = re.match(r'^"(\d+)","(.*?)","-","-","(.*)$', line)
+    if not m:
+        continue
+    tail = m.group(3).split('","')
+    if len(tail) < 8:
+        continue
+    out.append({"file": fname, "Line No": m.group(1), "Source": m.group(2), "# Samples": tail[2], "Instructions Executed": tail[3],
+                "Thread Instructions Executed": tail[4], "Avg. Threads Executed": str(float(tail[4] or 0) / max(1.0, float(tail[3] or 0)))})
+if not out:
+    print("no rows", file=sys.stderr)
+    sys.exit(1)
+
+
+def num(x):
+    try:
+        return float(x)
+    except ValueError:
+        return 0.0
+
+
+tot_i = sum(num(r["Instructions Executed"]) for r in out) or 1
+tot_s = sum(num(r["# Samples"]) for r in out) or 1
+print(f"total warp instructions {tot_i:.0f}, samples {tot_s:.0f}")
+print("share_inst share_samp avg_thr  file:line  source")
+for r in sorted(out, key=lambda r: -num(r["# Samples"]))[:top]:
+    print(f"{num(r['Instructions Executed']) / tot_i:9.3f} {num(r['# Samples']) / tot_s:9.3f} {num(r['Avg. Threads Executed']):7.1f}  {r['file']}:{r['Line No']:>4}  {r['Source'].strip()[:130]}")
