@@ -326,7 +326,7 @@ def main():
     # ---- correctness gate before anything is timed ---------------------------------------------------
     check = None
     if not args.no_check:
-        check = run_check(engine, text, args, rank, world, dist if world > 1 else None, device)
+        check = run_check(engine, genomes, args, rank, world, dist if world > 1 else None, device)
 
     for _ in range(args.warmup):
         rows, n_chunks = step_resident()
@@ -524,7 +524,11 @@ def main():
                                 "value": world * bases_per_step * secondary["steps"] / secondary["elapsed"], "unit": "bases/s",
                                 "ms_per_step": secondary["elapsed"] / secondary["steps"] * 1e3, "steps": secondary["steps"],
                                 "chunks_per_gpu": secondary["chunks"], "surviving_rows": secondary["rows"],
-                                "roofline": {k2: roof2[k2] for k2 in ("kernel", "achieved", "frac", "kernel_share_of_step", "pipeline_frac", "pipeline_achieved")}}
+                                "roofline": {k2: roof2[k2] for k2 in ("kernel", "achieved", "frac", "kernel_share_of_step", "pipeline_frac", "pipeline_achieved",
+                                                                       "kernel_time_share_of_wall")},
+                                "phases": phases_from_profile(secondary["profile"], secondary["steps"]),
+                                "kernels": {k2: {"launches": v["launches"], "ms": round(v["us"] / 1e3, 3)} for k2, v in
+                                            sorted(secondary["profile"].items(), key=lambda kv: -kv[1]["us"])[:12]}}
         if e2e:
             ts = sorted(e2e["times"])
             med = ts[len(ts) // 2]
@@ -556,14 +560,14 @@ def main():
     return 0
 
 
-def run_check(engine, text, args, rank, world, dist, device):
+def run_check(engine, genomes, args, rank, world, dist, device):
     """Known-answer gate on a CPU-sized prefix of the SAME reads with the SAME flags: the engine's table (through the
     path the timed steps take) against the oracle's, as TSV digests.  N > 1 additionally runs the key-exchange path on
     the prefix split over the ranks."""
     import numpy as np
     from oracle import mercat2_oracle as orc
     n_check = min(args.reads_per_gpu, int(os.environ.get("MC2_BENCH_CHECK_READS", 40_000)))
-    pre = text[: n_check * REC_BYTES]
+    pre = make_reads_text(device, genomes, n_check, 0)          # the job's first reads: the same text on every rank
     res = {"reads": n_check, "flags": f"-k {args.k} -c {args.c} -s 0"}
     if rank == 0:
         want = orc.find_kmers_text(pre.cpu().numpy().tobytes().decode(), args.k, args.c)

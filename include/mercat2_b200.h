@@ -44,6 +44,10 @@ void mc2_engine_destroy(mc2_engine* e);
 const char* mc2_last_error(void);
 const char* mc2_version(void);
 
+/* Release the engine's device workspace (the key arrays of the range partition are kept between calls: up to 8 bytes
+ * per window of the largest chunk counted so far) and return the stream-ordered pool's cached memory to the driver. */
+int mc2_engine_trim(mc2_engine* e);
+
 /* Tunables (mostly for tests): "dense_max_bins", "smem_max_bins", "batch_symbols", "force_path"
  * (0 auto, 1 dense, 2 sparse, 3 wide), "force_encoding" (-1 auto, 0 ACGT 2-bit, 1 A-Z 5-bit, 2 byte), "sparse_algo"
  * (0/2 range partition + shared-memory tables, 1 radix sort), "count_mode" (-1 auto, 0 / 1 see rangecount.cuh). */
@@ -63,6 +67,13 @@ int mc2_engine_profile(mc2_engine* e, char* buf, uint64_t cap, uint64_t* size);
  * keep those with count >= min_count.  `space` says whether `text` is a host or a device pointer. */
 int mc2_count_text(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
                    mc2_table** out);
+
+/* Replaces the sample loop of bin/mercat2.py:411-448 (one find_kmers task per sample file, each file smaller than
+ * the -s trigger, i.e. ONE piece) for n samples at once: out[j] is the table of texts[j], identical to n calls of
+ * mc2_count_text.  The samples are counted in a single pass (keys carry the sample index), which is what makes many
+ * small samples -- BASELINE config 5: 64 proteomes -- fill the GPU.  `space` applies to every text. */
+int mc2_count_batch(mc2_engine* e, const void* const* texts, const uint64_t* nbytes, uint32_t n, int space, int k, int64_t min_count,
+                    mc2_table** out);
 
 /* Replaces calculateKmerCount(seq, kmer) (lib/mercat2_kmers.py:10-28): `symbols` is a raw sequence, no
  * FASTA parsing (a '>' or newline in it is an ordinary character). */
@@ -200,6 +211,16 @@ int mc2_matrix_k(const mc2_matrix* m);
 int mc2_matrix_export(mc2_matrix* m, char* kmers, uint64_t* counts);
 int mc2_matrix_write_tsv(mc2_matrix* m, const char* path, const char* corner, const char* const* names, int transposed);
 void mc2_matrix_free(mc2_matrix* m);
+/* ---- row N4: what the alpha-diversity metrics and the top-k-mer summary read -----------------------------------------
+ * lib/mercat2_diversity.py:23-27 re-reads a sample's TSV to build the count vector it hands to scikit-bio;
+ * mc2_table_export_counts gives that vector straight from the table (counts: rows entries in sorted k-mer order, may be
+ * NULL) and its abundance spectrum reduced on the device (spectrum: 16 words, may be NULL: [0] observed k-mers, [1] sum
+ * of counts, [2..3] sum of squared counts (low / high 64 bits), [4] largest count, [5 + i] k-mers seen exactly i + 1
+ * times, i < 10).  The arithmetic of the metrics stays with skbio.
+ * lib/mercat2_figures.py:50-65 keeps the 5 k-mers with the largest mean count over the samples (earlier rows win ties);
+ * mc2_matrix_top_rows returns their row indices (largest first) in the matrix of mc2_merge_tables. */
+int mc2_table_export_counts(mc2_table* t, uint64_t* counts, uint64_t* spectrum);
+int mc2_matrix_top_rows(mc2_matrix* m, uint32_t top, uint64_t* rows_out, uint32_t* found);
 /* merge_tsv byte for byte as the reference writes it (lib/mercat2_report.py:98-160: a k-way cursor walk whose row label
  * is the smallest next k-mer among the files that advanced on the previous line -- with differing k-mer sets labels
  * repeat / appear out of order and some rows are dropped; identical to the sorted union when all samples hold the same

@@ -26,11 +26,13 @@ SYMBOLS = [
     ("mc2_engine_destroy", None, [_VP]),
     ("mc2_last_error", C.c_char_p, []),
     ("mc2_version", C.c_char_p, []),
+    ("mc2_engine_trim", _INT, [_VP]),
     ("mc2_engine_set_option", _INT, [_VP, C.c_char_p, _I64]),
     ("mc2_engine_get_stat", _I64, [_VP, C.c_char_p]),
     ("mc2_engine_profile", _INT, [_VP, _VP, _U64, _PU64]),
     ("mc2_count_text", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
     ("mc2_count_symbols", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
+    ("mc2_count_batch", _INT, [_VP, _VP, _VP, C.c_uint32, _INT, _INT, _I64, _VP]),
     ("mc2_count_sample", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _U64, _PP, _PU64, _PU64, _U64]),
     ("mc2_chunk_offsets", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64, _U64, _PU64]),
     ("mc2_sample_begin", _INT, [_VP, _INT, _I64, _PP]),
@@ -318,6 +320,10 @@ class Engine:
         except Exception:
             pass
 
+    def trim(self):
+        """Release the device workspace the engine keeps between calls (and the pool's cached memory)."""
+        _check(self._lib, self._lib.mc2_engine_trim(self._h))
+
     def set_option(self, name: str, value: int):
         _check(self._lib, self._lib.mc2_engine_set_option(self._h, name.encode(), int(value)))
 
@@ -338,6 +344,22 @@ class Engine:
         out = C.c_void_p()
         _check(self._lib, self._lib.mc2_count_text(self._h, addr, n, space, k, min_count, C.byref(out)))
         return Table(self, out)
+
+    def count_batch(self, texts, k: int, min_count: int) -> list:
+        """One table per text (each text = one sample file smaller than the -s trigger), counted in a single pass over
+        all of them; identical to [count_text(t, k, min_count) for t in texts]."""
+        bufs = [_as_buffer(t) for t in texts]
+        if not bufs:
+            return []
+        spaces = {b[2] for b in bufs}
+        if len(spaces) > 1:
+            raise ValueError("all texts of a batch must live in the same memory space")
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b[0] or None for b in bufs])
+        sizes = (C.c_uint64 * n)(*[b[1] for b in bufs])
+        outs = (C.c_void_p * n)()
+        _check(self._lib, self._lib.mc2_count_batch(self._h, ptrs, sizes, n, spaces.pop(), k, min_count, outs))
+        return [Table(self, C.c_void_p(outs[j])) for j in range(n)]
 
     def count_symbols(self, data, k: int, min_count: int = 1) -> Table:
         addr, n, space, keep = _as_buffer(data)

@@ -4,7 +4,9 @@ without Ray, figures, diversity or ORF calling).
 Same flags for the path: -i/-f, -k, -c [10], -s [100], -n, -o, -replace, -skipclean, -toupper.  Same output tree
 for it: <out>/clean/*, <out>/tsv_<type>/<base>_counts.tsv, <out>/report/metrics-protein.tsv.  Flags of subsystems
 that are out of scope (-prod, -fgs, -pca, -lowmem) are accepted and reported as skipped.  Under torchrun
-(WORLD_SIZE > 1) samples are sharded over the ranks (one process per GPU), each rank writes its own TSVs.
+(WORLD_SIZE > 1, one process per GPU, NCCL) whole samples are dealt to the ranks by size (longest processing time first:
+SURVEY 8e grain 1, no collective on the data path); each rank writes the TSVs of its samples and rank 0 writes the ONE
+report/metrics-protein.tsv from the rows the ranks hand in, in the reference's sample order.
 """
 from __future__ import annotations
 
@@ -76,10 +78,17 @@ def mercat_main(argv=None):
                 parser.error(f"Output folder exists, please specify another folder or use the flag '-replace' "
                              f"to override the files. '{out}'")
         out.mkdir(0o777, True, True)
+    dist = None
     if world > 1:
+        import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("gloo")
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")                      # (CPU-only hosts: the CLI's own tests)
         dist.barrier()
     if rank == 0:
         print(f"\nStarting MerCat2 (mercat2_b200 {__version__}) with k-mer {args.k} on {world} GPU(s)\n")
@@ -91,7 +100,10 @@ def mercat_main(argv=None):
         folder = os.path.abspath(os.path.expanduser(args.f))
         inputs += [str(Path(folder, name)) for name in sorted(os.listdir(folder))
                    if classify(Path(folder, name))[0] is not None]
-    todo = mcd.shard_round_robin(sorted(set(inputs)), rank, world)          # whole samples per rank
+    # whole samples per rank, balanced by on-disk size (longest processing time first)
+    inputs = sorted(set(inputs))
+    mine = set(mcd.shard_lpt([os.stat(f).st_size for f in inputs], world)[rank])
+    todo = [f for i, f in enumerate(inputs) if i in mine]
     cleanpath = os.path.join(out, "clean")
     samples = {"nucleotide": {}, "protein": {}}
     start = timeit.default_timer()
@@ -117,19 +129,28 @@ def mercat_main(argv=None):
         out_tsv = os.path.join(out, f"tsv_{sample_type}")
         os.makedirs(out_tsv, exist_ok=True)
         start = timeit.default_timer()
-        for base, file in samples[sample_type].items():
-            pipeline.run_mercat2(base, [file], os.path.join(out_tsv, f"{base}_counts.tsv"), args.k, args.c,
-                                 chunk_size_mb=args.s)
+        pipeline.run_samples(samples[sample_type], out_tsv, args.k, args.c, chunk_size_mb=args.s)
         print(f"Time to count {args.k}-mers: {round(timeit.default_timer() - start, 2)} seconds")
-    if samples["protein"]:
-        tsv = os.path.join(out, "report", "metrics-protein.tsv" if world == 1 else f"metrics-protein.{rank}.tsv")
-        with open(tsv, "w") as writer:
-            print("Sample", "seq_name", "length", "PI", "MW", "Hydro", sep="\t", file=writer)
-            for base, file in samples["protein"].items():
-                for header, name, length, pi, mw, hydro in pipeline.sample_metric_rows(file, args.s):
-                    print(header, name, length, "" if pi is None else pi, mw, hydro, sep="\t", file=writer)
+    # report/metrics-protein.tsv: every rank computes the rows of its samples, rank 0 writes the one file
+    rows = {}
+    for base, file in samples["protein"].items():
+        rows[base] = list(pipeline.sample_metric_rows(file, args.s))
+    gathered = [rows]
     if world > 1:
-        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(rows, gathered, dst=0)
+    if rank == 0:
+        merged = {}
+        for part in gathered:
+            merged.update(part)
+        order = [classify(Path(f))[1] for f in inputs if classify(Path(f))[0] == "protein"]
+        if merged:
+            with open(os.path.join(out, "report", "metrics-protein.tsv"), "w") as writer:
+                print("Sample", "seq_name", "length", "PI", "MW", "Hydro", sep="\t", file=writer)
+                for base in order:
+                    for header, name, length, pi, mw, hydro in merged.get(base, ()):
+                        print(header, name, length, "" if pi is None else pi, mw, hydro, sep="\t", file=writer)
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0

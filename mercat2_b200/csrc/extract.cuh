@@ -42,6 +42,30 @@ template <> struct EncTraits<ENC_BYTE> {
 struct SymView {
     const u8* sym;   // 16-byte aligned
     u64 n;           // symbols
+    // batched samples (mc2_count_batch): sample j owns the symbols [sample_start[j], sample_start[j + 1]); a window's key
+    // carries its sample in the bits above the k-mer code, so that one pass counts every (sample, k-mer) pair
+    const u64* sample_start = nullptr;
+    u32 n_samples = 0;
+    u32 sample_shift = 0;
+};
+
+// sample of a symbol position, for positions visited in ascending order by one thread
+struct SampleTag {
+    u32 sid;
+    u64 next;
+    __device__ __forceinline__ void init(const SymView& v, u64 s) {
+        sid = 0;
+        next = ~0ull;
+        if (!v.sample_start) return;
+        u32 lo = 0, hi = v.n_samples;                       // last j with sample_start[j] <= s
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (v.sample_start[mid] <= s) lo = mid; else hi = mid; }
+        sid = lo;
+        next = lo + 1 < v.n_samples ? v.sample_start[lo + 1] : ~0ull;
+    }
+    __device__ __forceinline__ u64 tag(const SymView& v, u64 s) {
+        while (s >= next) { ++sid; next = sid + 1 < v.n_samples ? v.sample_start[sid + 1] : ~0ull; }
+        return (u64)sid << v.sample_shift;
+    }
 };
 
 __device__ __forceinline__ void load_sym16(const SymView& v, i64 p0, u32 w[4]) {

@@ -149,7 +149,9 @@ template <int ENC>
 static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr) {
     range_kernel_attrs(e);
     const int k = s->k;
-    const int kb = k * EncTraits<ENC>::BITS;
+    int sample_bits = 0;                                         // batched samples: the sample index rides above the k-mer code
+    if (v.sample_start) while ((1u << sample_bits) < v.n_samples) ++sample_bits;
+    const int kb = k * EncTraits<ENC>::BITS + sample_bits;
     const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
     if (cap == 0) return;
     const u32 c = (u32)std::min<u64>(s->c, 0xFFFFFFFFull);
@@ -519,13 +521,15 @@ static void fn_dense_span(mc2_engine* e, mc2_sample* s, const PackedView& pv) {
 // keys).  Returns false if the result does not fit in free device memory (`extra` = bytes the caller still needs
 // afterwards) or a group would exceed `group_max` keys.
 struct Level0 {
-    DBuf<u64> keys0;
+    u64* keys0 = nullptr;                  // the engine's workspace array (borrowed) or, when that is taken, `own`
+    DBuf<u64> own;
+    bool borrowed = false;
     std::vector<u64> gbase;
     std::vector<u64> bounds;
     u64 gmax = 0;
 };
 static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>& pvs, const KeySpan* ks, u32 g0, u64 group_max, u64 extra,
-                             Level0& out, const u32* shist_given = nullptr) {
+                             Level0& out, const u32* shist_given = nullptr, bool hold_workspace = false) {
     range_kernel_attrs(e);
     u64 cap = ks ? ks->n : 0;
     for (auto& pv : pvs) cap += pv.n;
@@ -572,22 +576,34 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
         CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
         CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
         const u64 avail = (u64)free_b + (reserved > used ? (u64)(reserved - used) : 0);
-        if (total * 8 + extra + (1ull << 30) > avail) return false;
+        const RangeWork& w0 = range_work(e);
+        const u64 have = w0.keys0_busy ? 0 : w0.keys0.b.n * 8;              // the workspace array is re-used (it is freed first if it must grow)
+        if (total * 8 + extra + (1ull << 30) > avail + have) return false;
     }
     pt.mark("level-0 memory check");
-    out.keys0.alloc(e, total);
+    {
+        RangeWork& w = range_work(e);
+        if (!w.keys0_busy) {
+            out.keys0 = w.keys0.get(e, total);
+            out.borrowed = hold_workspace;
+            if (hold_workspace) w.keys0_busy = true;
+        } else {
+            out.own.alloc(e, total);
+            out.keys0 = out.own.p;
+        }
+    }
     DBuf<u64> gbase_dev(e, g0 + 1);
     DBuf<u32> cur0(e, g0);
     cur0.zero();
     pt.mark("level-0 allocation");
     CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur0.p, out.keys0.p,
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur0.p, out.keys0,
                (const u64*)gbase_dev.p);
     } else {
         for (auto& pv : pvs) {
             const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
-            if (grid) LAUNCH(e, fn_scatter1_kernel, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM_LUT, pv, k, rv, cur0.p, out.keys0.p, (const u64*)gbase_dev.p);
+            if (grid) LAUNCH(e, fn_scatter1_kernel, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM_LUT, pv, k, rv, cur0.p, out.keys0, (const u64*)gbase_dev.p);
         }
     }
     CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // (host vector was the source of an async copy)
@@ -615,7 +631,7 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     for (u32 g = 0; g < g0; ++g) {
         const u64 n = l0.gbase[g + 1] - l0.gbase[g];
         if (!n) continue;
-        KeySpan span{l0.keys0.p + l0.gbase[g], n, l0.bounds[g], std::max<u64>(l0.bounds[g + 1], l0.bounds[g] + 1)};
+        KeySpan span{l0.keys0 + l0.gbase[g], n, l0.bounds[g], std::max<u64>(l0.bounds[g + 1], l0.bounds[g] + 1)};
         sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
     }
     pt.mark("groups");

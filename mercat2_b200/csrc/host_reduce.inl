@@ -9,7 +9,7 @@ struct Parsed {
     ParseStats stats;
 };
 
-static void parse_text(mc2_engine* e, const u8* dtext, u64 len, int toupper, Parsed& out) {
+static void parse_text(mc2_engine* e, const u8* dtext, u64 len, int toupper, Parsed& out, DBuf<u64>* tile_off_out = nullptr) {
     memset(&out.stats, 0, sizeof out.stats);
     out.nsym = 0;
     if (len == 0) return;
@@ -35,6 +35,7 @@ static void parse_text(mc2_engine* e, const u8* dtext, u64 len, int toupper, Par
     if (out.nsym)
         LAUNCH(e, parse_emit_kernel<true>, (unsigned)ntiles, PARSE_THREADS, 0, dtext, len, tf.p, tr.p, cnt.p,
                (const u64*)off.p, out.sym.p, st.p, toupper);
+    if (tile_off_out) *tile_off_out = std::move(off);       // symbol index of every 4 KiB text tile's first symbol
 }
 
 // =====================================================================================================
@@ -57,6 +58,9 @@ static void make_plan(mc2_engine* e, const ParseStats& st, int k, Plan& plan) {
         bins = 1;
         for (int i = 0; i < k && bins <= (1ull << 40); ++i) bins *= base;
         if (bins <= e->opt_dense_max_bins && bins < (1ull << 31)) path = PATH_DENSE;
+        // a table much larger than the first chunk costs more to clear, fold and scan than the chunk costs to count
+        // sparsely (26^5 bins = 143 MB of tables for a 1.6 M-residue proteome): the range path takes such samples
+        if (path == PATH_DENSE && bins > e->opt_smem_max_bins && st.n_ascii * 4 < bins && e->opt_force_path != PATH_DENSE) path = PATH_SPARSE;
     }
     if (e->opt_force_path == PATH_SPARSE && kb <= 64) path = PATH_SPARSE;
     if (e->opt_force_path == PATH_WIDE) path = PATH_WIDE;

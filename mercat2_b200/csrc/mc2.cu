@@ -166,6 +166,10 @@ struct WBuf {
 // time than the kernels took.  One set of buffers, sized for the largest request so far, serves them all.
 struct RangeWork {
     WBuf<u64> keys1, keys2, row_off;
+    WBuf<u64> keys0;                       // level-0 key array of a very large chunk (8 B per window: tens of GB).  Kept between
+                                           // calls -- re-creating it cost 17 ms when the pool still held the memory and 0.2-0.9 s
+                                           // when it did not (e.g. after NCCL had sent from it) -- and released by mc2_engine_trim
+    bool keys0_busy = false;               // an mc2_keys object is holding it
     WBuf<u32> ghist, sub_base, cur1, cur2, tile_pref, ovf_list, rows, shist;
     WBuf<u8> slots1;                       // RcRow slots when min_count == 1 (otherwise the slots overlay keys1)
     WBuf<u16> lut[2];                      // level-0 plan and group / chunk plan are alive at the same time
@@ -420,6 +424,21 @@ void mc2_engine_destroy(mc2_engine* e) {
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
+}
+
+int mc2_engine_trim(mc2_engine* e) {
+    API_BEGIN
+    if (!e) throw Mc2Error(MC2_ERR_INVALID, "engine is NULL");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->work && e->work->keys0_busy) throw Mc2Error(MC2_ERR_INVALID, "a key partition (mc2_keys) still uses the workspace");
+    delete e->work;
+    e->work = nullptr;
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, e->device));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    CUDA_CHECK(cudaMemPoolTrimTo(pool, 0));
+    API_END
 }
 
 int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
@@ -723,6 +742,7 @@ int mc2_sample_dense_plan(mc2_sample* s, int encoding) {
 }
 
 struct mc2_keys {
+    ~mc2_keys() { if (l0.borrowed && e && e->work) e->work->keys0_busy = false; }
     mc2_engine* e = nullptr;
     int k = 0;
     u32 groups = 0;
@@ -803,7 +823,7 @@ int mc2_keys_partition(mc2_keys* ks, uint32_t groups) {
     ks->l0.gbase.assign(groups + 1, 0);
     ks->l0.bounds.assign(groups + 1, 1ull << 32);
     ks->l0.bounds[0] = 0;
-    if (!level0_partition(e, ks->k, ks->pvs, nullptr, groups, (1ull << 32) - 1, 0, ks->l0, ks->shist.p))
+    if (!level0_partition(e, ks->k, ks->pvs, nullptr, groups, (1ull << 32) - 1, 0, ks->l0, ks->shist.p, true))
         throw Mc2Error(MC2_ERR_LIMIT, "key partition: the keys do not fit in free device memory");
     ks->pvs.clear();
     ks->spans.clear();
@@ -828,7 +848,7 @@ int mc2_keys_info(mc2_keys* ks, const uint64_t** keys, uint64_t* sizes, uint64_t
     API_BEGIN
     if (!ks) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
     if (!ks->partitioned) throw Mc2Error(MC2_ERR_INVALID, "mc2_keys_partition has not run");
-    if (keys) *keys = (const uint64_t*)ks->l0.keys0.p;
+    if (keys) *keys = (const uint64_t*)ks->l0.keys0;
     if (sizes)
         for (u32 g = 0; g < ks->groups; ++g) sizes[g] = ks->l0.gbase[g + 1] - ks->l0.gbase[g];
     if (bounds)
@@ -1163,6 +1183,43 @@ int mc2_merge_tables_reference(mc2_engine* e, mc2_table* const* tables, uint32_t
     API_END
 }
 
+int mc2_table_export_counts(mc2_table* t, uint64_t* counts, uint64_t* spectrum) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    mc2_engine* e = t->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const u64 nf = t->fast.n, nw = t->wide.n;
+    if (counts) {
+        ensure_host(t);                                        // rows in sorted k-mer order, packed and literal rows merged
+        if (!t->counts.empty()) memcpy(counts, t->counts.data(), t->counts.size() * 8);
+    }
+    if (spectrum) {
+        DBuf<ull> sp(e, MG_SPECTRUM_WORDS);
+        sp.zero();
+        if (nf) LAUNCH(e, mg_spectrum_kernel, (unsigned)std::min<u64>(div_up(nf, 256 * 8), (u64)e->num_sms * 4), 256, 0, (const u64*)t->fast.counts.p, nf, sp.p);
+        if (nw) LAUNCH(e, mg_spectrum_kernel, (unsigned)std::min<u64>(div_up(nw, 256 * 8), (u64)e->num_sms * 4), 256, 0, (const u64*)t->wide.counts.p, nw, sp.p);
+        d2h(e, (ull*)spectrum, (const ull*)sp.p, (u64)MG_SPECTRUM_WORDS);
+    }
+    API_END
+}
+
+int mc2_matrix_top_rows(mc2_matrix* m, uint32_t top, uint64_t* rows_out, uint32_t* found) {
+    API_BEGIN
+    if (!m || !rows_out || !found) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (top > 32) throw Mc2Error(MC2_ERR_INVALID, "top must be <= 32");
+    mc2_engine* e = m->e;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const u32 take = (u32)std::min<u64>(top, m->rows);
+    *found = take;
+    if (take) {
+        DBuf<u64> sums(e, m->rows), out(e, take);
+        LAUNCH(e, mg_row_sums_kernel, (unsigned)div_up(m->rows, 256), 256, 0, (const u64*)m->counts.p, m->rows, m->samples, sums.p);
+        LAUNCH(e, mg_top_rows_kernel, 1, 1024, 0, (const u64*)sums.p, m->rows, take, out.p);
+        d2h(e, (u64*)rows_out, (const u64*)out.p, (u64)take);
+    }
+    API_END
+}
+
 void mc2_matrix_free(mc2_matrix* m) {
     if (!m) return;
     cudaSetDevice(m->e->device);
@@ -1210,6 +1267,134 @@ int mc2_count_sample(mc2_engine* e, const void* text, uint64_t nbytes, int space
     if (piece_offsets)
         for (u64 i = 0; i < bounds.size() && i < piece_capacity; ++i) piece_offsets[i] = bounds[i];
     *out = t;
+    API_END
+}
+
+// ---- several small samples in ONE pass (BASELINE config 5: many proteomes, one table each) --------------------------
+// Replaces the sample loop of bin/mercat2.py:411-448 (one countKmers task per file) for samples that are each ONE piece
+// (smaller than the -s trigger): the texts are laid out behind each other (a header line between them, each starting
+// on a 4 KiB parse tile), parsed once, and every window's key carries its sample index above the k-mer code, so a single
+// run of the range path counts all (sample, k-mer) pairs, filters each pair with min_count -- exactly the per-file
+// filter of lib/mercat2_kmers.py:73-78 -- and leaves the rows sorted by (sample, k-mer); the per-sample tables are
+// slices of that array.  A 1.6 M-residue proteome alone cannot fill the GPU (its whole pass is launch latency);
+// 64 of them together are one ordinary 100 MB piece.  Falls back to one pass per sample when the batch does not fit
+// the scheme (windows outside the packed alphabet, k too large for the key, too many symbols).
+static void count_one_text(mc2_engine* e, const u8* d, u64 nbytes, int k, u64 c, mc2_table** out) {
+    mc2_sample s;
+    s.e = e; s.k = k; s.c = c;
+    if (nbytes) count_chunk(e, &s, d, nbytes);
+    *out = sample_finish(&s);
+}
+
+__global__ void mask_keys_kernel(const u64* __restrict__ in, u64 n, u64 mask, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] & mask;
+}
+
+int mc2_count_batch(mc2_engine* e, const void* const* texts, const uint64_t* nbytes, uint32_t n, int space, int k, int64_t min_count,
+                    mc2_table** out) {
+    API_BEGIN
+    if (!e || !out || (n && (!texts || !nbytes))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    check_count_args(e, "", 0, k);
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const u64 c = min_count < 1 ? 1 : (u64)min_count;
+    for (u32 j = 0; j < n; ++j) out[j] = nullptr;
+    if (n == 0) return MC2_OK;
+    // layout: text j at off[j] (a multiple of the parse tile), then "\n>\n...\n" up to the next tile boundary: the header
+    // line closes the last record of sample j and emits the separator that keeps windows inside their sample
+    std::vector<u64> off(n + 1, 0);
+    for (u32 j = 0; j < n; ++j) {
+        if (!texts[j] && nbytes[j]) throw Mc2Error(MC2_ERR_INVALID, "NULL text");
+        off[j + 1] = (off[j] + nbytes[j] + 3 + PARSE_TILE - 1) / PARSE_TILE * PARSE_TILE;
+    }
+    const u64 total = off[n];
+    DBuf<u8> cat(e, total + 16);
+    CUDA_CHECK(cudaMemsetAsync(cat.p, '\n', total, e->stream));
+    for (u32 j = 0; j < n; ++j) {
+        if (nbytes[j]) {
+            CUDA_CHECK(cudaMemcpyAsync(cat.p + off[j], texts[j], nbytes[j], space == MC2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+            if (space != MC2_DEVICE) e->h2d_bytes += nbytes[j];
+        }
+        CUDA_CHECK(cudaMemsetAsync(cat.p + off[j] + nbytes[j] + 1, '>', 1, e->stream));
+    }
+    auto fallback = [&]() {
+        for (u32 j = 0; j < n; ++j)
+            if (!out[j]) count_one_text(e, cat.p + off[j], nbytes[j], k, c, &out[j]);
+    };
+    try {
+        Parsed ps;
+        DBuf<u64> tile_off;
+        parse_text(e, cat.p, total, 0, ps, &tile_off);
+        e->chunks += n;
+        Plan plan;
+        if (ps.stats.n_ascii) make_plan(e, ps.stats, k, plan);
+        int sbits = 0;
+        while ((1u << sbits) < n) ++sbits;
+        const int bits = plan.enc >= 0 ? enc_bits(plan.enc) : 8;
+        const u64 n_fast = plan.enc == ENC_NT2 ? ps.stats.n_acgt : plan.enc == ENC_AA5 ? ps.stats.n_upper : ps.stats.n_ascii;
+        mc2_sample probe;
+        probe.e = e; probe.k = k; probe.c = c;
+        const bool batchable = ps.stats.n_ascii > 0 && plan.enc >= 0 && plan.path != PATH_WIDE && k * bits + sbits <= 64 &&
+                               n_fast == ps.stats.n_ascii && ps.nsym <= range_batch_max(e, &probe) && ps.nsym < (1ull << 32) &&
+                               e->opt_sparse_algo != 1 && e->opt_force_path != PATH_WIDE;
+        if (!batchable) {
+            if (ps.stats.n_ascii == 0) {                    // nothing but headers: n empty tables
+                for (u32 j = 0; j < n; ++j) { mc2_sample s0; s0.e = e; s0.k = k; s0.c = c; out[j] = sample_finish(&s0); }
+                return MC2_OK;
+            }
+            fallback();
+            return MC2_OK;
+        }
+        // symbol index where every sample starts = symbol offset of its first parse tile
+        std::vector<u64> tiles(n);
+        for (u32 j = 0; j < n; ++j) tiles[j] = off[j] / PARSE_TILE;
+        DBuf<u64> dtiles(e, n), starts(e, n);
+        CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), n * 8ull, cudaMemcpyHostToDevice, e->stream));
+        LAUNCH(e, gather_u64_kernel, (unsigned)div_up(n, 256), 256, 0, (const u64*)tile_off.p, (const u64*)dtiles.p, (u64)n, starts.p);
+        mc2_sample s;
+        s.e = e; s.k = k; s.c = c;
+        s.plan = plan;
+        s.plan.path = PATH_SPARSE;
+        SymView v{ps.sym.p, ps.nsym, starts.p, n, (u32)(k * bits)};
+        if (plan.enc == ENC_NT2) sparse_chunk_range<ENC_NT2>(e, &s, v);
+        else if (plan.enc == ENC_AA5) sparse_chunk_range<ENC_AA5>(e, &s, v);
+        else sparse_chunk_range<ENC_BYTE>(e, &s, v);
+        FastPart all;
+        if (!s.fast.empty()) reduce_fast_parts(e, s.fast, k * bits + sbits, 1, all);
+        // cut the (sample, k-mer)-sorted rows at the sample boundaries
+        std::vector<u64> cuts(n + 1, 0);
+        cuts[n] = all.n;
+        if (all.n && n > 1) {
+            std::vector<u64> split(n - 1);
+            for (u32 j = 1; j < n; ++j) split[j - 1] = (u64)j << (k * bits);
+            DBuf<u64> sp(e, n - 1), lb(e, n - 1);
+            CUDA_CHECK(cudaMemcpyAsync(sp.p, split.data(), (n - 1) * 8ull, cudaMemcpyHostToDevice, e->stream));
+            LAUNCH(e, lower_bound_kernel, (unsigned)div_up(n - 1, 128), 128, 0, (const u64*)all.keys.p, (u64)all.n, (const u64*)sp.p, (u64)(n - 1), lb.p);
+            d2h(e, cuts.data() + 1, (const u64*)lb.p, (u64)(n - 1));
+        } else {
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));        // (host vectors were the sources of async copies)
+        }
+        const u64 kmask = k * bits >= 64 ? ~0ull : ((1ull << (k * bits)) - 1);
+        for (u32 j = 0; j < n; ++j) {
+            std::unique_ptr<mc2_table> t(new mc2_table);
+            t->e = e;
+            t->k = k;
+            t->enc = plan.enc;
+            const u64 rows = cuts[j + 1] - cuts[j];
+            t->fast.n = rows;
+            t->fast.keys.alloc(e, rows);
+            t->fast.counts.alloc(e, rows);
+            if (rows) {
+                LAUNCH(e, mask_keys_kernel, (unsigned)div_up(rows, 256), 256, 0, (const u64*)all.keys.p + cuts[j], rows, kmask, t->fast.keys.p);
+                CUDA_CHECK(cudaMemcpyAsync(t->fast.counts.p, all.counts.p + cuts[j], rows * 8, cudaMemcpyDeviceToDevice, e->stream));
+            }
+            out[j] = t.release();
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    } catch (...) {
+        for (u32 j = 0; j < n; ++j) { if (out[j]) { delete out[j]; out[j] = nullptr; } }
+        throw;
+    }
     API_END
 }
 

@@ -107,3 +107,79 @@ __global__ void mg_cell_write_kernel(const u64* __restrict__ vals, u64 stride_r,
     o += nd;
     if (c == ncols - 1) *o = '\n';
 }
+
+// ---- row N4: inputs of the alpha-diversity metrics and of the top-k-mer summary ---------------------------------------
+// The reference hands every sample's count vector to scikit-bio (lib/mercat2_diversity.py:23-27: counts += [int(line.split()[1])])
+// and picks the 5 k-mers with the largest mean count across samples for its summary plot (lib/mercat2_figures.py:50-65).
+// Both need reductions over counts only.  spectrum[0] = observed k-mers, [1] = sum of counts, [2..3] = sum of squared
+// counts (low, high 64 bits), [4] = largest count, [5 + i] = k-mers seen exactly i + 1 times (i < 10: the singleton /
+// doubleton / rare-abundance classes of chao1, goods_coverage and ace).  The arithmetic of the metrics stays with skbio.
+#define MG_SPECTRUM_WORDS 16
+__global__ void __launch_bounds__(256) mg_spectrum_kernel(const u64* __restrict__ counts, u64 n, unsigned long long* __restrict__ spectrum) {
+    __shared__ unsigned long long s[MG_SPECTRUM_WORDS];
+    if (threadIdx.x < MG_SPECTRUM_WORDS) s[threadIdx.x] = 0;
+    BLOCK_SYNC();
+    unsigned long long sum = 0, sq_lo = 0, sq_hi = 0, mx = 0, cls[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, rows = 0;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+        const unsigned long long c = counts[i];
+        ++rows;
+        sum += c;
+        const unsigned long long lo = c * c, hi = __umul64hi(c, c);
+        sq_lo += lo;
+        sq_hi += hi + (sq_lo < lo ? 1ull : 0ull);
+        mx = max(mx, c);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) cls[j] += (c == (unsigned long long)(j + 1)) ? 1ull : 0ull;
+    }
+    atomicAdd(&s[0], rows);
+    atomicAdd(&s[1], sum);
+    const unsigned long long old = atomicAdd(&s[2], sq_lo);
+    atomicAdd(&s[3], sq_hi + (old + sq_lo < old ? 1ull : 0ull));
+    atomicMax(&s[4], mx);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) if (cls[j]) atomicAdd(&s[5 + j], cls[j]);
+    BLOCK_SYNC();
+    if (threadIdx.x < MG_SPECTRUM_WORDS && threadIdx.x != 2 && threadIdx.x != 3 && threadIdx.x != 4 && s[threadIdx.x]) atomicAdd(&spectrum[threadIdx.x], s[threadIdx.x]);
+    if (threadIdx.x == 4) atomicMax(&spectrum[4], s[4]);
+    if (threadIdx.x == 2) {
+        const unsigned long long o = atomicAdd(&spectrum[2], s[2]);
+        atomicAdd(&spectrum[3], s[3] + (o + s[2] < o ? 1ull : 0ull));
+    }
+}
+// sum of every matrix row (counts: rows x samples, row-major)
+__global__ void mg_row_sums_kernel(const u64* __restrict__ counts, u64 rows, u32 samples, u64* __restrict__ sums) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    u64 acc = 0;
+    for (u32 j = 0; j < samples; ++j) acc += counts[r * samples + j];
+    sums[r] = acc;
+}
+// The `top` rows with the largest sums, earlier rows winning ties (one CTA; top <= 32): every round takes the
+// lexicographic maximum of (sum, ~row) over the rows not taken yet.
+__global__ void __launch_bounds__(1024) mg_top_rows_kernel(const u64* __restrict__ sums, u64 rows, u32 top, u64* __restrict__ out) {
+    __shared__ u64 s_sum[1024], s_row[1024];
+    __shared__ u64 taken[32];
+    for (u32 t = 0; t < top; ++t) {
+        u64 best = 0, best_row = ~0ull;
+        for (u64 r = threadIdx.x; r < rows; r += 1024) {
+            bool skip = false;
+            for (u32 q = 0; q < t; ++q) skip |= taken[q] == r;
+            if (skip) continue;
+            const u64 v = sums[r];
+            if (best_row == ~0ull || v > best) { best = v; best_row = r; }       // (ascending r per thread: ties keep the earlier row)
+        }
+        s_sum[threadIdx.x] = best;
+        s_row[threadIdx.x] = best_row;
+        BLOCK_SYNC();
+        for (u32 d = 512; d; d >>= 1) {
+            if (threadIdx.x < d) {
+                const u64 a = s_sum[threadIdx.x], ar = s_row[threadIdx.x], b = s_sum[threadIdx.x + d], br = s_row[threadIdx.x + d];
+                const bool take_b = ar == ~0ull || (br != ~0ull && (b > a || (b == a && br < ar)));
+                if (take_b) { s_sum[threadIdx.x] = b; s_row[threadIdx.x] = br; }
+            }
+            BLOCK_SYNC();
+        }
+        if (threadIdx.x == 0) { taken[t] = s_row[0]; out[t] = s_row[0]; }
+        BLOCK_SYNC();
+    }
+}

@@ -209,8 +209,10 @@ rp_sample_sym_kernel(SymView v, int k, u64 tile_stride, u32 down, u32 up, u32 ba
         TileCtx<ENC> ctx;
         tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
         const u64 first = tile_start + 16ull * threadIdx.x;
+        SampleTag st;
+        st.init(v, first);
         tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
-            if (fast && first + i < v.n) atomicAdd(&hist[rp_lut_index(rp_prefix(code & mask, down, up), base, sh)], 1u);
+            if (fast && first + i < v.n) atomicAdd(&hist[rp_lut_index(rp_prefix((code & mask) | st.tag(v, first + i), down, up), base, sh)], 1u);
         });
         BLOCK_SYNC();
     }
@@ -240,8 +242,10 @@ hc_hist_kernel(SymView v, u64 s0, u64 s1, int k, RpView r, u32 nb, u32* __restri
         TileCtx<ENC> ctx;
         tile_begin<ENC>(v, tile_start, k, s_code, s_meta, ctx);
         const u64 first = tile_start + 16ull * threadIdx.x;
+        SampleTag st;
+        st.init(v, first);
         tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
-            if (fast && first + i < s1) atomicAdd(&hist[rp_sub(rs, r, rp_prefix(code & mask, r.down, r.up))], 1u);
+            if (fast && first + i < s1) atomicAdd(&hist[rp_sub(rs, r, rp_prefix((code & mask) | st.tag(v, first + i), r.down, r.up))], 1u);
         });
         BLOCK_SYNC();
     }
@@ -367,9 +371,11 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, RpView r, u32* __restrict__
     const u64 first = tile_start + 16ull * threadIdx.x;
     u64 mine[16];
     u32 valid = 0;
+    SampleTag st;
+    st.init(v, first);
     tile_walk<ENC>(ctx, k, [&](int i, u64 code, bool fast) {
         mine[i] = code & mask;
-        if (fast && first + i < s1) valid |= 1u << i;
+        if (fast && first + i < s1) { valid |= 1u << i; mine[i] |= st.tag(v, first + i); }
     });
     auto key = [&](int i) { return mine[i]; };
     auto dig = [&](int i) { return ((valid >> i) & 1u) ? (u32)s_lut[rp_lut_index(rp_prefix(mine[i], r.down, r.up), r.base, r.sh)] : 0u; };

@@ -73,3 +73,56 @@ def sample_metric_rows(file, chunk_size_mb: int = 0, engine=None):
     offsets = list(engine.chunk_offsets(data, chunk)) + [len(data)]
     for a, b in zip(offsets[:-1], offsets[1:]):
         yield from mercat2_metrics.file_metrics_text(data[a:b], engine)
+
+
+# ---------------------------------------------------------------------------------------------------
+# many samples (bin/mercat2.py:411-448: one run_mercat2 task per sample)
+# ---------------------------------------------------------------------------------------------------
+BATCH_BYTES = 96 << 20          # text of one batched pass (about one ordinary 100 MB piece)
+BATCH_SAMPLES = 256
+
+
+def run_samples(samples: dict, out_dir, kmer: int, min_count: int, chunk_size_mb: int = 0, engine=None, quiet: bool = False) -> dict:
+    """Count every sample of ``samples`` ({basename: file}) and write ``<out_dir>/<basename>_counts.tsv`` like the
+    reference's sample loop.  Samples that are ONE piece (on-disk size below the ``-s`` trigger) and small are counted
+    several at a time in a single pass of the engine (``Engine.count_batch``: keys carry the sample index) -- a
+    1.6 M-residue proteome alone is all launch latency on a B200; the others go through ``run_mercat2`` one by one.
+    Returns {basename: tsv path or None}."""
+    from .mercat2_kmers import read_text_bytes
+    engine = engine or _native.default_engine()
+    results, batch, batch_bytes = {}, [], 0
+
+    def flush():
+        nonlocal batch, batch_bytes
+        if not batch:
+            return
+        tables = engine.count_batch([text for _, text in batch], kmer, min_count)
+        for (base, _), table in zip(batch, tables):
+            out_file = os.path.join(out_dir, f"{base}_counts.tsv")
+            rows = table.rows
+            if rows:
+                if not quiet:
+                    print(f"Significant k-mers: {rows}")
+                table.write_tsv(out_file, base)
+                results[base] = out_file
+            else:
+                if not quiet:
+                    print("No significant k-mers found")
+                results[base] = None
+            table.close()
+        batch, batch_bytes = [], 0
+
+    for base, file in samples.items():
+        small = not chunk_trigger(file, chunk_size_mb) and os.stat(file).st_size <= BATCH_BYTES // 8
+        if not small:
+            flush()
+            results[base] = run_mercat2(base, [file], os.path.join(out_dir, f"{base}_counts.tsv"), kmer, min_count,
+                                        chunk_size_mb=chunk_size_mb, engine=engine, quiet=quiet)[1]
+            continue
+        text = read_text_bytes(Path(file))
+        if batch and (batch_bytes + len(text) > BATCH_BYTES or len(batch) >= BATCH_SAMPLES):
+            flush()
+        batch.append((base, text))
+        batch_bytes += len(text)
+    flush()
+    return {base: results[base] for base in samples}

@@ -959,3 +959,70 @@ def test_add_rows_sums_with_counted_text(engine):
                 sample.add_rows(ok, oc)
             got = sample.finish().to_dict()
             assert got == want, f"k={k} c={c} rows_first={rows_first}: {diff_msg(got, want)}"
+
+
+# ---- BASELINE config 5: many protein samples, one table each -------------------------------------------------------
+def test_count_batch_equals_per_sample(engine):
+    """Engine.count_batch (all samples in ONE pass, the sample index rides above the k-mer code) against the oracle on
+    every sample: S5 proteomes, samples without a trailing newline / starting without a header / empty / headers only,
+    nucleotide samples, and a batch that must fall back (lower-case residues -> literal-byte rows)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from tools import synth_s5
+    reset(engine)
+    prot = [synth_s5.sample_text(j, 120) for j in range(9)]
+    odd = [b"MKVLAAGIVGLLLAQWERTY", b"", b">only a header\n", b">p\nMKV*LAAG\nIVGLL*\n>q\nMKVLAAGIVG", prot[0][:-1], b"\n\n>x\n" + prot[1]]
+    for texts, k, c in ((prot, 5, 2), (prot, 5, 10), (prot + odd, 3, 2), (odd + prot[:2], 5, 1), (prot[:1], 5, 2), (prot, 12, 1)):
+        tables = engine.count_batch(texts, k, c)
+        assert len(tables) == len(texts)
+        for j, (text, table) in enumerate(zip(texts, tables)):
+            want = orc.find_kmers_text(text.decode(), k, c)
+            got = table.to_dict()
+            assert got == want, f"sample {j} k={k} c={c}: {diff_msg(got, want)}"
+            if want:
+                assert table.tsv_bytes("s") == orc.tsv_bytes("s", want)
+    reads = [synth_reads(400, 150, seed=300 + j, n_rate=0.0, lower_rate=0.0, genome_len=9000) for j in range(5)]
+    for texts, k, c in ((reads, 21, 2), (reads, 15, 1)):
+        for j, table in enumerate(engine.count_batch(texts, k, c)):
+            want = orc.find_kmers_text(texts[j].decode(), k, c)
+            assert table.to_dict() == want, f"reads sample {j} k={k}: {diff_msg(table.to_dict(), want)}"
+    mixed = [prot[0], prot[1].lower(), b">n\nACGTNNACGTacgt\n", prot[2]]                       # not batchable: per-sample fallback
+    for j, table in enumerate(engine.count_batch(mixed, 4, 2)):
+        want = orc.find_kmers_text(mixed[j].decode(), 4, 2)
+        assert table.to_dict() == want, f"mixed sample {j}: {diff_msg(table.to_dict(), want)}"
+    import torch
+    dev = [torch.from_numpy(np.frombuffer(t, dtype=np.uint8).copy()).cuda() for t in prot[:4]]      # device-resident texts
+    for j, table in enumerate(engine.count_batch(dev, 5, 2)):
+        assert table.to_dict() == orc.find_kmers_text(prot[j].decode(), 5, 2)
+
+
+def test_cfg5_sample_set_pipeline(engine, tmp_path):
+    """64 synthetic proteomes (S5 at a size the oracle finishes in seconds), k=5 -c 10 and -c 2, through
+    pipeline.run_samples (batched passes): every per-sample TSV byte-identical to the oracle's, no file for a sample
+    without survivors; LPT sharding covers every sample exactly once"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from tools import synth_s5
+    from mercat2_b200 import distributed as mcd, pipeline
+    reset(engine)
+    files = {}
+    for j in range(64):
+        path = tmp_path / f"s{j:02d}.faa"
+        path.write_bytes(synth_s5.sample_text(j, 150 if j % 7 else 600))
+        files[f"s{j:02d}"] = str(path)
+    for c in (10, 2):
+        out = tmp_path / f"tsv_{c}"
+        out.mkdir()
+        res = pipeline.run_samples(files, str(out), 5, c, chunk_size_mb=100, engine=engine, quiet=True)
+        assert list(res) == list(files)
+        for base, path in files.items():
+            want = orc.find_kmers(__import__("pathlib").Path(path), 5, c)
+            if want:
+                assert res[base] and open(res[base], "rb").read() == orc.tsv_bytes(base, want), base
+            else:
+                assert res[base] is None and not (out / f"{base}_counts.tsv").exists(), base
+    sizes = [os.stat(f).st_size for f in files.values()]
+    shards = mcd.shard_lpt(sizes, 8)
+    assert sorted(i for sh in shards for i in sh) == list(range(64))
+    loads = [sum(sizes[i] for i in sh) for sh in shards]
+    assert max(loads) <= 1.25 * (sum(sizes) / 8)
