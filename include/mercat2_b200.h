@@ -68,6 +68,15 @@ int mc2_engine_profile(mc2_engine* e, char* buf, uint64_t cap, uint64_t* size);
 int mc2_count_text(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
                    mc2_table** out);
 
+/* mc2_count_text whose table is delivered as packed rows straight into HOST memory: host_rows receives *rows rows of 16
+ * bytes (uint64 order-preserving key, uint64 count), sorted by key; capacity = rows the buffer holds.  For a text too
+ * large for one pass (one global table over tens of Gbp, min_count >= 2) the rows of finished key ranges leave on the
+ * copy stream while later ranges are still being counted, so the download hides behind the counting; use pinned
+ * memory.  Fails with MC2_ERR_LIMIT when the table holds k-mers outside the packed alphabet (decode: mc2_table_info
+ * conventions, 2 bits per base for nucleotide text). */
+int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
+                        uint64_t capacity, uint64_t* rows);
+
 /* Replaces the sample loop of bin/mercat2.py:411-448 (one find_kmers task per sample file, each file smaller than
  * the -s trigger, i.e. ONE piece) for n samples at once: out[j] is the table of texts[j], identical to n calls of
  * mc2_count_text.  The samples are counted in a single pass (keys carry the sample index), which is what makes many

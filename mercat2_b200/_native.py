@@ -33,6 +33,7 @@ SYMBOLS = [
     ("mc2_count_text", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
     ("mc2_count_symbols", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _PP]),
     ("mc2_count_batch", _INT, [_VP, _VP, _VP, C.c_uint32, _INT, _INT, _I64, _VP]),
+    ("mc2_count_text_rows", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _VP, _U64, _PU64]),
     ("mc2_count_sample", _INT, [_VP, _VP, _U64, _INT, _INT, _I64, _U64, _PP, _PU64, _PU64, _U64]),
     ("mc2_chunk_offsets", _INT, [_VP, _VP, _U64, _INT, _U64, _PU64, _U64, _PU64]),
     ("mc2_sample_begin", _INT, [_VP, _INT, _I64, _PP]),
@@ -74,6 +75,8 @@ SYMBOLS = [
     ("mc2_matrix_write_tsv", _INT, [_VP, C.c_char_p, C.c_char_p, _VP, _INT]),
     ("mc2_matrix_free", None, [_VP]),
     ("mc2_merge_tables_reference", _INT, [_VP, _VP, C.c_uint32, C.c_char_p, C.c_char_p, _VP]),
+    ("mc2_table_export_counts", _INT, [_VP, _VP, _VP]),
+    ("mc2_matrix_top_rows", _INT, [_VP, C.c_uint32, _VP, C.POINTER(C.c_uint32)]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -226,6 +229,22 @@ class Table:
         self.packed_to_host(keys.ctypes.data, counts.ctypes.data, n)
         return keys, counts
 
+    def counts_array(self) -> np.ndarray:
+        """The count vector of the table (sorted k-mer order) without the k-mer text: what the alpha-diversity metrics read."""
+        counts = np.empty(self.rows, dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_export_counts(self._h, counts.ctypes.data, None))
+        return counts
+
+    def count_spectrum(self) -> dict:
+        """Reductions of the count vector computed on the device: observed k-mers, sum and sum of squares of the counts,
+        largest count and the number of k-mers seen exactly 1..10 times."""
+        sp = np.zeros(16, dtype=np.uint64)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_table_export_counts(self._h, None, sp.ctypes.data))
+        return {"observed": int(sp[0]), "total": int(sp[1]), "sum_squares": int(sp[2]) + (int(sp[3]) << 64), "max": int(sp[4]),
+                "seen_exactly": {i + 1: int(sp[5 + i]) for i in range(10)}}
+
     def lower_bound(self, splitters) -> list:
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
         cuts = np.zeros(len(sp), dtype=np.uint64)
@@ -286,6 +305,15 @@ class Matrix:
         _check(lib, lib.mc2_matrix_export(self._h, kmers.ctypes.data, counts.ctypes.data))
         return kmers, counts
 
+    def top_rows(self, top: int = 5) -> list:
+        """Row indices of the `top` k-mers with the largest count sum (= mean) over the samples, largest first, earlier
+        rows winning ties (the selection of lib/mercat2_figures.py:50-65)."""
+        out = np.zeros(max(top, 1), dtype=np.uint64)
+        found = C.c_uint32(0)
+        lib = self._engine._lib
+        _check(lib, lib.mc2_matrix_top_rows(self._h, top, out.ctypes.data, C.byref(found)))
+        return [int(x) for x in out[:found.value]]
+
     def write_tsv(self, path, corner: str, names, transposed: bool = False):
         names = [str(n).encode() for n in names]
         if len(names) != self.samples:
@@ -344,6 +372,14 @@ class Engine:
         out = C.c_void_p()
         _check(self._lib, self._lib.mc2_count_text(self._h, addr, n, space, k, min_count, C.byref(out)))
         return Table(self, out)
+
+    def count_text_rows(self, data, k: int, min_count: int, rows_addr: int, capacity: int) -> int:
+        """count_text with the table delivered as packed rows (16 bytes: key, count; sorted) into host memory at
+        `rows_addr` (room for `capacity` rows; pinned memory lets the download overlap the counting).  Returns the rows."""
+        addr, n, space, keep = _as_buffer(data)
+        rows = C.c_uint64(0)
+        _check(self._lib, self._lib.mc2_count_text_rows(self._h, addr, n, space, k, min_count, rows_addr or None, capacity, C.byref(rows)))
+        return int(rows.value)
 
     def count_batch(self, texts, k: int, min_count: int) -> list:
         """One table per text (each text = one sample file smaller than the -s trigger), counted in a single pass over

@@ -45,6 +45,18 @@ static void count_key_range_sorted(mc2_engine* e, mc2_sample* s, const u64* keys
 
 static void prefetch_next_count_pass(mc2_engine* e, mc2_sample* s);
 
+// Where the sorted rows of the groups of ONE very large chunk go when the host does not wait for each group
+// (min_count >= 2): back to back, as 16-byte rows, into the part of the level-0 key array whose keys have already been
+// consumed -- a group of n keys has at most n / 2 surviving rows, so the rows of groups 0..g (16 B each) always fit in
+// front of group g + 1's keys (8 B each).  counters (device): [0] rows so far, [1] overflow keys, [2] flagged keys
+// (bitmap mode), [3] keys of all groups, [4] overflowed sub-buckets.
+struct GroupSink {
+    RcRow* arena;
+    ull* counters;
+    u64* ovf_keys;
+    u64 ovf_cap;
+};
+
 struct KeySpan {               // keys already extracted (one level-0 group of a very large chunk, or keys received from other ranks)
     const u64* keys;
     u64 n;
@@ -114,7 +126,7 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
         shist.p = w.shist.get(e, RP_LUT);
         CUDA_CHECK(cudaMemsetAsync(shist.p, 0, RP_LUT * 4, e->stream));
         if (ks) {
-            const u64 stride = std::max<u64>(1, ks->n / RP_SAMPLE_WINDOWS);
+            const u64 stride = std::max<u64>(1, ks->n / (RP_SAMPLE_WINDOWS / 4));       // (a narrow key range: a quarter of the sample does)
             const u64 grid = std::min<u64>(div_up(div_up(ks->n, stride), HK_HIST_THREADS), (u64)e->num_sms * 2);
             if (ks->n) LAUNCH(e, rp_sample_keys_kernel, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, 0, ks->keys, ks->n, stride, pl.down, pl.up, pl.base, pl.sh, shist.p);
         } else if (!pvs.empty()) {
@@ -146,7 +158,8 @@ static u64 range_batch_max(const mc2_engine* e, const mc2_sample* s) {
 // symbol stream `v` (encoding ENC), from the packed nucleotide stream `pv`, or from a key array `ks`.  The surviving
 // rows are appended to the sample as ONE part that is already sorted by key.
 template <int ENC>
-static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr) {
+static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const PackedView* pv = nullptr, const KeySpan* ks = nullptr,
+                               const GroupSink* sink = nullptr) {
     range_kernel_attrs(e);
     const int k = s->k;
     int sample_bits = 0;                                         // batched samples: the sample index rides above the k-mer code
@@ -169,7 +182,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     if (pv) pvs.push_back(*pv);
     build_plan<ENC>(e, k, pvs, ks, v, cap, pl, 1);
     const RpView rv = pl.view();
-    struct Tail { ull total, rows; u32 ovf_n, pad; };
+    struct Tail { ull total, rows, flagged; u32 ovf_n, pad; };
     // (the bucket histogram and the result counters share one allocation: one memset per chunk instead of two)
     RangeWork& w = range_work(e);
     struct { u32* p; } ghist{w.ghist.get(e, nb + sizeof(Tail) / 4)}, sub_base{w.sub_base.get(e, nb + 1)}, cur1{w.cur1.get(e, nb1)}, cur2{w.cur2.get(e, nb)},
@@ -235,12 +248,23 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
                 h[4], h[5], h[6], h[7], h[8], ((pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) || b1 || b2) ? "  MISMATCH" : "");
     }
     const unsigned cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
+    ull* flagged_dev = sink ? sink->counters + 2 : &tail.p->flagged;
     if (mode == 1)
         LAUNCHN(e, "rc_count_kernel<1>", rc_count_kernel<1>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,
-                ovf_list.p, &tail.p->ovf_n);
+                ovf_list.p, &tail.p->ovf_n, flagged_dev);
     else
         LAUNCHN(e, "rc_count_kernel<0>", rc_count_kernel<0>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,
-                ovf_list.p, &tail.p->ovf_n);
+                ovf_list.p, &tail.p->ovf_n, flagged_dev);
+    if (sink) {
+        // no host round trip: rows go behind the rows of the earlier groups (device counter), overflowed sub-buckets are
+        // copied aside by the device, the statistics accumulate in the sink's counters
+        LAUNCH(e, rc_offsets_kernel, 1, 1024, 0, (const u32*)rows.p, nb, row_off.p, sink->counters, &tail.p->rows, 1);
+        LAUNCH(e, rc_gather_kernel, (unsigned)std::min<u64>(div_up(nb, 8), (u64)e->num_sms * 8), 256, 0, (const RcRow*)slots, (const u32*)sub_base.p,
+               (const u32*)rows.p, (const u64*)row_off.p, nb, c, (u64*)nullptr, (u64*)nullptr, sink->arena);
+        LAUNCH(e, rc_overflow_collect_kernel, 64, 256, 0, (const u32*)ovf_list.p, (const u32*)&tail.p->ovf_n, (const u32*)sub_base.p, (const u64*)keys2.p,
+               (const ull*)&tail.p->total, sink->ovf_keys, sink->ovf_cap, sink->counters);
+        return;
+    }
     LAUNCH(e, rc_offsets_kernel, 1, 1024, 0, (const u32*)rows.p, nb, row_off.p, (ull*)nullptr, &tail.p->rows, 0);
     if (pv && !ks) prefetch_next_count_pass(e, s);               // rides on the synchronisation below
     const Tail t = read_scalar<Tail>(e, tail.p);
@@ -266,10 +290,10 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
         fprintf(stderr, "[range] survivors: tables %llu (+%u overflowed buckets) sort %llu%s\n", (ull)t.rows, t.ovf_n, (ull)ref_rows,
                 (!t.ovf_n && ref_rows != t.rows) ? "  MISMATCH" : "");
     }
-    // duplicate-rich data (survivors carry a quarter of the keys or more): the following chunks / groups of the sample
+    // duplicate-rich data (at least half of the keys found their bitmap bit already set): the following chunks / groups of the sample
     // skip the bitmap pre-filter.  If that makes tables overflow, go back.
     if (c >= 2) {
-        if (mode == 1 && t.rows * (u64)c * 4 >= t.total && t.total >= 65536) s->dup_rich = true;
+        if (mode == 1 && t.flagged * 2 >= t.total && t.total >= 65536) s->dup_rich = true;      // half of the keys are repeats
         if (mode == 0 && (u64)t.ovf_n * 50 > nb) s->dup_rich = false;
     }
     if (t.ovf_n) {
@@ -620,7 +644,7 @@ static u32 level0_groups(u64 cap, u64 hash_max) {
 // two-level pipeline per group.  All occurrences of a key meet in one group, so the -c filter stays exact for the
 // whole chunk, and the groups' sorted rows follow each other in key order.  Returns false (nothing counted) when the
 // keys do not fit in free device memory.
-static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, const KeySpan* ks, u64 hash_max) {
+static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<PackedView>& pvs, const KeySpan* ks, u64 hash_max, bool allow_async = true) {
     u64 cap = ks ? ks->n : 0;
     for (auto& pv : pvs) cap += pv.n;
     const u32 g0 = level0_groups(cap, hash_max);
@@ -628,13 +652,103 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     Level0 l0;
     if (!level0_partition(e, s->k, pvs, ks, g0, hash_max, 3 * 8 * div_up(cap, g0) * 2, l0)) return false;
     PhaseTimer pt(e);
-    for (u32 g = 0; g < g0; ++g) {
-        const u64 n = l0.gbase[g + 1] - l0.gbase[g];
-        if (!n) continue;
-        KeySpan span{l0.keys0 + l0.gbase[g], n, l0.bounds[g], std::max<u64>(l0.bounds[g + 1], l0.bounds[g] + 1)};
-        sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
+    auto span_of = [&](u32 g) {
+        return KeySpan{l0.keys0 + l0.gbase[g], l0.gbase[g + 1] - l0.gbase[g], l0.bounds[g], std::max<u64>(l0.bounds[g + 1], l0.bounds[g] + 1)};
+    };
+    const u64 total = l0.gbase[g0];
+    if (s->c < 2 || !allow_async || e->opt_group_sync) {
+        // min_count 1 (a group may emit as many 16-byte rows as it has 8-byte keys): one host round trip per group
+        for (u32 g = 0; g < g0; ++g) {
+            const KeySpan span = span_of(g);
+            if (span.n) sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span);
+        }
+        pt.mark("groups");
+        return true;
     }
+    // min_count >= 2: the groups are enqueued back to back; their rows collect in the consumed front of the key array
+    DBuf<ull> counters(e, 8);
+    counters.zero();
+    const u64 ovf_cap = std::max<u64>(l0.gmax, total / 32) + 4096;
+    DBuf<u64> ovf_keys(e, ovf_cap);
+    GroupSink sink{reinterpret_cast<RcRow*>(l0.keys0), counters.p, ovf_keys.p, ovf_cap};
+    HostRowSink* hs = e->host_rows.active && !e->host_rows.failed ? &e->host_rows : nullptr;
+    std::vector<cudaEvent_t> evs;
+    u64 copied = 0;
+    u32 next_copy = 0, launched = 0;
+    ull* pin = nullptr;
+    if (hs) {
+        if (!e->pin_groups) CUDA_CHECK(cudaMallocHost((void**)&e->pin_groups, (HC_MAX_NB1 + 8) * sizeof(ull)));
+        pin = e->pin_groups;
+    }
+    auto drain = [&](bool all) {
+        // hand the rows of finished groups to the copy stream (their count arrived with an earlier event)
+        while (hs && next_copy < launched && (all || cudaEventQuery(evs[next_copy]) == cudaSuccess)) {
+            if (all) CUDA_CHECK(cudaEventSynchronize(evs[next_copy]));
+            const u64 upto = pin[next_copy];
+            if (upto > hs->capacity) { hs->failed = true; hs = nullptr; break; }
+            if (upto > copied) {
+                CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, evs[next_copy], 0));
+                CUDA_CHECK(cudaMemcpyAsync((RcRow*)hs->rows + copied, sink.arena + copied, (upto - copied) * sizeof(RcRow), cudaMemcpyDeviceToHost, e->copy_stream));
+                e->d2h_bytes += (upto - copied) * sizeof(RcRow);
+                copied = upto;
+            }
+            ++next_copy;
+        }
+    };
+    bool mode_known = s->dup_rich || e->opt_count_mode >= 0;
+    for (u32 g = 0; g < g0; ++g) {
+        const KeySpan span = span_of(g);
+        if (!span.n) continue;
+        sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span, &sink);
+        if (!mode_known) {                                       // one look at the first group decides the counting mode of the rest
+            ull c5[8];
+            d2h(e, c5, (const ull*)counters.p, 8);
+            if (c5[2] * 2 >= c5[3] && c5[3] >= 65536) s->dup_rich = true;
+            mode_known = true;
+        }
+        if (hs) {
+            CUDA_CHECK(cudaMemcpyAsync(&pin[launched], counters.p, sizeof(ull), cudaMemcpyDeviceToHost, e->stream));
+            cudaEvent_t ev = e->get_event();
+            CUDA_CHECK(cudaEventRecord(ev, e->stream));
+            evs.push_back(ev);
+            ++launched;
+            drain(false);
+        }
+    }
+    ull fin[8];
+    d2h(e, fin, (const ull*)counters.p, 8);
     pt.mark("groups");
+    drain(true);
+    for (auto ev : evs) e->ev_pool.push_back(ev);
+    const u64 R = fin[0], ovf_m = fin[1];
+    if (ovf_m > ovf_cap) {
+        // more overflowed keys than the side array holds (heavily skewed data): redo the chunk with one round trip per group
+        CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+        if (e->host_rows.active) e->host_rows.failed = true;
+        l0 = Level0();
+        return sparse_chunk_big(e, s, pvs, ks, hash_max, false);
+    }
+    e->ovf_buckets += fin[4];
+    if ((u64)fin[4] * 200 > div_up(total, std::max<u64>(1, e->opt_hash_bucket_keys)) && s->bucket_scale > 0.3) s->bucket_scale *= 0.8;
+    const bool host_done = hs && !ovf_m;
+    if (hs && ovf_m) e->host_rows.failed = true;               // rows of the sort path would have to be merged in: the caller falls back
+    if (host_done) {
+        CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+        e->host_rows.delivered = R;
+        e->host_rows.complete = true;
+    } else if (R) {
+        CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+        FastPart part;
+        part.n = R;
+        part.sorted = true;
+        part.keys.alloc(e, R);
+        part.counts.alloc(e, R);
+        LAUNCH(e, rc_split_rows_kernel, (unsigned)div_up(R, 256), 256, 0, (const RcRow*)sink.arena, R, part.keys.p, part.counts.p);
+        s->fast.push_back(std::move(part));
+    }
+    if (ovf_m) count_key_range_sorted(e, s, ovf_keys.p, ovf_m, 2 * s->k);
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));               // (the key array may be handed to the next chunk)
+    pt.mark("rows");
     return true;
 }
 
@@ -774,9 +888,10 @@ static bool count_chunk_fast_nt(mc2_engine* e, mc2_sample* s, const u8* dtext, u
     std::vector<PackedView> pvs;
     for (auto& sp : spans)
         if (sp.nsym) pvs.push_back(PackedView{sp.codes.p, sp.bad, sp.nsym});
-    if (!sparse_chunk_big(e, s, pvs, nullptr, hash_max)) return false;
     const FnStats fs3 = read_scalar<FnStats>(e, st.p);
     *need_exceptions = (fs3.packed2 >> 32) != 0;
+    if (*need_exceptions) e->host_rows.failed = true;            // literal-byte rows will join the table: no streaming of packed rows
+    if (!sparse_chunk_big(e, s, pvs, nullptr, hash_max)) { *need_exceptions = false; return false; }
     return true;
 }
 

@@ -28,6 +28,13 @@ static thread_local std::string g_err;
 // engine
 // =====================================================================================================
 struct RangeWork;
+// Rows of a count delivered straight to caller-owned host memory (mc2_count_text_rows): the groups of a very large chunk
+// stream their finished rows out on the copy stream while later groups are still being counted.
+struct HostRowSink {
+    bool active = false, failed = false, complete = false;
+    void* rows = nullptr;                  // 16 bytes per row: key, count
+    u64 capacity = 0, delivered = 0;
+};
 struct mc2_engine {
     int device = 0;
     RangeWork* work = nullptr;             // device workspace of the range-partition path, grown on demand and reused by every chunk
@@ -46,6 +53,9 @@ struct mc2_engine {
     int opt_parse_single = 0;              // packed lane: 1 = one pass over the text with chained look-back (measured slower: 0.39 vs 0.28 ms per 100 MiB)
     u64 opt_file_piece = 32ull << 20;      // bytes per piece of the streaming file reader
     u64 opt_span_bytes = 1ull << 30;       // the packed lane parses a chunk in spans of about this many bytes
+    int opt_group_sync = 0;                // very large chunks: 1 = one host round trip per level-0 group (the min_count 1 path) even for min_count >= 2
+    HostRowSink host_rows;
+    unsigned long long* pin_groups = nullptr;   // pinned: per-group row counters of the streaming download
     int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)
     int opt_sparse_algo = 0;               // 0 auto (range partition + shared-memory tables), 1 radix sort, 2 range partition
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
@@ -418,6 +428,7 @@ void mc2_engine_destroy(mc2_engine* e) {
         if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
     }
     if (e->pin_small) cudaFreeHost(e->pin_small);
+    if (e->pin_groups) cudaFreeHost(e->pin_groups);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     delete e->work;
@@ -453,6 +464,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "count_mode") e->opt_count_mode = (int)value;
+    else if (n == "group_sync") e->opt_group_sync = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
     else if (n == "parse_single") e->opt_parse_single = (int)value;
     else if (n == "prefetch_pass") e->opt_prefetch_pass = (int)value;
@@ -1395,6 +1407,57 @@ int mc2_count_batch(mc2_engine* e, const void* const* texts, const uint64_t* nby
         for (u32 j = 0; j < n; ++j) { if (out[j]) { delete out[j]; out[j] = nullptr; } }
         throw;
     }
+    API_END
+}
+
+int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
+                        uint64_t capacity, uint64_t* rows) {
+    API_BEGIN
+    check_count_args(e, text, nbytes, k);
+    if (!rows || (capacity && !host_rows)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    mc2_sample s;
+    s.e = e;
+    s.k = k;
+    s.c = min_count < 1 ? 1 : (u64)min_count;
+    CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
+    e->host_rows = HostRowSink();
+    e->host_rows.active = true;
+    e->host_rows.rows = host_rows;
+    e->host_rows.capacity = capacity;
+    HostRowSink hs;
+    try {
+        DBuf<u8> holder;
+        const u8* d = to_device(e, text, nbytes, space, holder);
+        if (nbytes) count_chunk(e, &s, d, nbytes);
+        hs = e->host_rows;
+        e->host_rows = HostRowSink();
+    } catch (...) {
+        cudaStreamSynchronize(e->copy_stream);
+        e->host_rows = HostRowSink();
+        throw;
+    }
+    if (hs.complete && s.fast.empty() && s.wide.empty() && s.plan.path == PATH_SPARSE) {
+        *rows = hs.delivered;                                   // every row already sits in the caller's buffer
+    } else {
+        std::unique_ptr<mc2_table> t(sample_finish(&s));
+        if (t->wide.n) throw Mc2Error(MC2_ERR_LIMIT, "the table holds literal-byte rows (k-mers outside the packed alphabet): use mc2_count_text");
+        if (t->fast.n > capacity) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+        if (t->fast.n) {
+            DBuf<RcRow> aos(e, t->fast.n);
+            LAUNCH(e, rc_join_rows_kernel, (unsigned)div_up(t->fast.n, 256), 256, 0, (const u64*)t->fast.keys.p, (const u64*)t->fast.counts.p, (u64)t->fast.n, aos.p);
+            CUDA_CHECK(cudaMemcpyAsync(host_rows, aos.p, t->fast.n * sizeof(RcRow), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            e->d2h_bytes += t->fast.n * sizeof(RcRow);
+        }
+        *rows = t->fast.n;
+    }
+    CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+    CUDA_CHECK(cudaEventSynchronize(e->ev1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->device_us = ms * 1000.0;
+    e->resolve_profile();
     API_END
 }
 

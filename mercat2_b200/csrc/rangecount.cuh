@@ -553,7 +553,8 @@ __device__ __forceinline__ void rc_insert0(ull key, ull* tkeys, u32* tcnt, u32* 
 template <int MODE>
 __global__ void __launch_bounds__(RC_THREADS, 2)
 rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u32 c, RpView r,
-                RcRow* __restrict__ out, u32* __restrict__ rows, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n) {
+                RcRow* __restrict__ out, u32* __restrict__ rows, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n,
+                ull* __restrict__ flagged_total /*MODE 1: keys that found their bitmap bit set (repeats + ~1 % false positives)*/) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* bm = reinterpret_cast<u32*>(dyn);                                               // region A
     ull* skey = reinterpret_cast<ull*>(dyn);
@@ -585,6 +586,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
     }
     BLOCK_SYNC();
     u32 par = 0;
+    ull cta_flagged = 0;
     for (; b < nb; b += gridDim.x, par ^= 1u) {
         u32* scal = s_scal[par];
         const u32 n = n_n, lo = lo_n;
@@ -633,6 +635,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         }
         BLOCK_SYNC();
         bool ovf = scal[2] != 0;
+        if (MODE == 1) cta_flagged += scal[5];
         const u32 nd = MODE == 1 ? min(scal[1], (u32)RC_CLAIM_CAP) : RC_SLOTS;      // table slots the emit pass visits
         bool exact = MODE == 0;
         if (MODE == 1) {
@@ -766,6 +769,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         }
         BLOCK_SYNC();
     }
+    if (MODE == 1 && threadIdx.x == 0 && flagged_total && cta_flagged) atomicAdd(flagged_total, cta_flagged);
 }
 
 // ---- survivor slots -> one dense array ----------------------------------------------------------------------------------
@@ -803,9 +807,38 @@ rc_gather_kernel(const RcRow* __restrict__ slots, const u32* __restrict__ sub_ba
         }
     }
 }
+// Device-driven handling of overflowed sub-buckets when the host does not wait for every group of a very large chunk:
+// their keys are appended to one array (counted by the sort path after the last group).  counters: [1] overflow keys,
+// [3] keys of all groups, [4] overflowed sub-buckets.  Keys beyond `cap` are not copied (the host sees [1] > cap and
+// redoes the chunk group by group).
+__global__ void __launch_bounds__(256)
+rc_overflow_collect_kernel(const u32* __restrict__ ovf_list, const u32* __restrict__ ovf_n, const u32* __restrict__ sub_base, const u64* __restrict__ keys2,
+                           const ull* __restrict__ group_total, u64* __restrict__ ovf_keys, u64 cap, ull* __restrict__ counters) {
+    __shared__ ull s_at;
+    const u32 n_ovf = *ovf_n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&counters[3], *group_total);
+        if (n_ovf) atomicAdd(&counters[4], (ull)n_ovf);
+    }
+    for (u32 i = blockIdx.x; i < n_ovf; i += gridDim.x) {
+        const u32 b = ovf_list[i];
+        const u32 lo = sub_base[b], n = sub_base[b + 1] - lo;
+        if (threadIdx.x == 0) s_at = atomicAdd(&counters[1], (ull)n);
+        BLOCK_SYNC();
+        const ull at = s_at;
+        if (at + n <= cap)
+            for (u32 j = threadIdx.x; j < n; j += 256) ovf_keys[at + j] = keys2[lo + j];
+        BLOCK_SYNC();
+    }
+}
 __global__ void rc_split_rows_kernel(const RcRow* __restrict__ in, u64 n, u64* __restrict__ keys, u64* __restrict__ counts) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const RcRow row = in[i]; keys[i] = row.key; counts[i] = row.count; }
+}
+
+__global__ void rc_join_rows_kernel(const u64* __restrict__ keys, const u64* __restrict__ counts, u64 n, RcRow* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { RcRow row; row.key = keys[i]; row.count = counts[i]; out[i] = row; }
 }
 
 // ---- debug: every key of the level-1 / level-2 arrays must sit in the range of its own bucket -------------------

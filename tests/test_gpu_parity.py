@@ -1026,3 +1026,76 @@ def test_cfg5_sample_set_pipeline(engine, tmp_path):
     assert sorted(i for sh in shards for i in sh) == list(range(64))
     loads = [sum(sizes[i] for i in sh) for sh in shards]
     assert max(loads) <= 1.25 * (sum(sizes) / 8)
+
+
+def test_diversity_inputs_and_top_kmers(engine):
+    """row N4: the count vector and its device-side abundance spectrum against numpy on the oracle's table; the top-5
+    k-mers by mean count against the reference's streaming selection restated on the merged table"""
+    from mercat2_b200 import mercat2_diversity
+    reset(engine)
+    texts = {f"s{j}": synth_reads(2500, 150, seed=400 + j, n_rate=0.002, lower_rate=0.01, genome_len=30000 + 7000 * j) for j in range(4)}
+    tables = {name: engine.count_text(text, 9, 2) for name, text in texts.items()}
+    for name, text in texts.items():
+        want = orc.find_kmers_text(text.decode(), 9, 2)
+        vec = np.array([want[key] for key in sorted(want)], dtype=np.uint64)
+        inputs = mercat2_diversity.alpha_inputs(tables[name])
+        assert np.array_equal(inputs["counts"], vec)
+        sp = inputs["spectrum"]
+        assert sp["observed"] == len(vec) and sp["total"] == int(vec.sum()) and sp["max"] == int(vec.max())
+        assert sp["sum_squares"] == sum(int(x) ** 2 for x in vec.tolist())
+        assert sp["seen_exactly"] == {i: int((vec == i).sum()) for i in range(1, 11)}
+    names, top = mercat2_diversity.top_kmers(tables, 5, engine)
+    dicts = {name: orc.find_kmers_text(texts[name].decode(), 9, 2) for name in names}
+    union = sorted(set().union(*[set(d) for d in dicts.values()]))
+    keep = []                                              # lib/mercat2_figures.py:50-65, on the sorted-union table
+    for kmer in union:
+        row = [dicts[n].get(kmer, 0) for n in names]
+        if len(keep) < 5:
+            keep.append((kmer, row))
+        else:
+            keep.sort(key=lambda kr: sum(kr[1]) / len(kr[1]))
+            if sum(row) / len(row) > sum(keep[0][1]) / len(keep[0][1]):
+                keep[0] = (kmer, row)
+    assert sorted(top) == sorted(keep)
+    assert [sum(r) for _, r in top] == sorted((sum(r) for _, r in top), reverse=True)
+    for t in tables.values():
+        t.close()
+
+
+def test_big_chunk_async_groups_and_row_streaming(engine):
+    """a very large chunk with min_count >= 2: the level-0 groups are enqueued without a host round trip, their rows
+    collect in the consumed front of the key array, overflowed sub-buckets are copied aside by the device; and
+    count_text_rows streams the rows of finished groups to (pinned) host memory.  All variants must give numpy's table."""
+    import torch
+    reset(engine)
+    text, codes = numpy_piece(60_000, 3_000_000, seed=17, dup_every=4, dup_copies=2)        # 7.2 M windows
+    dev = torch.from_numpy(text).cuda()
+    for c in (2, 3):
+        want_k, want_c = numpy_table(codes, 31, c)
+        for opts in ({"batch_symbols": 1 << 20}, {"batch_symbols": 1 << 20, "group_sync": 1}, {"batch_symbols": 1 << 20, "count_mode": 0},
+                     {"batch_symbols": 1 << 20, "hash_bucket_keys": 1_000_000, "count_mode": 0},       # tables overflow -> device-side collection -> sort path
+                     {"batch_symbols": 1 << 19, "hash_bucket_keys": 1_000_000, "count_mode": 1}):
+            for name, value in opts.items():
+                engine.set_option(name, value)
+            try:
+                table = engine.count_text(dev, 31, c)
+                got_k, got_c = table.packed_arrays()
+                table.close()
+                rows = torch.empty((len(want_k) + 8, 2), dtype=torch.int64, pin_memory=True)
+                n = engine.count_text_rows(dev, 31, c, rows.data_ptr(), rows.shape[0])
+            finally:
+                engine.set_option("group_sync", 0)
+                reset(engine)
+            assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c), (c, opts)
+            got = rows[:n].numpy().view(np.uint64)
+            assert n == len(want_k) and np.array_equal(got[:, 0], want_k) and np.array_equal(got[:, 1], want_c), (c, opts, n)
+    # a text with k-mers outside ACGT cannot be delivered as packed rows; small texts take the ordinary path
+    import mercat2_b200
+    rows = torch.empty((1024, 2), dtype=torch.int64, pin_memory=True)
+    with pytest.raises(mercat2_b200.Mc2Error):
+        engine.count_text_rows(b">r\nACGTNACGTACGTNNACGT\n", 3, 1, rows.data_ptr(), 1024)
+    n = engine.count_text_rows(b">r\nACGTACGTACGT\n", 3, 2, rows.data_ptr(), 1024)
+    want = orc.find_kmers_text(">r\nACGTACGTACGT\n", 3, 2)
+    assert n == len(want)
+    with pytest.raises(mercat2_b200.Mc2Error):
+        engine.count_text_rows(dev, 31, 2, rows.data_ptr(), 16)                                  # buffer too small
