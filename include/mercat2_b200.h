@@ -237,6 +237,16 @@ int mc2_matrix_top_rows(mc2_matrix* m, uint32_t top, uint64_t* rows_out, uint32_
 int mc2_merge_tables_reference(mc2_engine* e, mc2_table* const* tables, uint32_t n, const char* path, const char* corner,
                                const char* const* names);
 
+/* ---- text transforms ahead of the hot path ------------------------------------------------
+ * The transformed text stays on the device (mc2_text_info: pointer + size, usable as `text` with MC2_DEVICE in every
+ * counting call) and can be downloaded for the artefact the reference keeps on disk (clean/<base>.fna.gz).
+ * mc2_fastq_to_fasta replaces fq2fa's `sed -n '1~4s/^@/>/p;2~4p'` (lib/mercat2_fasta.py:175-198). */
+typedef struct mc2_text mc2_text;
+int mc2_fastq_to_fasta(mc2_engine* e, const void* text, uint64_t nbytes, int space, mc2_text** out);
+int mc2_text_info(const mc2_text* t, const void** device_ptr, uint64_t* nbytes);
+int mc2_text_export(mc2_text* t, void* host, uint64_t capacity);
+void mc2_text_free(mc2_text* t);
+
 /* ---- protein metrics ----------------------------------------------------------------------------
  * Replaces the numeric part of plot_sample_metrics (lib/mercat2_figures.py:157-183) and
  * predict_isoelectric_point_ProMoST / calculate_MW / calculate_hydro (lib/mercat2_metrics.py:57-170)

@@ -77,6 +77,10 @@ SYMBOLS = [
     ("mc2_merge_tables_reference", _INT, [_VP, _VP, C.c_uint32, C.c_char_p, C.c_char_p, _VP]),
     ("mc2_table_export_counts", _INT, [_VP, _VP, _VP]),
     ("mc2_matrix_top_rows", _INT, [_VP, C.c_uint32, _VP, C.POINTER(C.c_uint32)]),
+    ("mc2_fastq_to_fasta", _INT, [_VP, _VP, _U64, _INT, _PP]),
+    ("mc2_text_info", _INT, [_VP, _PP, _PU64]),
+    ("mc2_text_export", _INT, [_VP, _VP, _U64]),
+    ("mc2_text_free", None, [_VP]),
     ("mc2_protein_metrics", _INT, [_VP, _VP, _U64, _INT, _PP]),
     ("mc2_sequence_metrics", _INT, [_VP, _VP, _PU64, _U64, _PP]),
     ("mc2_metrics_records", _U64, [_VP]),
@@ -125,7 +129,9 @@ def _check(lib, status):
 
 
 def _as_buffer(data):
-    """-> (address, nbytes, memspace, keepalive) for bytes-like, numpy or CUDA torch tensors."""
+    """-> (address, nbytes, memspace, keepalive) for bytes-like, numpy, CUDA torch tensors or a DeviceText."""
+    if isinstance(data, DeviceText):
+        return data.ptr, data.nbytes, MC2_DEVICE, data
     if hasattr(data, "is_cuda"):                      # torch tensor (uint8), host or device
         t = data.contiguous()
         if t.element_size() != 1:
@@ -143,6 +149,32 @@ def _as_buffer(data):
     mv = memoryview(data)
     a = np.frombuffer(mv, dtype=np.uint8)
     return a.ctypes.data, a.size, MC2_HOST, (mv, a)
+
+
+class DeviceText:
+    """A text produced on the device (e.g. FASTA converted from FASTQ): usable as input of every counting call."""
+
+    def __init__(self, engine, handle):
+        self._engine, self._h = engine, handle
+        ptr, n = C.c_void_p(), C.c_uint64(0)
+        _check(engine._lib, engine._lib.mc2_text_info(handle, C.byref(ptr), C.byref(n)))
+        self.ptr, self.nbytes = ptr.value or 0, int(n.value)
+
+    def to_bytes(self) -> bytes:
+        buf = bytearray(self.nbytes)
+        if self.nbytes:
+            ref = (C.c_char * self.nbytes).from_buffer(buf)
+            _check(self._engine._lib, self._engine._lib.mc2_text_export(self._h, ref, self.nbytes))
+            del ref
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._engine._h:
+            self._engine._lib.mc2_text_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Table:
@@ -474,6 +506,13 @@ class Engine:
         out = C.c_void_p()
         _check(self._lib, self._lib.mc2_keys_open(self._h, addr, n, space, k, C.byref(out)))
         return Keys(self, out)
+
+    def fastq_to_fasta(self, data) -> DeviceText:
+        """FASTQ text -> FASTA text on the device (lib/mercat2_fasta.py:175-198: `sed -n '1~4s/^@/>/p;2~4p'`)."""
+        addr, n, space, keep = _as_buffer(data)
+        out = C.c_void_p()
+        _check(self._lib, self._lib.mc2_fastq_to_fasta(self._h, addr, n, space, C.byref(out)))
+        return DeviceText(self, out)
 
     def count_exceptions(self, data, k: int) -> Table:
         """Unfiltered table of the windows that hold a symbol outside ACGT (literal-byte rows)."""

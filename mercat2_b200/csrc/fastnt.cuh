@@ -345,13 +345,15 @@ fn_hist_kernel(PackedView pv, int k, RpView r, u32 nb, u32* __restrict__ ghist) 
     const u32 hist32 = (u32)__cvta_generic_to_shared(hist);
     const u32 pm = fn_pmask(k);
     const u64 nwords = (pv.n + 15) >> 4;
+    const bool lin = *r.linear != 0;
     for (u64 g = (u64)blockIdx.x * FN_HIST_THREADS + threadIdx.x; g < nwords; g += (u64)gridDim.x * FN_HIST_THREADS) {
         FnWords w;
         const u32 valid = fn_load_windows(pv, g, k, w);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {                     // predicated reduction: no branch per window
             const u32 p = fn_hi(w, j) & pm;
-            smem_red_inc_if(hist32 + 4u * (FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)), (valid >> j) & 1u);
+            const u32 b1 = lin ? rp_b1_linear(r, p) : rp_b1(rs, r, p);
+            smem_red_inc_if(hist32 + 4u * (FINE ? b1 * HC_NB2 + rp_b2(rs.l1[b1], p) : b1), (valid >> j) & 1u);
         }
     }
     BLOCK_SYNC();
@@ -546,7 +548,11 @@ fn_scatter1_kernel(PackedView pv, int k, RpView r, u32* __restrict__ cur1, u64* 
     const u32 valid = fn_load_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, w);
     // keys and digits are recomputed (funnel shifts) wherever they are needed instead of living in 32 registers
     auto key = [&](int i) { return fn_key(w, i, rshift); };
-    auto dig = [&](int i) { return (u32)s_lut[rp_lut_index(fn_hi(w, i) & pm, r.base, r.sh)]; };
+    const bool lin = *r.linear != 0;
+    auto dig = [&](int i) {
+        const u32 p = fn_hi(w, i) & pm;
+        return lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)];
+    };
     hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
 }
 

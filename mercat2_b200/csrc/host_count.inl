@@ -67,8 +67,9 @@ struct KeySpan {               // keys already extracted (one level-0 group of a
 struct RpPlan {
     u16* lut = nullptr;
     uint2* l1 = nullptr;
-    u32 base = 0, sh = 0, nb1 = 1, nidx = 1, down = 0, up = 0;
-    RpView view() const { return RpView{lut, l1, base, sh, nb1, down, up}; }
+    u32* linear = nullptr;
+    u32 base = 0, sh = 0, nb1 = 1, nidx = 1, down = 0, up = 0, mul = 0;
+    RpView view() const { return RpView{lut, l1, base, sh, nb1, down, up, linear, mul}; }
 };
 static RangeWork& range_work(mc2_engine* e) {
     if (!e->work) e->work = new RangeWork;
@@ -83,6 +84,7 @@ static void plan_geometry(RpPlan& pl, int kb, u32 nb1, u64 p_lo, u64 p_hi) {
     pl.sh = 0;
     while (((span - 1) >> pl.sh) >= RP_LUT) ++pl.sh;
     pl.nidx = (u32)((span - 1) >> pl.sh) + 1;
+    pl.mul = (u32)(((u64)nb1 << RP_MUL_SHIFT) / pl.nidx);           // closed-form LUT: (index * mul) >> RP_MUL_SHIFT  (< nb1)
 }
 static const u64 RP_SAMPLE_WINDOWS = 1ull << 21;     // keys whose prefixes shape a level's LUT
 
@@ -119,7 +121,8 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
                        int level, const u32* shist_given = nullptr) {
     RangeWork& w = range_work(e);
     pl.lut = w.lut[level].get(e, RP_LUT);
-    pl.l1 = w.l1[level].get(e, HC_MAX_NB1);
+    pl.l1 = w.l1[level].get(e, HC_MAX_NB1 + 1);
+    pl.linear = reinterpret_cast<u32*>(pl.l1 + HC_MAX_NB1);         // (one spare descriptor slot holds the flag)
     struct { u32* p; } shist{nullptr};
     const u32* sh_p = shist_given;
     if (!sh_p) {
@@ -145,7 +148,7 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
         }
         sh_p = shist.p;
     }
-    LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.lut, pl.l1);
+    LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.mul, pl.lut, pl.l1, pl.linear);
 }
 
 // keys one two-level partition can take (beyond it: level-0 partition first)
@@ -712,6 +715,9 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
             CUDA_CHECK(cudaEventRecord(ev, e->stream));
             evs.push_back(ev);
             ++launched;
+            // stay at most three groups ahead of the device: the row counts of finished groups must reach the host while
+            // later groups are still running, or nothing could be handed to the copy engine before the end
+            if (launched >= 3) CUDA_CHECK(cudaEventSynchronize(evs[launched - 3]));
             drain(false);
         }
     }

@@ -21,6 +21,7 @@
 #include "metrics.cuh"
 #include "tsv.cuh"
 #include "merge.cuh"
+#include "textprep.cuh"
 
 static thread_local std::string g_err;
 
@@ -1280,6 +1281,79 @@ int mc2_count_sample(mc2_engine* e, const void* text, uint64_t nbytes, int space
         for (u64 i = 0; i < bounds.size() && i < piece_capacity; ++i) piece_offsets[i] = bounds[i];
     *out = t;
     API_END
+}
+
+// ---- text transforms ahead of the hot path (rows N1 / N2) ---------------------------------------------------------------
+struct mc2_text {
+    mc2_engine* e = nullptr;
+    DBuf<u8> data;
+    u64 nbytes = 0;
+};
+
+// '\n' positions of a device text (ascending); returns their number
+static u64 newline_positions(mc2_engine* e, const u8* d, u64 n, DBuf<u64>& nl) {
+    const u64 ntiles = div_up(std::max<u64>(n, 1), MG_TILE);
+    DBuf<u32> tc(e, ntiles);
+    DBuf<u64> to(e, ntiles);
+    LAUNCH(e, mg_newline_count_kernel, (unsigned)ntiles, MG_THREADS, 0, d, n, tc.p);
+    const u64 n_nl = offsets_from_counts(e, tc.p, to.p, ntiles);
+    nl.alloc(e, std::max<u64>(n_nl, 1));
+    if (n_nl) LAUNCH(e, mg_newline_write_kernel, (unsigned)ntiles, MG_THREADS, 0, d, n, (const u64*)to.p, nl.p);
+    return n_nl;
+}
+
+int mc2_fastq_to_fasta(mc2_engine* e, const void* text, uint64_t nbytes, int space, mc2_text** out) {
+    API_BEGIN
+    if (!e || !out || (nbytes && !text)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::unique_ptr<mc2_text> t(new mc2_text);
+    t->e = e;
+    if (nbytes) {
+        DBuf<u8> holder;
+        const u8* d = to_device(e, text, nbytes, space, holder);
+        DBuf<u64> nl;
+        const u64 n_nl = newline_positions(e, d, nbytes, nl);
+        u8 last = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&last, d + nbytes - 1, 1, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        const u64 nlines = n_nl + (last != '\n' ? 1 : 0);
+        DBuf<u32> len(e, nlines);
+        DBuf<u64> off(e, nlines);
+        DBuf<ull> total(e, 1);
+        LAUNCH(e, fq_line_len_kernel, (unsigned)div_up(nlines, 256), 256, 0, d, (u64)nbytes, (const u64*)nl.p, n_nl, nlines, len.p);
+        dev_exclusive_scan<u32, u64>(e, len.p, off.p, nlines, total.p);
+        t->nbytes = (u64)read_scalar<ull>(e, total.p);
+        t->data.alloc(e, t->nbytes + 16);
+        if (t->nbytes)
+            LAUNCH(e, fq_copy_kernel, (unsigned)div_up(nlines, 8), 256, 0, d, (u64)nbytes, (const u64*)nl.p, n_nl, nlines, (const u32*)len.p,
+                   (const u64*)off.p, t->data.p);
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    *out = t.release();
+    API_END
+}
+
+int mc2_text_info(const mc2_text* t, const void** device_ptr, uint64_t* nbytes) {
+    API_BEGIN
+    if (!t) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (device_ptr) *device_ptr = t->data.p;
+    if (nbytes) *nbytes = t->nbytes;
+    API_END
+}
+
+int mc2_text_export(mc2_text* t, void* host, uint64_t capacity) {
+    API_BEGIN
+    if (!t || (t->nbytes && !host)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    if (capacity < t->nbytes) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
+    CUDA_CHECK(cudaSetDevice(t->e->device));
+    d2h(t->e, (u8*)host, (const u8*)t->data.p, t->nbytes);
+    API_END
+}
+
+void mc2_text_free(mc2_text* t) {
+    if (!t) return;
+    cudaSetDevice(t->e->device);
+    delete t;
 }
 
 // ---- several small samples in ONE pass (BASELINE config 5: many proteomes, one table each) --------------------------

@@ -49,7 +49,13 @@ struct RpView {
     const uint2* l1;       // nb1 entries: .x = first prefix of the bucket, .y = scale of its linear sub-buckets (2^39 / span)
     u32 base, sh, nb1;
     u32 down, up;          // prefix of a right-aligned key of kb bits: (u32)(key >> down) << up   (kb >= 32: down = kb - 32)
+    // When the sampled prefixes are spread evenly enough, rp_plan_kernel fills the LUT with the closed form
+    // lut[i] = (i * mul) >> RP_MUL_SHIFT and sets *linear: the kernels then compute the bucket instead of looking it up
+    // (one shared-memory load less per key in kernels that are bound by shared-memory traffic).
+    const u32* linear;
+    u32 mul;
 };
+#define RP_MUL_SHIFT 20
 __device__ __forceinline__ u32 rp_prefix(u64 key, u32 down, u32 up) { return (u32)(key >> down) << up; }
 __device__ __forceinline__ u32 rp_lut_index(u32 p, u32 base, u32 sh) { return min((p - base) >> sh, RP_LUT - 1u); }
 
@@ -89,6 +95,7 @@ __device__ __forceinline__ void rp_load_shared(const RpView& r, RpShared& s, boo
     if (with_l1)
         for (u32 i = threadIdx.x; i < r.nb1; i += blockDim.x) s.l1[i] = r.l1[i];
 }
+__device__ __forceinline__ u32 rp_b1_linear(const RpView& r, u32 p) { return min((rp_lut_index(p, r.base, r.sh) * r.mul) >> RP_MUL_SHIFT, r.nb1 - 1u); }
 __device__ __forceinline__ u32 rp_b1(const RpShared& s, const RpView& r, u32 p) { return s.lut[rp_lut_index(p, r.base, r.sh)]; }
 // (< 128 by construction of .y for every prefix of the bucket; the clamp only guards a caller that passed wrong bounds)
 __device__ __forceinline__ u32 rp_b2(uint2 d, u32 p) { return min(__umulhi(p - d.x, d.y), HC_NB2 - 1u); }
@@ -104,23 +111,39 @@ __device__ __forceinline__ u32 rp_sub(const RpShared& s, const RpView& r, u32 p)
 // = floor(nb1 * (sample mass before i) / total): monotone, and no bucket exceeds its share by more than one index.
 // With an empty sample the indices are spread evenly.  A bucket id that no index maps to stays empty (zero keys).
 __global__ void __launch_bounds__(1024)
-rp_plan_kernel(const u32* __restrict__ shist, u32 nb1, u32 base, u32 sh, u32 nidx, u16* __restrict__ lut, uint2* __restrict__ l1) {
+rp_plan_kernel(const u32* __restrict__ shist, u32 nb1, u32 base, u32 sh, u32 nidx, u32 mul, u16* __restrict__ lut, uint2* __restrict__ l1,
+               u32* __restrict__ linear) {
     __shared__ u64 sm[1024 / 32 + 1];
     __shared__ u32 first[HC_MAX_NB1 + 1];
+    __shared__ u32 mass[HC_MAX_NB1];
+    __shared__ u32 s_max;
     constexpr u32 PER = RP_LUT / 1024;
     u32 h[PER];
     u64 acc = 0;
 #pragma unroll
     for (u32 j = 0; j < PER; ++j) { h[j] = shist[threadIdx.x * PER + j]; acc += h[j]; }
     for (u32 i = threadIdx.x; i <= nb1; i += 1024) first[i] = 0xFFFFFFFFu;
+    for (u32 i = threadIdx.x; i < nb1; i += 1024) mass[i] = 0;
+    if (threadIdx.x == 0) s_max = 0;
     u64 total;
     u64 run = block_exclusive_sum64<32>(acc, sm, &total);
+    // sample mass per bucket under the closed-form (evenly spaced) assignment: good enough if no bucket exceeds its share by 12 %
+#pragma unroll
+    for (u32 j = 0; j < PER; ++j) {
+        const u32 idx = threadIdx.x * PER + j;
+        if (idx < nidx && h[j]) atomicAdd(&mass[min(nb1 - 1, (idx * mul) >> RP_MUL_SHIFT)], h[j]);
+    }
+    BLOCK_SYNC();
+    for (u32 i = threadIdx.x; i < nb1; i += 1024) atomicMax(&s_max, mass[i]);
+    BLOCK_SYNC();
+    const bool lin = total == 0 || (u64)s_max * nb1 * 100 <= total * 112;
+    if (threadIdx.x == 0) *linear = lin ? 1u : 0u;
 #pragma unroll
     for (u32 j = 0; j < PER; ++j) {
         const u32 idx = threadIdx.x * PER + j;
         u32 b;
-        if (idx >= nidx) b = nb1 - 1;
-        else if (total == 0) b = (u32)(((u64)idx * nb1) / nidx);
+        if (lin) b = min(nb1 - 1, (min(idx, RP_LUT - 1u) * mul) >> RP_MUL_SHIFT);
+        else if (idx >= nidx) b = nb1 - 1;
         else b = (u32)min((u64)(nb1 - 1), (run * nb1) / total);
         lut[idx] = (u16)b;
         if (idx < nidx) atomicMin(&first[b], idx);
@@ -168,6 +191,11 @@ hk_hist_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32 nb, u32* __res
     rp_load_shared(r, rs, FINE);
     for (u32 i = threadIdx.x; i < nb; i += HK_HIST_THREADS) hist[i] = 0;
     BLOCK_SYNC();
+    const bool lin = *r.linear != 0;
+    auto bucket = [&](u32 p) {
+        const u32 b1 = lin ? rp_b1_linear(r, p) : rp_b1(rs, r, p);
+        return FINE ? b1 * HC_NB2 + rp_b2(rs.l1[b1], p) : b1;
+    };
     // four independent loads in flight per thread (one per iteration left the kernel latency-bound: 0.24 ms per 65 M keys)
     const u64 stride = (u64)gridDim.x * HK_HIST_THREADS;
     u64 i = (u64)blockIdx.x * HK_HIST_THREADS + threadIdx.x;
@@ -176,15 +204,9 @@ hk_hist_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32 nb, u32* __res
 #pragma unroll
         for (int j = 0; j < 4; ++j) kk[j] = keys[i + j * stride];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const u32 p = rp_prefix(kk[j], r.down, r.up);
-            smem_red_inc(&hist[FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)]);
-        }
+        for (int j = 0; j < 4; ++j) smem_red_inc(&hist[bucket(rp_prefix(kk[j], r.down, r.up))]);
     }
-    for (; i < n; i += stride) {
-        const u32 p = rp_prefix(keys[i], r.down, r.up);
-        smem_red_inc(&hist[FINE ? rp_sub(rs, r, p) : rp_b1(rs, r, p)]);
-    }
+    for (; i < n; i += stride) smem_red_inc(&hist[bucket(rp_prefix(keys[i], r.down, r.up))]);
     BLOCK_SYNC();
     for (u32 b = threadIdx.x; b < nb; b += HK_HIST_THREADS) {
         const u32 c = hist[b];
@@ -404,8 +426,12 @@ hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32* __restric
         if (i < n) { mine[j] = keys[i]; valid |= 1u << j; }
     }
     BLOCK_SYNC();
+    const bool lin = *r.linear != 0;
     auto key = [&](int i) { return mine[i]; };
-    auto dig = [&](int i) { return ((valid >> i) & 1u) ? (u32)s_lut[rp_lut_index(rp_prefix(mine[i], r.down, r.up), r.base, r.sh)] : 0u; };
+    auto dig = [&](int i) {
+        const u32 p = rp_prefix(mine[i], r.down, r.up);
+        return ((valid >> i) & 1u) ? (lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)]) : 0u;
+    };
     if (base + HC_TILE <= n) hc_group_and_write<true>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
     else hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
 }

@@ -1,8 +1,8 @@
-"""Host-side pre-processing that feeds the hot path (the reference's lib/mercat2_fasta.py, the parts
-in scope): ``removeN`` (+ ``-toupper``) and the FASTQ -> FASTA conversion.  These stay plain Python
-on the host, like in the reference; they produce the same ``clean/<base>_clean.fna.gz`` /
-``clean/<base>.fna.gz`` artefacts whose on-disk size drives the chunk trigger
-(bin/mercat2.py:101)."""
+"""Pre-processing that feeds the hot path (the reference's lib/mercat2_fasta.py, the parts in scope): ``removeN``
+(+ ``-toupper``) and the FASTQ -> FASTA conversion.  Both produce the same ``clean/<base>_clean.fna.gz`` /
+``clean/<base>.fna.gz`` artefacts as the reference, whose on-disk size drives the chunk trigger (bin/mercat2.py:101).
+``fq2fa`` converts on the device (``fq2fa_device`` hands back the FASTA text still in HBM, ready to be counted);
+``removeN`` is plain Python on the host like in the reference (its device version is the next step: DESIGN.md)."""
 from __future__ import annotations
 
 import gzip
@@ -72,9 +72,10 @@ def removeN(fasta, outpath, toupper: bool):
     return out_fasta.absolute(), {"GC Content": 100.0 * gc_count / total}
 
 
-def fq2fa(fq_file, outpath, f_name: str) -> str:
-    """lib/mercat2_fasta.py:175-198 (``sed -n '1~4s/^@/>/p;2~4p'``): of every 4 lines keep the first
-    with its leading '@' turned into '>' (dropped if it does not start with '@') and the second."""
+def fq2fa_host(fq_file, outpath, f_name: str) -> str:
+    """lib/mercat2_fasta.py:175-198 (``sed -n '1~4s/^@/>/p;2~4p'``) in plain Python: of every 4 lines keep the first
+    with its leading '@' turned into '>' (dropped if it does not start with '@') and the second.  Test helper / CPU
+    hosts; the product path is ``fq2fa``."""
     os.makedirs(outpath, exist_ok=True)
     fna_file = os.path.join(outpath, f_name + ".fna.gz")
     opener = gzip.open if str(fq_file).endswith(".gz") else open
@@ -85,4 +86,28 @@ def fq2fa(fq_file, outpath, f_name: str) -> str:
                     writer.write(b">" + line[1:])
             elif i % 4 == 1:
                 writer.write(line)
+    return os.path.abspath(fna_file)
+
+
+def fq2fa_device(fq_file, engine=None):
+    """FASTQ file -> FASTA text on the device (``_native.DeviceText``: pass it to the counting calls as it is)."""
+    from . import _native
+    engine = engine or _native.default_engine()
+    opener = gzip.open if str(fq_file).endswith(".gz") else open
+    with opener(fq_file, "rb") as reader:
+        data = reader.read()
+    return engine.fastq_to_fasta(data)
+
+
+def fq2fa(fq_file, outpath, f_name: str, engine=None) -> str:
+    """lib/mercat2_fasta.py:175-198: writes ``<outpath>/<f_name>.fna.gz`` (same bytes as the reference's sed pipeline)
+    from the text converted on the device; returns its path."""
+    os.makedirs(outpath, exist_ok=True)
+    fna_file = os.path.join(outpath, f_name + ".fna.gz")
+    text = fq2fa_device(fq_file, engine)
+    try:
+        with gzip.open(fna_file, "wb") as writer:
+            writer.write(text.to_bytes())
+    finally:
+        text.close()
     return os.path.abspath(fna_file)

@@ -1093,9 +1093,34 @@ def test_big_chunk_async_groups_and_row_streaming(engine):
     import mercat2_b200
     rows = torch.empty((1024, 2), dtype=torch.int64, pin_memory=True)
     with pytest.raises(mercat2_b200.Mc2Error):
-        engine.count_text_rows(b">r\nACGTNACGTACGTNNACGT\n", 3, 1, rows.data_ptr(), 1024)
+        engine.count_text_rows(b">r\nACGTACGTACGTACGTACGTACGTACGTaACGTACGTACGTACGT\n", 3, 1, rows.data_ptr(), 1024)      # 'a': a literal-byte row
     n = engine.count_text_rows(b">r\nACGTACGTACGT\n", 3, 2, rows.data_ptr(), 1024)
     want = orc.find_kmers_text(">r\nACGTACGTACGT\n", 3, 2)
     assert n == len(want)
     with pytest.raises(mercat2_b200.Mc2Error):
         engine.count_text_rows(dev, 31, 2, rows.data_ptr(), 16)                                  # buffer too small
+
+
+def test_fastq_to_fasta_on_device(engine, golden_configs, tmp_path):
+    """row N2: fq2fa on the device against the reference's sed pipeline (golden digest of Test_R1) and against the host
+    restatement on awkward inputs; the converted text is counted straight from HBM"""
+    from mercat2_b200 import mercat2_fasta
+    reset(engine)
+    out = mercat2_fasta.fq2fa(str(GOLDEN / "data/Test_R1.fastq.gz"), str(tmp_path / "clean"), "Test_R1", engine)
+    assert md5(gzip.open(out, "rb").read()) == golden_configs["test_r1_k12"]["fasta_md5"]
+    text = mercat2_fasta.fq2fa_device(str(GOLDEN / "data/Test_R1.fastq.gz"), engine)
+    for c in (1, 2):
+        want = orc.find_kmers_text(gzip.open(out, "rb").read().decode(), 12, c)
+        assert engine.count_text(text, 12, c).to_dict() == want
+    text.close()
+    cases = [b"", b"@r1\nACGT\n+\nIIII\n", b"@r1\nACGT\n+\nIIII", b"@r1\r\nACGT\r\n+\r\nIIII\r\n@r2\nAC", b"r1 no at\nACGT\n+\nIIII\n@r2\nGG\n+\nII\n",
+              b"@r1\n\n+\n\n@r2\nTTTT\n+\nIIII\n", b"\n\n\n\n@x\nA\n", b"@only"]
+    rng = random.Random(3)
+    big = b"".join(b"@read%d extra\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGTN") for _ in range(rng.randrange(1, 300))), b"I" * 5) for i in range(5000))
+    for j, data in enumerate(cases + [big, big[:-1]]):
+        src = tmp_path / f"case{j}.fastq"
+        src.write_bytes(data)
+        ref = mercat2_fasta.fq2fa_host(str(src), str(tmp_path / "ref"), f"case{j}")
+        dev = engine.fastq_to_fasta(data)
+        assert dev.to_bytes() == gzip.open(ref, "rb").read(), f"case {j}"
+        dev.close()

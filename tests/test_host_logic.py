@@ -78,7 +78,7 @@ def test_removeN_scaffolds_with_N_runs(toupper, golden_configs, tmp_path):
 
 
 def test_fq2fa_matches_reference(golden_configs, tmp_path):
-    from mercat2_b200.mercat2_fasta import fq2fa
+    from mercat2_b200.mercat2_fasta import fq2fa_host as fq2fa          # (the host restatement: the CPU suite has no device)
     out = fq2fa(str(GOLDEN / "data/Test_R1.fastq.gz"), str(tmp_path / "clean"), "Test_R1")
     assert out.endswith("Test_R1.fna.gz")
     assert md5(gzip.open(out, "rb").read()) == golden_configs["test_r1_k12"]["fasta_md5"]
