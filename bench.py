@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("-s", type=int, default=0, help="chunk size in MB (0 = one global table, the headline)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the CPU sample (0 = auto)")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of the 1 Gbp metagenome to synthesise (profiling runs)")
-    ap.add_argument("--groups-per-rank", type=int, default=24, help="N > 1: exchange rounds (key ranges per rank)")
+    ap.add_argument("--groups-per-rank", type=int, default=0, help="N > 1: exchange rounds (key ranges per rank); 0 = sized from the text")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
@@ -309,7 +309,7 @@ def main():
         chunk_bytes = s_mb * 1024 * 1024 if (s_mb > 0 and nbytes >= s_mb * 1024 * 1024) else 0
         if s_mb == 0 and world > 1:
             # ONE piece whose text is spread over the ranks: keys exchanged before the filter
-            return mcd.count_piece_position_sharded(engine, buf, k, c, dist, device, groups_per_rank=args.groups_per_rank, timings=timings), 1
+            return mcd.count_piece_position_sharded(engine, buf, k, c, dist, device, groups_per_rank=args.groups_per_rank or None, timings=timings), 1
         table, offsets = engine.count_sample(buf, k, c, chunk_bytes)
         if world > 1:                       # whole pieces per rank, filtered per piece: sum the filtered tables by key range
             part = mcd.merge_table_device(engine, table, dist, device)
@@ -502,7 +502,7 @@ def main():
         limiting = max(((k2, v) for k2, v in phases.items() if k2.endswith("_ms") and not k2.startswith("host_")), key=lambda kv: kv[1])[0]
         if timings and phases.get("host_exchange_wait_ms", 0) > phases[limiting]:
             limiting = "host_exchange_wait_ms"
-        parallelism = (f"key-range partition x{world}: NCCL all-to-all of the keys before the filter, {args.groups_per_rank} rounds"
+        parallelism = (f"key-range partition x{world}: NCCL all-to-all of the keys before the filter, {args.groups_per_rank or 'auto'} rounds per rank"
                        if (world > 1 and args.s == 0) else f"chunk-sharded x{world}" if world > 1 else "single GPU")
         out = {
             "metric": METRIC,

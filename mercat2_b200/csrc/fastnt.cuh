@@ -530,7 +530,8 @@ fn_dense_kernel(PackedView pv, int k, u32 bins, u32 nrep, u32* __restrict__ tabl
     }
 }
 
-// packed stream -> keys grouped by level-1 bucket (or by level-0 group with 64-bit group bases)
+// packed stream -> keys grouped by level-1 bucket (or by level-0 group with 64-bit group bases); persistent CTAs, the
+// LUT is loaded once per CTA and only when the plan is not the closed form (see hk_scatter1_kernel)
 __global__ void __launch_bounds__(EX_THREADS)
 fn_scatter1_kernel(PackedView pv, int k, RpView r, u32* __restrict__ cur1, u64* __restrict__ keys1, const u64* __restrict__ base64) {
     extern __shared__ __align__(16) u8 dyn_sc[];                    // HC_SCATTER_SMEM_LUT bytes
@@ -539,21 +540,27 @@ fn_scatter1_kernel(PackedView pv, int k, RpView r, u32* __restrict__ cur1, u64* 
     u16* s_lut = reinterpret_cast<u16*>(dyn_sc + HC_SCATTER_SMEM16);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
-    for (u32 i = threadIdx.x; i < r.nb1; i += EX_THREADS) cnt[i] = 0;
-    for (u32 i = threadIdx.x; i < RP_LUT / 8; i += EX_THREADS) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(r.lut)[i];
-    BLOCK_SYNC();
+    const bool lin = *r.linear != 0;
+    if (!lin)
+        for (u32 i = threadIdx.x; i < RP_LUT / 8; i += EX_THREADS) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(r.lut)[i];
     const int rshift = 64 - 2 * k;
     const u32 pm = fn_pmask(k);
-    FnWords w;
-    const u32 valid = fn_load_windows(pv, (u64)blockIdx.x * EX_THREADS + threadIdx.x, k, w);
-    // keys and digits are recomputed (funnel shifts) wherever they are needed instead of living in 32 registers
-    auto key = [&](int i) { return fn_key(w, i, rshift); };
-    const bool lin = *r.linear != 0;
-    auto dig = [&](int i) {
-        const u32 p = fn_hi(w, i) & pm;
-        return lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)];
-    };
-    hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
+    const u64 nwords = (pv.n + 15) >> 4;
+    const u64 ntiles = (nwords + EX_THREADS - 1) / EX_THREADS;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (u32 i = threadIdx.x; i < r.nb1; i += EX_THREADS) cnt[i] = 0;
+        FnWords w;
+        const u32 valid = fn_load_windows(pv, tile * EX_THREADS + threadIdx.x, k, w);
+        BLOCK_SYNC();
+        // keys and digits are recomputed (funnel shifts) wherever they are needed instead of living in 32 registers
+        auto key = [&](int i) { return fn_key(w, i, rshift); };
+        auto dig = [&](int i) {
+            const u32 p = fn_hi(w, i) & pm;
+            return lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)];
+        };
+        hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
+        BLOCK_SYNC();                                          // the staging area and the counters are re-used by the next tile
+    }
 }
 
 // debug: order-independent checksum of all countable windows of the packed stream

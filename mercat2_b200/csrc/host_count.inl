@@ -112,6 +112,9 @@ static void range_kernel_attrs(mc2_engine* e) {
     CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_CHECK(cudaFuncSetAttribute(rc_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_CHECK(cudaFuncSetAttribute(fn_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(hkv_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HKV_SCATTER_SMEM_LUT));
+    CUDA_CHECK(cudaFuncSetAttribute(hkv_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HKV_SCATTER_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(rc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
     e->range_attrs_set = true;
 }
 
@@ -151,10 +154,18 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
     LAUNCH(e, rp_plan_kernel, 1, 1024, 0, sh_p, pl.nb1, pl.base, pl.sh, pl.nidx, pl.mul, pl.lut, pl.l1, pl.linear);
 }
 
+// keys a sub-bucket is sized for.  min_count 1 keeps every distinct key in the table (smaller buckets); duplicate-rich
+// data (most keys repeat: few distinct keys per bucket) takes 25 % more keys per bucket -- still one register round for
+// most buckets (two rounds measured 9 % slower in the counting kernel), and a 2.1e8-key exchange round of the 8-GPU
+// job then fits one two-level pass.
+static double bucket_fill(const mc2_engine* e, const mc2_sample* s) {
+    if (s->c < 2) return 0.7;
+    const bool direct = e->opt_count_mode >= 0 ? e->opt_count_mode == 0 : s->dup_rich;
+    return direct && s->dup_rich ? 1.25 : 1.0;
+}
 // keys one two-level partition can take (beyond it: level-0 partition first)
 static u64 range_batch_max(const mc2_engine* e, const mc2_sample* s) {
-    const double fill = s->c < 2 ? 0.7 : 1.0;                    // min_count 1 keeps every distinct key in the table
-    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * fill), e->opt_batch_symbols);
+    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * bucket_fill(e, s)), e->opt_batch_symbols);
 }
 
 // Range partition + shared-memory tables (rangecount.cuh); the chunk must fit one batch.  Keys come from the byte
@@ -175,7 +186,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     const int mode = c < 2 ? 0 : e->opt_count_mode >= 0 ? (e->opt_count_mode ? 1 : 0) : (s->dup_rich ? 0 : 1);
     // (`cap` of a symbol stream counts ~25 % more positions than windows; a key array is exact, so aim lower there to
     // keep the same head room below the keys a table may hold)
-    const double fill = (ks ? 0.8 : 1.0) * (mode == 0 && c < 2 ? 0.7 : 1.0);
+    const double fill = (ks ? 0.8 : 1.0) * bucket_fill(e, s);
     const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * fill));
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
@@ -220,9 +231,9 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(cap, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur1.p, keys1.p, (const u64*)nullptr);
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)std::min<u64>(div_up(cap, HC_TILE), (u64)e->num_sms * 3), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else if (pv) {
-        LAUNCH(e, fn_scatter1_kernel, (unsigned)div_up(div_up(cap, 16), EX_THREADS), EX_THREADS, HC_SCATTER_SMEM_LUT, *pv, k, rv, cur1.p, keys1.p, (const u64*)nullptr);
+        LAUNCH(e, fn_scatter1_kernel, (unsigned)std::min<u64>(div_up(div_up(cap, 16), EX_THREADS), (u64)e->num_sms * 3), EX_THREADS, HC_SCATTER_SMEM_LUT, *pv, k, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else {
         auto kern = hc_scatter1_kernel<ENC>;
         LAUNCHN(e, "hc_scatter1_kernel", kern, (unsigned)div_up(cap, EX_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, v, (u64)0, v.n, k, rv, cur1.p, keys1.p);
@@ -325,6 +336,63 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
         e->ovf_buckets += t.ovf_n;
         if ((u64)t.ovf_n * 200 > nb && s->bucket_scale > 0.3) s->bucket_scale *= 0.8;      // > 0.5 % of the buckets overflowed
     }
+}
+
+// Sum M (key, count) rows by key through the range partition (rowmerge.cuh): `out` receives the summed rows sorted by
+// key.  Returns false (nothing done) when the rows are too few to be worth it, too many for one two-level pass, or a
+// sub-bucket held more distinct keys than its table (the caller then sorts).
+static u64 merge_rows_capacity(const mc2_engine* e) {
+    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * 0.6), (1ull << 32) - 1);
+}
+static bool merge_rows_range(mc2_engine* e, const u64* keys, const u64* counts, u64 M, int key_bits, FastPart& out) {
+    if (M < 32768 || M > merge_rows_capacity(e)) return false;
+    e->row_merges++;
+    range_kernel_attrs(e);
+    const u64 bucket_keys = std::max<u64>(16, (u64)((double)e->opt_hash_bucket_keys * 0.6));      // every key of a bucket may be distinct
+    const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(M, bucket_keys * HC_NB2)));
+    const u32 nb = nb1 * HC_NB2;
+    RpPlan pl;
+    plan_geometry(pl, key_bits, nb1, 0, 1ull << 32);
+    KeySpan ks{keys, M, 0, 1ull << 32};
+    build_plan<ENC_NT2>(e, 0, std::vector<PackedView>(), &ks, SymView{nullptr, 0}, M, pl, 1);
+    const RpView rv = pl.view();
+    RangeWork& w = range_work(e);
+    struct Tail { ull total, rows; u32 ovf_n, pad; };
+    u32* ghist = w.ghist.get(e, nb + sizeof(Tail) / 4 + 8);
+    u32* sub_base = w.sub_base.get(e, nb + 1);
+    u32* cur1 = w.cur1.get(e, nb1);
+    u32* cur2 = w.cur2.get(e, nb);
+    u32* tile_pref = w.tile_pref.get(e, nb1 + 1);
+    u32* rows = w.rows.get(e, nb);
+    u64* row_off = w.row_off.get(e, nb);
+    Tail* tail = reinterpret_cast<Tail*>(ghist + nb);
+    CUDA_CHECK(cudaMemsetAsync(ghist, 0, (size_t)nb * 4 + sizeof(Tail), e->stream));
+    const size_t hist_smem = sizeof(RpShared) + (size_t)nb * 4;
+    LAUNCHN(e, "hk_hist_kernel", hk_hist_kernel<true>, (unsigned)std::max<u64>(std::min<u64>(div_up(M, HK_HIST_THREADS * 8), (u64)e->num_sms), 1), HK_HIST_THREADS,
+            hist_smem, keys, M, rv, nb, ghist);
+    LAUNCH(e, hc_scan_kernel, 1, 1024, (size_t)nb * 4, (const u32*)ghist, nb, nb1, (u32)HC_NB2, sub_base, cur1, cur2, tile_pref, &tail->total);
+    // keys1 / keys2 serve as key arrays, two fresh arrays carry the counts; the 16-byte row slots need 2 * M words
+    u64* keys1 = w.keys1.get(e, M + 8);
+    u64* keys2 = w.keys2.get(e, M + 8);
+    DBuf<u64> vals1(e, M), vals2(e, M);
+    DBuf<RcRow> slots(e, M + 2);
+    LAUNCH(e, hkv_scatter1_kernel, (unsigned)std::min<u64>(div_up(M, HC_TILE), (u64)e->num_sms * 2), EX_THREADS, HKV_SCATTER_SMEM_LUT, keys, counts, M, rv, cur1,
+           keys1, vals1.p);
+    LAUNCH(e, hkv_scatter2_kernel, (unsigned)(div_up(M, HC_TILE) + nb1), EX_THREADS, HKV_SCATTER_SMEM, (const u64*)keys1, (const u64*)vals1.p,
+           (const u32*)sub_base, (const u32*)tile_pref, nb, (u32)HC_NB2, rv, cur2, keys2, vals2.p);
+    LAUNCH(e, rc_merge_kernel, (unsigned)std::min<u64>(nb, 2ull * e->num_sms), RM_THREADS, RM_SMEM, (const u64*)keys2, (const u64*)vals2.p, (const u32*)sub_base,
+           nb, rv, slots.p, rows, &tail->ovf_n);
+    LAUNCH(e, rc_offsets_kernel, 1, 1024, 0, (const u32*)rows, nb, row_off, (ull*)nullptr, &tail->rows, 0);
+    const Tail t = read_scalar<Tail>(e, tail);
+    if (t.ovf_n) return false;
+    out.n = t.rows;
+    out.sorted = true;
+    out.keys.alloc(e, t.rows);
+    out.counts.alloc(e, t.rows);
+    if (t.rows)
+        LAUNCH(e, rc_gather_kernel, (unsigned)std::min<u64>(div_up(nb, 8), (u64)e->num_sms * 8), 256, 0, (const RcRow*)slots.p, (const u32*)sub_base, (const u32*)rows,
+               (const u64*)row_off, nb, 1u, out.keys.p, out.counts.p, (RcRow*)nullptr);
+    return true;
 }
 
 template <int ENC>
@@ -625,11 +693,11 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     pt.mark("level-0 allocation");
     CUDA_CHECK(cudaMemcpyAsync(gbase_dev.p, out.gbase.data(), (g0 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)div_up(ks->n, HC_TILE), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur0.p, out.keys0,
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)std::min<u64>(div_up(ks->n, HC_TILE), (u64)e->num_sms * 3), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur0.p, out.keys0,
                (const u64*)gbase_dev.p);
     } else {
         for (auto& pv : pvs) {
-            const u64 grid = div_up(div_up(pv.n, 16), EX_THREADS);
+            const u64 grid = std::min<u64>(div_up(div_up(pv.n, 16), EX_THREADS), (u64)e->num_sms * 3);
             if (grid) LAUNCH(e, fn_scatter1_kernel, (unsigned)grid, EX_THREADS, HC_SCATTER_SMEM_LUT, pv, k, rv, cur0.p, out.keys0, (const u64*)gbase_dev.p);
         }
     }

@@ -158,6 +158,90 @@ static bool concat_sorted_parts(mc2_engine* e, std::vector<FastPart>& parts, u64
     return true;
 }
 
+static bool merge_rows_range(mc2_engine* e, const u64* keys, const u64* counts, u64 M, int key_bits, FastPart& out);   // host_count.inl
+static u64 merge_rows_capacity(const mc2_engine* e);                                                                     // host_count.inl
+__global__ void lower_bound_kernel(const u64* __restrict__ keys, u64 n, const u64* __restrict__ q, u64 m, u64* __restrict__ out);
+
+// More rows than one two-level pass takes, every part sorted (the filtered tables of the many pieces of a large sample):
+// cut ALL parts at the same splitter keys (quantiles of the largest part), sum each key range on its own and put the
+// results behind each other -- ranges are disjoint and ascending, so the concatenation is the sorted table.
+static bool merge_sorted_parts_by_range(mc2_engine* e, std::vector<FastPart>& parts, u64 M, int key_bits, FastPart& out) {
+    const u64 cap = merge_rows_capacity(e);
+    std::vector<FastPart*> live;
+    for (auto& p : parts) {
+        if (!p.n) continue;
+        if (!p.sorted) return false;
+        live.push_back(&p);
+    }
+    const u32 S = (u32)std::min<u64>(4096, div_up(M, std::max<u64>(1, cap / 2)));         // ranges
+    if (S < 2 || live.size() < 2) return false;
+    FastPart* big = live[0];
+    for (auto* p : live) if (p->n > big->n) big = p;
+    std::vector<u64> pick(S - 1), split(S - 1);
+    for (u32 j = 1; j < S; ++j) pick[j - 1] = (u64)(((unsigned __int128)big->n * j) / S);
+    DBuf<u64> dpick(e, S - 1), dsplit(e, S - 1), dcut(e, S - 1);
+    CUDA_CHECK(cudaMemcpyAsync(dpick.p, pick.data(), (S - 1) * 8ull, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, gather_u64_kernel, (unsigned)div_up(S - 1, 256), 256, 0, (const u64*)big->keys.p, (const u64*)dpick.p, (u64)(S - 1), dsplit.p);
+    std::vector<std::vector<u64>> cuts(live.size(), std::vector<u64>(S + 1, 0));
+    for (size_t i = 0; i < live.size(); ++i) {
+        LAUNCH(e, lower_bound_kernel, (unsigned)div_up(S - 1, 128), 128, 0, (const u64*)live[i]->keys.p, (u64)live[i]->n, (const u64*)dsplit.p, (u64)(S - 1), dcut.p);
+        d2h(e, cuts[i].data() + 1, (const u64*)dcut.p, (u64)(S - 1));
+        cuts[i][S] = live[i]->n;
+        for (u32 j = 1; j <= S; ++j) cuts[i][j] = std::max(cuts[i][j], cuts[i][j - 1]);   // (equal splitters: keep the cuts monotone)
+    }
+    u64 biggest = 0;
+    for (u32 j = 0; j < S; ++j) {
+        u64 m = 0;
+        for (size_t i = 0; i < live.size(); ++i) m += cuts[i][j + 1] - cuts[i][j];
+        biggest = std::max(biggest, m);
+    }
+    if (biggest > cap) return false;                           // (parts too unlike each other: the caller sorts)
+    std::vector<FastPart> done(S);
+    DBuf<u64> k0(e, biggest), v0(e, biggest);
+    u64 total = 0;
+    for (u32 j = 0; j < S; ++j) {
+        u64 m = 0;
+        for (size_t i = 0; i < live.size(); ++i) {
+            const u64 a = cuts[i][j], n = cuts[i][j + 1] - a;
+            if (!n) continue;
+            CUDA_CHECK(cudaMemcpyAsync(k0.p + m, live[i]->keys.p + a, n * 8, cudaMemcpyDeviceToDevice, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(v0.p + m, live[i]->counts.p + a, n * 8, cudaMemcpyDeviceToDevice, e->stream));
+            m += n;
+        }
+        if (!m) continue;
+        if (!merge_rows_range(e, k0.p, v0.p, m, key_bits, done[j])) {
+            // a range too small for the range pass (or one that overflowed a table): the sort-based sum of just this range
+            DBuf<u64> k1(e, m), v1(e, m);
+            const int r = radix_sort<u64, true>(e, k0.p, k1.p, v0.p, v1.p, m, 0, std::min(64, (key_bits + 7) & ~7));
+            const u64* ks = r ? k1.p : k0.p;
+            const u64* vs = r ? v1.p : v0.p;
+            DBuf<u64> start, count;
+            KeyEq acc{ks};
+            const u64 ns = seg_reduce(e, acc, m, vs, 1, start, count);
+            done[j].n = ns;
+            done[j].keys.alloc(e, ns);
+            done[j].counts = std::move(count);
+            if (ns) LAUNCH(e, gather_u64_kernel, (unsigned)div_up(ns, 256), 256, 0, ks, (const u64*)start.p, ns, done[j].keys.p);
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+        total += done[j].n;
+    }
+    for (auto* p : live) { p->keys.release(); p->counts.release(); p->n = 0; }
+    out.n = total;
+    out.sorted = true;
+    out.keys.alloc(e, total);
+    out.counts.alloc(e, total);
+    u64 at = 0;
+    for (u32 j = 0; j < S; ++j) {
+        if (!done[j].n) continue;
+        CUDA_CHECK(cudaMemcpyAsync(out.keys.p + at, done[j].keys.p, done[j].n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(out.counts.p + at, done[j].counts.p, done[j].n * 8, cudaMemcpyDeviceToDevice, e->stream));
+        at += done[j].n;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    return true;
+}
+
 // merge several (key, count) parts: concat, sort pairs, sum equal keys, keep sums >= c
 static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int key_bits, u64 c, FastPart& out) {
     u64 M = 0;
@@ -170,6 +254,7 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
         for (auto& p : parts) if (p.n) { only = &p; nonempty++; }
         if (nonempty == 1 && only->sorted) { out = std::move(*only); return; }
         if (nonempty > 1 && concat_sorted_parts(e, parts, M, out)) return;
+        if (nonempty > 1 && e->opt_sparse_algo != 1 && M > merge_rows_capacity(e) && merge_sorted_parts_by_range(e, parts, M, key_bits, out)) return;
     }
     DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
     u64 at = 0;
@@ -179,6 +264,8 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
         CUDA_CHECK(cudaMemcpyAsync(v0.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
         at += p.n;
     }
+    // plain sums (the dict merge of already filtered tables): through the range partition, born sorted, no sort passes
+    if (c <= 1 && e->opt_sparse_algo != 1 && merge_rows_range(e, k0.p, v0.p, M, key_bits, out)) return;
     const int r = radix_sort<u64, true>(e, k0.p, k1.p, v0.p, v1.p, M, 0, std::min(64, (key_bits + 7) & ~7));
     const u64* ks = r ? k1.p : k0.p;
     const u64* vs = r ? v1.p : v0.p;

@@ -17,6 +17,7 @@
 #include "wide.cuh"
 #include "chunker.cuh"
 #include "rangecount.cuh"
+#include "rowmerge.cuh"
 #include "fastnt.cuh"
 #include "metrics.cuh"
 #include "tsv.cuh"
@@ -63,7 +64,7 @@ struct mc2_engine {
     bool range_attrs_set = false;          // kernel attributes (dynamic shared memory opt-in) are per device: set once per engine
     bool dense_attrs_set[3] = {false, false, false};
     // stats
-    u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0, ovf_buckets = 0;
+    u64 launches = 0, h2d_bytes = 0, d2h_bytes = 0, chunks = 0, ovf_buckets = 0, row_merges = 0;
     double device_us = 0;
     // pinned scratch
     void* pin_small = nullptr;                 // 4 KiB for scalar readbacks
@@ -489,6 +490,7 @@ int64_t mc2_engine_get_stat(mc2_engine* e, const char* name) {
     if (n == "d2h_bytes") return (int64_t)e->d2h_bytes;
     if (n == "chunks") return (int64_t)e->chunks;
     if (n == "overflow_buckets") return (int64_t)e->ovf_buckets;
+    if (n == "row_merges") return (int64_t)e->row_merges;       // (key, count) row sets summed on the range path
     if (n == "device_us") return (int64_t)e->device_us;
     if (n == "num_sms") return e->num_sms;
     return -1;

@@ -405,6 +405,8 @@ hc_scatter1_kernel(SymView v, u64 s0, u64 s1, int k, RpView r, u32* __restrict__
 }
 
 // ---- hk_scatter1: key array -> level-1 groups (or level-0 groups with base64) -----------------------------------------
+// Persistent CTAs (three per SM) walk the tiles: the 16 KB LUT is loaded once per CTA -- per 4096-key tile it was half as
+// many bytes again as the keys themselves -- and not at all when the plan is the closed form.
 __global__ void __launch_bounds__(EX_THREADS, 3)
 hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32* __restrict__ cur1, u64* __restrict__ keys1,
                    const u64* __restrict__ base64) {
@@ -414,26 +416,31 @@ hk_scatter1_kernel(const u64* __restrict__ keys, u64 n, RpView r, u32* __restric
     u16* s_lut = reinterpret_cast<u16*>(dyn_sc + HC_SCATTER_SMEM16);
     __shared__ u32 cnt[HC_MAX_NB1], loff[HC_MAX_NB1], gbase[HC_MAX_NB1];
     __shared__ u32 sm[EX_WARPS + 1];
-    for (u32 i = threadIdx.x; i < r.nb1; i += EX_THREADS) cnt[i] = 0;
-    for (u32 i = threadIdx.x; i < RP_LUT / 8; i += EX_THREADS) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(r.lut)[i];
-    const u64 base = (u64)blockIdx.x * HC_TILE;
-    u64 mine[16];
-    u32 valid = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const u64 i = base + (u64)j * EX_THREADS + threadIdx.x;
-        mine[j] = 0;
-        if (i < n) { mine[j] = keys[i]; valid |= 1u << j; }
-    }
-    BLOCK_SYNC();
     const bool lin = *r.linear != 0;
-    auto key = [&](int i) { return mine[i]; };
-    auto dig = [&](int i) {
-        const u32 p = rp_prefix(mine[i], r.down, r.up);
-        return ((valid >> i) & 1u) ? (lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)]) : 0u;
-    };
-    if (base + HC_TILE <= n) hc_group_and_write<true>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
-    else hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
+    if (!lin)
+        for (u32 i = threadIdx.x; i < RP_LUT / 8; i += EX_THREADS) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(r.lut)[i];
+    const u64 ntiles = (n + HC_TILE - 1) / HC_TILE;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (u32 i = threadIdx.x; i < r.nb1; i += EX_THREADS) cnt[i] = 0;
+        const u64 base = tile * HC_TILE;
+        u64 mine[16];
+        u32 valid = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const u64 i = base + (u64)j * EX_THREADS + threadIdx.x;
+            mine[j] = 0;
+            if (i < n) { mine[j] = keys[i]; valid |= 1u << j; }
+        }
+        BLOCK_SYNC();
+        auto key = [&](int i) { return mine[i]; };
+        auto dig = [&](int i) {
+            const u32 p = rp_prefix(mine[i], r.down, r.up);
+            return ((valid >> i) & 1u) ? (lin ? rp_b1_linear(r, p) : (u32)s_lut[rp_lut_index(p, r.base, r.sh)]) : 0u;
+        };
+        if (base + HC_TILE <= n) hc_group_and_write<true>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
+        else hc_group_and_write<false>(key, dig, valid, r.nb1, stage, sdig, cnt, loff, gbase, sm, cur1, keys1, base64);
+        BLOCK_SYNC();                                          // the staging area and the counters are re-used by the next tile
+    }
 }
 
 // ---- hc_scatter2: level-1 groups -> sub-buckets --------------------------------------------------------------

@@ -407,7 +407,7 @@ def _prefix_text(p: int, n: int) -> bytes:
 
 
 def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, device, out_path=None,
-                                 basename: str = "sample", groups_per_rank: int = 16, timings: dict | None = None):
+                                 basename: str = "sample", groups_per_rank: int | None = None, timings: dict | None = None):
     """ONE piece (chunk) whose text is split by position over the ranks (each part starts at a header line).  The
     `-c` filter must see whole-piece counts (lib/mercat2_kmers.py:73-78 on the unsplit piece), so keys are exchanged
     BEFORE counting:
@@ -427,6 +427,12 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
     import time
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
+    if groups_per_rank is None:
+        # rounds of about 1.7e8 keys: one pass of the engine's two-level partition (a round beyond that takes the level-0
+        # route: one more pass over its keys); ~0.75 windows per text byte for short reads
+        nbytes = max(_agree(dist, len(my_text) if not hasattr(my_text, "numel") else int(my_text.numel()))) if world > 1 else \
+            (len(my_text) if not hasattr(my_text, "numel") else int(my_text.numel()))
+        groups_per_rank = min(max(4, -(-int(nbytes * 0.75) // 170_000_000)), max(1, 384 // world))
     m = groups_per_rank
     groups = world * m
     t_last = [time.perf_counter()]

@@ -70,3 +70,45 @@ def test_sharding_helpers():
     assert sorted(i for p in parts for i in p) == list(range(6))
     loads = [sum([9, 1, 8, 2, 7, 3][i] for i in p) for p in parts]
     assert max(loads) - min(loads) <= 1
+
+
+def _encoding_worker(rank, world, port, tmp):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from mercat2_b200 import distributed as mcd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 0 sees a soft-masked (lower-case) stretch, rank 1 plain ACGT: alone they would pick different encodings
+    first = [b">a\n" + b"acgtnacgtn" * 50 + b"\n", b">b\n" + b"ACGT" * 4000 + b"\n"][rank]
+    alone = mcd.ENC_NT2 if (lambda n, a, u: n == 0 or a * 10 >= n * 9)(*mcd.alphabet_stats(first)) else None
+    agreed = mcd.agree_encoding(first, dist)
+    got = [None] * world
+    dist.all_gather_object(got, (alone, agreed))
+    if rank == 0:
+        assert got[0][0] is None and got[1][0] == mcd.ENC_NT2           # the ranks disagree on their own ...
+        assert got[0][1] == got[1][1] == mcd.ENC_NT2                    # ... and agree on the summed statistics
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_ranks_agree_on_encoding_world2():
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as tmp:
+        port = 31500 + os.getpid() % 2000
+        mp.spawn(_encoding_worker, args=(2, port, tmp), nprocs=2, join=True)
+        assert os.path.exists(os.path.join(tmp, "ok"))
+
+
+def test_position_sharding_host_helpers():
+    from mercat2_b200 import distributed as mcd
+    text = b">a\nACGT\n>b\nGGCC\n>c\nTTAA\n>d\nAC\n"
+    for world in (1, 2, 3, 4, 7):
+        parts = mcd.split_at_headers(text, world)
+        assert b"".join(parts) == text and len(parts) == world
+        assert all(p == b"" or p.startswith(b">") for p in parts)        # every part starts at a header line
+    assert mcd.split_at_headers(b">a", 4) == [b"", b">a", b"", b""]      # (tiny text: no cut at byte 1)
+    assert mcd._prefix_text(0, 16) == b"A" * 16 and mcd._prefix_text(0xFFFFFFFF, 16) == b"T" * 16
+    assert mcd._prefix_text(0b00011011 << 24, 4) == b"ACGT"
+    assert mcd.alphabet_stats(b">h ACGT\nACGTNN\nacgt*\n") == (10, 4, 6)
+    assert mcd.decode_key(0b00011011, 4, mcd.ENC_NT2, mcd.KEY_CODE) == b"ACGT"

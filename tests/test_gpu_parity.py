@@ -793,6 +793,12 @@ def test_bench_json_contract():
     for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert key in line["e2e"], key
     assert line["e2e"]["h2d_bytes_per_step"] == 700000 * 164 and line["e2e"]["value"] > 0
+    # the headline is config 4 as written: one global table (-s 0 -c 2) with survivors, the table read back, checked first
+    assert "-c 2 -s 0" in line["config"]["workload"] and line["config"]["surviving_rows"] > 0
+    assert line["e2e"]["d2h_bytes_per_step"] == 16 * line["config"]["surviving_rows"]
+    assert line["check"]["ok"] and line["check"]["oracle_md5"] == line["check"]["engine_md5"] and line["check"]["rows"] > 0
+    assert set(("parse_ms", "partition_ms", "count_ms", "emit_ms")) <= set(line["phases"]) and line["limiting_phase"] in line["phases"]
+    assert "-c 10 -s 100" in line["secondary"]["workload"] and line["secondary"]["value"] > 0
     for key in ("value", "unit", "cores", "kind", "sample"):
         assert key in line["cpu_baseline"], key
     ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
@@ -1124,3 +1130,59 @@ def test_fastq_to_fasta_on_device(engine, golden_configs, tmp_path):
         dev = engine.fastq_to_fasta(data)
         assert dev.to_bytes() == gzip.open(ref, "rb").read(), f"case {j}"
         dev.close()
+
+
+def test_row_merge_through_range_partition(engine):
+    """the dict merge of many filtered tables (bin/mercat2.py:121-127) on the range path: a sample of many pieces with
+    survivors (parts with overlapping key ranges) and a table rebuilt from unsorted rows with repeated keys must equal
+    numpy's reduce-by-key; the radix-sort merge (sparse_algo=1) is the cross-check"""
+    import torch
+    reset(engine)
+    text, codes = numpy_piece(120_000, 4_000_000, seed=23)                 # 14.4 M windows, ~3.6x coverage
+    dev = torch.from_numpy(text).cuda()
+    pieces = 12
+    merges0 = engine.stat("row_merges")
+    table, offs = engine.count_sample(dev, 31, 2, len(text) // pieces)
+    got_k, got_c = table.packed_arrays()
+    table.close()
+    assert engine.stat("row_merges") > merges0                         # (not the sort fallback)
+    engine.set_option("hash_bucket_keys", 40)                          # rows beyond one pass: parts cut at common splitters, ranges summed one by one
+    try:
+        merges0 = engine.stat("row_merges")
+        table, _ = engine.count_sample(dev, 31, 2, len(text) // pieces)
+        cut_k, cut_c = table.packed_arrays()
+        table.close()
+        assert engine.stat("row_merges") >= merges0 + 2
+    finally:
+        reset(engine)
+    bounds = [o // 164 for o in offs] + [120_000]
+    parts = [numpy_table(codes[a:b], 31, 2) for a, b in zip(bounds[:-1], bounds[1:])]
+    all_k = np.concatenate([p[0] for p in parts])
+    all_c = np.concatenate([p[1] for p in parts])
+    uk, inv = np.unique(all_k, return_inverse=True)
+    uc = np.zeros(len(uk), dtype=np.uint64)
+    np.add.at(uc, inv, all_c)
+    assert len(offs) >= pieces and len(all_k) > 500_000
+    assert np.array_equal(got_k, uk) and np.array_equal(got_c, uc)
+    assert np.array_equal(cut_k, uk) and np.array_equal(cut_c, uc)
+    # unsorted rows with repeats and huge counts (64-bit sums), straight into table_from_rows
+    rng = np.random.default_rng(4)
+    keys = rng.integers(0, 1 << 62, 300_000, dtype=np.int64).astype(np.uint64)
+    keys = np.concatenate([keys, keys[:100_000], keys[:50_000], np.array([(1 << 62) - 1] * 3, dtype=np.uint64)])
+    cnts = rng.integers(1, 1 << 40, len(keys), dtype=np.int64).astype(np.uint64)
+    perm = rng.permutation(len(keys))
+    keys, cnts = keys[perm], cnts[perm]
+    wk, winv = np.unique(keys, return_inverse=True)
+    wc = np.zeros(len(wk), dtype=np.uint64)
+    np.add.at(wc, winv, cnts)
+    dk, dc = torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(cnts.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    for algo in (0, 1):
+        engine.set_option("sparse_algo", algo)
+        try:
+            t = engine.table_from_rows(31, 0, 0, dk.data_ptr(), dc.data_ptr(), len(keys), True)
+            tk, tc = t.packed_arrays()
+            t.close()
+        finally:
+            reset(engine)
+        assert np.array_equal(tk, wk) and np.array_equal(tc, wc), algo

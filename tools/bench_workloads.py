@@ -146,6 +146,38 @@ def main():
                       "seconds": round(dt, 4), "symbols_per_s": round(6e6 * sc * 150 / dt), "file_GB_per_s": round(nbytes / dt / 1e9, 2)}), flush=True)
     os.unlink(fpath)
 
+    # BASELINE config 5: 64 synthetic proteomes (S5), k=5 -c 10, one table each -- all in ONE batched pass vs one pass per sample
+    from tools import synth_s5
+    for proteins, label in ((5000, "S5"), (50000, "S5 x10")):
+        proteins = max(50, int(proteins * sc))
+        texts = [torch.frombuffer(bytearray(synth_s5.sample_text(j, proteins)), dtype=torch.uint8).to(dev) for j in range(64)]
+        residues = sum(int(t.numel()) for t in texts)              # (text bytes: residues + headers + newlines)
+        torch.cuda.synchronize()
+        for mode in ("batched", "one pass per sample"):
+            best = None
+            for _ in range(args.reps):
+                t0 = time.perf_counter()
+                if mode == "batched":
+                    tables = []
+                    at = 0
+                    while at < len(texts):                           # batches of <= 96 MB of text
+                        size, end = 0, at
+                        while end < len(texts) and (end == at or size + int(texts[end].numel()) <= (96 << 20)):
+                            size += int(texts[end].numel())
+                            end += 1
+                        tables += engine.count_batch(texts[at:end], 5, 10)
+                        at = end
+                else:
+                    tables = [engine.count_text(t, 5, 10) for t in texts]
+                rows = sum(t.rows for t in tables)
+                for t in tables:
+                    t.close()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            print(json.dumps({"workload": f"cfg5 {label}: 64 proteomes x {proteins} proteins, k=5 -c 10, {mode}", "text_bytes": residues,
+                              "rows": rows, "seconds": round(best, 5), "samples_per_s": round(64 / best, 1), "text_bytes_per_s": round(residues / best)}), flush=True)
+        del texts
+
     text, n = protein_text(dev, int(50000 * sc), 1000)
     run(engine, "S5 x10: 50 k proteins, k=5 -c 10 (dense 26^5)", text, n, 5, 10, 0, args.reps, tsv=True)
     run(engine, "50 k proteins, k=3 -c 10 (dense, shared memory)", text, n, 3, 10, 0, args.reps, tsv=True)
