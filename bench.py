@@ -486,7 +486,10 @@ def main():
         try:                                        # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
             tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
             if top[0] in tj["kernels"]:
-                roof["traffic"], roof["traffic_source"] = tj["kernels"][top[0]]["dram_bytes_per_launch"], tj["source"]
+                # measured DRAM bytes per key of the captured launch x the keys one launch of THIS run handles
+                per_key = tj["kernels"][top[0]]["dram_bytes_per_key"]
+                roof["traffic"] = per_key * windows * args.steps / max(1, top[1]["launches"])
+                roof["traffic_source"] = tj["source"]
         except (OSError, ValueError, KeyError):
             pass
         phases = phases_from_profile(profile, args.steps)

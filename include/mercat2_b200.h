@@ -50,7 +50,8 @@ int mc2_engine_trim(mc2_engine* e);
 
 /* Tunables (mostly for tests): "dense_max_bins", "smem_max_bins", "batch_symbols", "force_path"
  * (0 auto, 1 dense, 2 sparse, 3 wide), "force_encoding" (-1 auto, 0 ACGT 2-bit, 1 A-Z 5-bit, 2 byte), "sparse_algo"
- * (0/2 range partition + shared-memory tables, 1 radix sort), "count_mode" (-1 auto, 0 / 1 see rangecount.cuh). */
+ * (0/2 range partition + shared-memory tables, 1 radix sort), "count_mode" (-1 auto, 0 / 1 see rangecount.cuh),
+ * "row_merge" (sums of (key, count) row sets: 0 sort + segmented sum, 1 range partition + shared-memory sums). */
 int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value);
 /* Counters: "launches" (kernels launched so far), "h2d_bytes", "d2h_bytes", "chunks", "device_ms"
  * (CUDA-event time of the last count call, microseconds in "device_us"). */

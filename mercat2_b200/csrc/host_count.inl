@@ -342,13 +342,13 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
 // key.  Returns false (nothing done) when the rows are too few to be worth it, too many for one two-level pass, or a
 // sub-bucket held more distinct keys than its table (the caller then sorts).
 static u64 merge_rows_capacity(const mc2_engine* e) {
-    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * 0.6), (1ull << 32) - 1);
+    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * 0.45), (1ull << 32) - 1);
 }
 static bool merge_rows_range(mc2_engine* e, const u64* keys, const u64* counts, u64 M, int key_bits, FastPart& out) {
     if (M < 32768 || M > merge_rows_capacity(e)) return false;
     e->row_merges++;
     range_kernel_attrs(e);
-    const u64 bucket_keys = std::max<u64>(16, (u64)((double)e->opt_hash_bucket_keys * 0.6));      // every key of a bucket may be distinct
+    const u64 bucket_keys = std::max<u64>(16, (u64)((double)e->opt_hash_bucket_keys * 0.45));     // every row of a bucket may be a distinct key, and sub-buckets are uneven
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(M, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
     RpPlan pl;

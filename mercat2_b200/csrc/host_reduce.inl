@@ -254,7 +254,7 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
         for (auto& p : parts) if (p.n) { only = &p; nonempty++; }
         if (nonempty == 1 && only->sorted) { out = std::move(*only); return; }
         if (nonempty > 1 && concat_sorted_parts(e, parts, M, out)) return;
-        if (nonempty > 1 && e->opt_sparse_algo != 1 && M > merge_rows_capacity(e) && merge_sorted_parts_by_range(e, parts, M, key_bits, out)) return;
+        if (nonempty > 1 && e->opt_row_merge == 1 && M > merge_rows_capacity(e) && merge_sorted_parts_by_range(e, parts, M, key_bits, out)) return;
     }
     DBuf<u64> k0(e, M), k1(e, M), v0(e, M), v1(e, M);
     u64 at = 0;
@@ -264,8 +264,9 @@ static void reduce_fast_parts(mc2_engine* e, std::vector<FastPart>& parts, int k
         CUDA_CHECK(cudaMemcpyAsync(v0.p + at, p.counts.p, p.n * 8, cudaMemcpyDeviceToDevice, e->stream));
         at += p.n;
     }
-    // plain sums (the dict merge of already filtered tables): through the range partition, born sorted, no sort passes
-    if (c <= 1 && e->opt_sparse_algo != 1 && merge_rows_range(e, k0.p, v0.p, M, key_bits, out)) return;
+    // plain sums (the dict merge of already filtered tables) through the range partition: opt-in ("row_merge" = 1).
+    // Measured on 16 filtered pieces, 350 M rows: 0.77-1.26 s against 0.63 s for the sort below.
+    if (c <= 1 && e->opt_row_merge == 1 && merge_rows_range(e, k0.p, v0.p, M, key_bits, out)) return;
     const int r = radix_sort<u64, true>(e, k0.p, k1.p, v0.p, v1.p, M, 0, std::min(64, (key_bits + 7) & ~7));
     const u64* ks = r ? k1.p : k0.p;
     const u64* vs = r ? v1.p : v0.p;

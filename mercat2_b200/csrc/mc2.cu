@@ -58,6 +58,7 @@ struct mc2_engine {
     int opt_group_sync = 0;                // very large chunks: 1 = one host round trip per level-0 group (the min_count 1 path) even for min_count >= 2
     HostRowSink host_rows;
     unsigned long long* pin_groups = nullptr;   // pinned: per-group row counters of the streaming download
+    int opt_row_merge = 0;                 // sums of (key, count) row sets: 0 = sort + segmented sum, 1 = range partition + shared-memory sums
     int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)
     int opt_sparse_algo = 0;               // 0 auto (range partition + shared-memory tables), 1 radix sort, 2 range partition
     u64 opt_hash_bucket_keys = 3500;       // target keys per shared-memory table
@@ -466,6 +467,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "sparse_algo") e->opt_sparse_algo = (int)value;
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "count_mode") e->opt_count_mode = (int)value;
+    else if (n == "row_merge") e->opt_row_merge = (int)value;
     else if (n == "group_sync") e->opt_group_sync = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
     else if (n == "parse_single") e->opt_parse_single = (int)value;

@@ -159,21 +159,36 @@ rc_merge_kernel(const u64* __restrict__ keys2, const u64* __restrict__ vals2, co
         const u32 lo = sub_base[b], n = sub_base[b + 1] - lo;
         const uint2 d1 = __ldg(&r.l1[b >> HC_NB2_LOG2]);
         auto fine = [&](ull key) { return rp_fine(d1, rp_prefix(key, r.down, r.up), RC_FINE_LOG2); };
-        for (u32 i = threadIdx.x; i < n; i += RM_THREADS) {
-            const ull key = keys2[lo + i], w = vals2[lo + i];
-            if (key == HC_EMPTY) { atomicAdd(&s_empty, w); continue; }
-            u32 p = rc_slot(rc_hash(key));
-            u32 probes = 0;
-            for (; probes < RC_PROBE_LIMIT; ++probes) {
-                ull cur = tkeys[p];
-                if (cur == HC_EMPTY) {
-                    cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
-                    if (cur == HC_EMPTY) cur = key;
-                }
-                if (cur == key) { atomicAdd(&tsum[p], w); break; }
-                p = (p + 1) & (RM_SLOTS - 1);
+        // rounds of 4 rows per thread: the loads of a round are in flight together (one load at a time left the kernel
+        // waiting on memory: 3 G rows/s)
+        for (u32 i0 = 0; i0 < n; i0 += 4 * RM_THREADS) {
+            ull kk[4], ww[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const u32 i = i0 + j * RM_THREADS + threadIdx.x;
+                kk[j] = i < n ? keys2[lo + i] : 0ull;
+                ww[j] = i < n ? vals2[lo + i] : 0ull;
             }
-            if (probes == RC_PROBE_LIMIT) s_ovf = 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const u32 i = i0 + j * RM_THREADS + threadIdx.x;
+                if (i >= n) continue;
+                const ull key = kk[j], w = ww[j];
+                if (key == HC_EMPTY) { atomicAdd(&s_empty, w); continue; }
+                u32 p = rc_slot(rc_hash(key));
+                u32 probes = 0;
+#pragma unroll 1
+                for (; probes < RC_PROBE_LIMIT; ++probes) {
+                    ull cur = tkeys[p];
+                    if (cur == HC_EMPTY) {
+                        cur = atomicCAS(&tkeys[p], HC_EMPTY, key);
+                        if (cur == HC_EMPTY) cur = key;
+                    }
+                    if (cur == key) { atomicAdd(&tsum[p], w); break; }
+                    p = (p + 1) & (RM_SLOTS - 1);
+                }
+                if (probes == RC_PROBE_LIMIT) s_ovf = 1;
+            }
         }
         BLOCK_SYNC();
         const bool ovf = s_ovf != 0;

@@ -39,6 +39,7 @@ def reset(engine):
     engine.set_option("hash_bucket_keys", 3500)
     engine.set_option("parse_single", 0)
     engine.set_option("count_mode", -1)
+    engine.set_option("row_merge", 0)
 
 
 def diff_msg(got, want):
@@ -1133,11 +1134,12 @@ def test_fastq_to_fasta_on_device(engine, golden_configs, tmp_path):
 
 
 def test_row_merge_through_range_partition(engine):
-    """the dict merge of many filtered tables (bin/mercat2.py:121-127) on the range path: a sample of many pieces with
-    survivors (parts with overlapping key ranges) and a table rebuilt from unsorted rows with repeated keys must equal
-    numpy's reduce-by-key; the radix-sort merge (sparse_algo=1) is the cross-check"""
+    """the dict merge of many filtered tables (bin/mercat2.py:121-127) on the opt-in range path (row_merge=1): a sample of
+    many pieces with survivors (parts with overlapping key ranges) and a table rebuilt from unsorted rows with repeated keys
+    must equal numpy's reduce-by-key, and so must the default sort-based merge"""
     import torch
     reset(engine)
+    engine.set_option("row_merge", 1)
     text, codes = numpy_piece(120_000, 4_000_000, seed=23)                 # 14.4 M windows, ~3.6x coverage
     dev = torch.from_numpy(text).cuda()
     pieces = 12
@@ -1147,6 +1149,7 @@ def test_row_merge_through_range_partition(engine):
     table.close()
     assert engine.stat("row_merges") > merges0                         # (not the sort fallback)
     engine.set_option("hash_bucket_keys", 40)                          # rows beyond one pass: parts cut at common splitters, ranges summed one by one
+    engine.set_option("row_merge", 1)
     try:
         merges0 = engine.stat("row_merges")
         table, _ = engine.count_sample(dev, 31, 2, len(text) // pieces)
@@ -1155,6 +1158,11 @@ def test_row_merge_through_range_partition(engine):
         assert engine.stat("row_merges") >= merges0 + 2
     finally:
         reset(engine)
+    merges0 = engine.stat("row_merges")
+    table, _ = engine.count_sample(dev, 31, 2, len(text) // pieces)    # the default: sort + segmented sum
+    srt_k, srt_c = table.packed_arrays()
+    table.close()
+    assert engine.stat("row_merges") == merges0
     bounds = [o // 164 for o in offs] + [120_000]
     parts = [numpy_table(codes[a:b], 31, 2) for a, b in zip(bounds[:-1], bounds[1:])]
     all_k = np.concatenate([p[0] for p in parts])
@@ -1165,6 +1173,7 @@ def test_row_merge_through_range_partition(engine):
     assert len(offs) >= pieces and len(all_k) > 500_000
     assert np.array_equal(got_k, uk) and np.array_equal(got_c, uc)
     assert np.array_equal(cut_k, uk) and np.array_equal(cut_c, uc)
+    assert np.array_equal(srt_k, uk) and np.array_equal(srt_c, uc)
     # unsorted rows with repeats and huge counts (64-bit sums), straight into table_from_rows
     rng = np.random.default_rng(4)
     keys = rng.integers(0, 1 << 62, 300_000, dtype=np.int64).astype(np.uint64)
@@ -1178,7 +1187,7 @@ def test_row_merge_through_range_partition(engine):
     dk, dc = torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(cnts.view(np.int64)).cuda()
     torch.cuda.synchronize()
     for algo in (0, 1):
-        engine.set_option("sparse_algo", algo)
+        engine.set_option("row_merge", 1 - algo)
         try:
             t = engine.table_from_rows(31, 0, 0, dk.data_ptr(), dc.data_ptr(), len(keys), True)
             tk, tc = t.packed_arrays()
