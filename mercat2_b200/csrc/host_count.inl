@@ -158,10 +158,17 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
 // data (most keys repeat: few distinct keys per bucket) takes 25 % more keys per bucket -- still one register round for
 // most buckets (two rounds measured 9 % slower in the counting kernel), and a 2.1e8-key exchange round of the 8-GPU
 // job then fits one two-level pass.
+#define RC_DISTINCT_TARGET 1600.0
 static double bucket_fill(const mc2_engine* e, const mc2_sample* s) {
     if (s->c < 2) return 0.7;
     const bool direct = e->opt_count_mode >= 0 ? e->opt_count_mode == 0 : s->dup_rich;
-    return direct && s->dup_rich ? 1.25 : 1.0;
+    if (!(direct && s->dup_rich)) return 1.0;
+    // every distinct key takes a table slot, however often it occurs: with r keys per distinct key a sub-bucket may hold
+    // r times the keys (further rounds of the counting kernel) for the same table load.  Fewer, larger sub-buckets =
+    // fewer table walks per key and fewer bins in the scatters.  Aim at RC_DISTINCT_TARGET distinct keys, at most 16 K keys.
+    if (s->dup_ratio > 0 && e->opt_bucket_growth)
+        return std::min(16384.0 / 3500.0, std::max(1.25, RC_DISTINCT_TARGET * s->dup_ratio / 3500.0));
+    return 1.25;
 }
 // keys one two-level partition can take (beyond it: level-0 partition first)
 static u64 range_batch_max(const mc2_engine* e, const mc2_sample* s) {
@@ -262,7 +269,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
                 h[4], h[5], h[6], h[7], h[8], ((pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) || b1 || b2) ? "  MISMATCH" : "");
     }
     const unsigned cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
-    ull* flagged_dev = sink ? sink->counters + 2 : &tail.p->flagged;
+    ull* flagged_dev = sink ? sink->counters + (mode == 1 ? 2 : 5) : &tail.p->flagged;      // (MODE 0 reports distinct keys there)
     if (mode == 1)
         LAUNCHN(e, "rc_count_kernel<1>", rc_count_kernel<1>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,
                 ovf_list.p, &tail.p->ovf_n, flagged_dev);
@@ -309,6 +316,8 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     if (c >= 2) {
         if (mode == 1 && t.flagged * 2 >= t.total && t.total >= 65536) s->dup_rich = true;      // half of the keys are repeats
         if (mode == 0 && (u64)t.ovf_n * 50 > nb) s->dup_rich = false;
+        if (mode == 0 && t.flagged && t.total >= 65536) s->dup_ratio = (double)t.total / (double)t.flagged;
+        if (mode == 0 && (u64)t.ovf_n * 200 > nb) s->dup_ratio = std::max(1.0, s->dup_ratio * 0.5);
     }
     if (t.ovf_n) {
         // Sub-buckets whose distinct (MODE 0) or repeated (MODE 1) keys do not fit the table: their keys are gathered
@@ -767,15 +776,22 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
         }
     };
     bool mode_known = s->dup_rich || e->opt_count_mode >= 0;
+    bool ratio_known = s->dup_ratio > 0;
     for (u32 g = 0; g < g0; ++g) {
         const KeySpan span = span_of(g);
         if (!span.n) continue;
+        const bool direct = e->opt_count_mode >= 0 ? e->opt_count_mode == 0 : s->dup_rich;
         sparse_chunk_range<ENC_NT2>(e, s, SymView{nullptr, 0}, nullptr, &span, &sink);
         if (!mode_known) {                                       // one look at the first group decides the counting mode of the rest
             ull c5[8];
             d2h(e, c5, (const ull*)counters.p, 8);
             if (c5[2] * 2 >= c5[3] && c5[3] >= 65536) s->dup_rich = true;
             mode_known = true;
+        } else if (!ratio_known && direct && s->dup_rich) {      // ... and one at the first group counted without the pre-filter sizes the sub-buckets
+            ull c5[8];
+            d2h(e, c5, (const ull*)counters.p, 8);
+            if (c5[5] && span.n >= 65536) s->dup_ratio = (double)span.n / (double)c5[5];
+            ratio_known = true;
         }
         if (hs) {
             CUDA_CHECK(cudaMemcpyAsync(&pin[launched], counters.p, sizeof(ull), cudaMemcpyDeviceToHost, e->stream));
@@ -804,6 +820,7 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     }
     e->ovf_buckets += fin[4];
     if ((u64)fin[4] * 200 > div_up(total, std::max<u64>(1, e->opt_hash_bucket_keys)) && s->bucket_scale > 0.3) s->bucket_scale *= 0.8;
+    if ((u64)fin[4] * 200 > div_up(total, (u64)(e->opt_hash_bucket_keys * bucket_fill(e, s)) + 1)) s->dup_ratio = std::max(1.0, s->dup_ratio * 0.5);
     const bool host_done = hs && !ovf_m;
     if (hs && ovf_m) e->host_rows.failed = true;               // rows of the sort path would have to be merged in: the caller falls back
     if (host_done) {

@@ -58,6 +58,7 @@ struct mc2_engine {
     int opt_group_sync = 0;                // very large chunks: 1 = one host round trip per level-0 group (the min_count 1 path) even for min_count >= 2
     HostRowSink host_rows;
     unsigned long long* pin_groups = nullptr;   // pinned: per-group row counters of the streaming download
+    int opt_bucket_growth = 1;             // duplicate-rich data: size sub-buckets by the measured keys per distinct key (0 = fixed 1.25 x)
     int opt_row_merge = 0;                 // sums of (key, count) row sets: 0 = sort + segmented sum, 1 = range partition + shared-memory sums
     int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)
     int opt_sparse_algo = 0;               // 0 auto (range partition + shared-memory tables), 1 radix sort, 2 range partition
@@ -342,6 +343,7 @@ struct mc2_sample {
     std::vector<WidePart> wide;
     u64 n_chunks = 0;
     double bucket_scale = 1.0;             // shrinks when many sub-buckets overflow their table
+    double dup_ratio = 0;                  // duplicate-rich data: keys per distinct key, measured on an earlier chunk / group (0 = not known)
     bool dup_rich = false;                 // most keys repeat (seen on an earlier chunk / group): count without the bitmap pre-filter
     PrePass pre;
     const u8* next_text = nullptr;         // the chunk that follows the one being counted (resident text), for PrePass
@@ -468,6 +470,7 @@ int mc2_engine_set_option(mc2_engine* e, const char* name, int64_t value) {
     else if (n == "fast_nt") e->opt_fast_nt = (int)value;
     else if (n == "count_mode") e->opt_count_mode = (int)value;
     else if (n == "row_merge") e->opt_row_merge = (int)value;
+    else if (n == "bucket_growth") e->opt_bucket_growth = (int)value;
     else if (n == "group_sync") e->opt_group_sync = (int)value;
     else if (n == "big_chunks") e->opt_big_chunks = (int)value;
     else if (n == "parse_single") e->opt_parse_single = (int)value;

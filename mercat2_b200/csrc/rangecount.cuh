@@ -587,7 +587,8 @@ template <int MODE>
 __global__ void __launch_bounds__(RC_THREADS, 2)
 rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base, u32 nb, u32 c, RpView r,
                 RcRow* __restrict__ out, u32* __restrict__ rows, u32* __restrict__ ovf_list, u32* __restrict__ ovf_n,
-                ull* __restrict__ flagged_total /*MODE 1: keys that found their bitmap bit set (repeats + ~1 % false positives)*/) {
+                ull* __restrict__ flagged_total /*MODE 1: keys that found their bitmap bit set (repeats + ~1 % false positives);
+                                                  MODE 0: distinct keys held by the tables (overflowed sub-buckets excluded)*/) {
     extern __shared__ __align__(16) u8 dyn[];
     u32* bm = reinterpret_cast<u32*>(dyn);                                               // region A
     ull* skey = reinterpret_cast<ull*>(dyn);
@@ -641,11 +642,18 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         // ---- pass 1 ----
         for (u32 rd = 0; rd < max(nrounds, 1u); ++rd) {
             const u32 off = rd * RC_ROUND;
+            if (rd > 0) {                                        // (uniform) a further round: its loads are in flight together
+#pragma unroll
+                for (int j = 0; j < RC_PREFETCH; ++j) {
+                    const u32 i = off + j * RC_THREADS + threadIdx.x;
+                    kcur[j] = i < n ? keys2[lo + i] : 0ull;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < RC_PREFETCH; ++j) {
                 const u32 i = off + j * RC_THREADS + threadIdx.x;
                 if (i < n) {
-                    const ull key = rd == 0 ? kcur[j] : keys2[lo + i];
+                    const ull key = kcur[j];
                     if (MODE == 1) rc_pass1(key, bm, tkeys, tcnt, claimed, flist, scal, need_at);
                     else if (key == HC_EMPTY) smem_red_inc(&scal[4]);
                     else rc_insert0(key, tkeys, tcnt, scal);
@@ -684,7 +692,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
 #pragma unroll
                     for (int j = 0; j < RC_PREFETCH; ++j) {
                         const u32 i = off + j * RC_THREADS + threadIdx.x;
-                        if (i < n) rc_pass2(rd == 0 ? kcur[j] : keys2[lo + i], tkeys, tcnt, scal);
+                        if (i < n) rc_pass2(nrounds == 1 ? kcur[j] : keys2[lo + i], tkeys, tcnt, scal);
                     }
                 }
                 BLOCK_SYNC();
@@ -699,11 +707,19 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         u32 nsurv = 0;
         if (exact && !ovf) {                                       // (block-uniform)
             // A: survivors per ordering bin (bins are zero here)
+            u32 held = 0;                                          // MODE 0: distinct keys of the bucket (occupied slots)
             for (u32 i = threadIdx.x; i < nd; i += RC_THREADS) {
                 const u32 p = slot_of(i);
-                if (tcnt[p] >= c) smem_red_inc(&bins[fine(tkeys[p])]);
+                const u32 cnt = tcnt[p];
+                if (MODE == 0) held += cnt ? 1u : 0u;
+                if (cnt >= c) smem_red_inc(&bins[fine(tkeys[p])]);
+            }
+            if (MODE == 0) {
+                held = __reduce_add_sync(0xffffffffu, held);
+                if (lane == 0 && held) atomicAdd(&scal[1], held);
             }
             BLOCK_SYNC();
+            if (MODE == 0) cta_flagged += scal[1];
             // exclusive scan of the bins (2 per thread), in place: bins[d] = first staging row of bin d; total = survivors
             const u32 c0 = bins[2 * threadIdx.x], c1 = bins[2 * threadIdx.x + 1];
             __syncwarp();
@@ -802,7 +818,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         }
         BLOCK_SYNC();
     }
-    if (MODE == 1 && threadIdx.x == 0 && flagged_total && cta_flagged) atomicAdd(flagged_total, cta_flagged);
+    if (threadIdx.x == 0 && flagged_total && cta_flagged) atomicAdd(flagged_total, cta_flagged);
 }
 
 // ---- survivor slots -> one dense array ----------------------------------------------------------------------------------

@@ -800,6 +800,9 @@ def test_bench_json_contract():
     assert line["check"]["ok"] and line["check"]["oracle_md5"] == line["check"]["engine_md5"] and line["check"]["rows"] > 0
     assert set(("parse_ms", "partition_ms", "count_ms", "emit_ms")) <= set(line["phases"]) and line["limiting_phase"] in line["phases"]
     assert "-c 10 -s 100" in line["secondary"]["workload"] and line["secondary"]["value"] > 0
+    cfg5 = line["secondary"]["cfg5"]                                   # BASELINE config 5: 64 proteomes, one table + metrics each
+    assert "error" not in cfg5, cfg5
+    assert cfg5["samples"] == 64 and cfg5["proteins"] == 64 * 5000 and cfg5["rows"] > 0 and cfg5["samples_per_s"] > 0
     for key in ("value", "unit", "cores", "kind", "sample"):
         assert key in line["cpu_baseline"], key
     ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
