@@ -159,20 +159,24 @@ static void build_plan(mc2_engine* e, int k, const std::vector<PackedView>& pvs,
 // most buckets (two rounds measured 9 % slower in the counting kernel), and a 2.1e8-key exchange round of the 8-GPU
 // job then fits one two-level pass.
 #define RC_DISTINCT_TARGET 1600.0
+#define RC_NB1_SWEET 192u                 // level-1 bins up to which the scatters keep their speed (measured: 46 ms / 10^10 keys at <= 220 bins, 95 ms at 384)
 static double bucket_fill(const mc2_engine* e, const mc2_sample* s) {
     if (s->c < 2) return 0.7;
     const bool direct = e->opt_count_mode >= 0 ? e->opt_count_mode == 0 : s->dup_rich;
-    if (!(direct && s->dup_rich)) return 1.0;
-    // every distinct key takes a table slot, however often it occurs: with r keys per distinct key a sub-bucket may hold
-    // r times the keys (further rounds of the counting kernel) for the same table load.  Fewer, larger sub-buckets =
-    // fewer table walks per key and fewer bins in the scatters.  Aim at RC_DISTINCT_TARGET distinct keys, at most 16 K keys.
-    if (s->dup_ratio > 0 && e->opt_bucket_growth)
-        return std::min(16384.0 / 3500.0, std::max(1.25, RC_DISTINCT_TARGET * s->dup_ratio / 3500.0));
-    return 1.25;
+    return direct && s->dup_rich ? 1.25 : 1.0;
+}
+// Every distinct key takes a table slot, however often it occurs: with r keys per distinct key (measured on an earlier
+// chunk / group of the sample) a sub-bucket may hold r times the keys -- further rounds of the counting kernel -- for the
+// same table load.  Used only where the default size would need more than RC_NB1_SWEET level-1 bins: larger sub-buckets cost
+// the counting kernel ~25 % (measured), too many bins cost the scatters 2x.
+static double bucket_fill_max(const mc2_engine* e, const mc2_sample* s) {
+    const double base = bucket_fill(e, s);
+    if (base < 1.25 || !(s->dup_ratio > 0) || !e->opt_bucket_growth) return base;
+    return std::min(16384.0 / 3500.0, std::max(base, RC_DISTINCT_TARGET * s->dup_ratio / 3500.0));
 }
 // keys one two-level partition can take (beyond it: level-0 partition first)
 static u64 range_batch_max(const mc2_engine* e, const mc2_sample* s) {
-    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * bucket_fill(e, s)), e->opt_batch_symbols);
+    return std::min<u64>((u64)((double)HC_MAX_NB1 * HC_NB2 * (double)e->opt_hash_bucket_keys * bucket_fill_max(e, s)), e->opt_batch_symbols);
 }
 
 // Range partition + shared-memory tables (rangecount.cuh); the chunk must fit one batch.  Keys come from the byte
@@ -194,7 +198,11 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     // (`cap` of a symbol stream counts ~25 % more positions than windows; a key array is exact, so aim lower there to
     // keep the same head room below the keys a table may hold)
     const double fill = (ks ? 0.8 : 1.0) * bucket_fill(e, s);
-    const u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * fill));
+    u64 bucket_keys = std::max<u64>(1, (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * fill));
+    if (div_up(cap, bucket_keys * HC_NB2) > RC_NB1_SWEET) {
+        const u64 most = (u64)((double)e->opt_hash_bucket_keys * s->bucket_scale * (ks ? 0.8 : 1.0) * bucket_fill_max(e, s));
+        bucket_keys = std::max(bucket_keys, std::min(most, div_up(cap, (u64)RC_NB1_SWEET * HC_NB2)));
+    }
     const u32 nb1 = (u32)std::min<u64>(HC_MAX_NB1, std::max<u64>(1, div_up(cap, bucket_keys * HC_NB2)));
     const u32 nb = nb1 * HC_NB2;
     RpPlan pl;
@@ -820,7 +828,7 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     }
     e->ovf_buckets += fin[4];
     if ((u64)fin[4] * 200 > div_up(total, std::max<u64>(1, e->opt_hash_bucket_keys)) && s->bucket_scale > 0.3) s->bucket_scale *= 0.8;
-    if ((u64)fin[4] * 200 > div_up(total, (u64)(e->opt_hash_bucket_keys * bucket_fill(e, s)) + 1)) s->dup_ratio = std::max(1.0, s->dup_ratio * 0.5);
+    if ((u64)fin[4] * 200 > div_up(total, (u64)(e->opt_hash_bucket_keys * bucket_fill_max(e, s)) + 1)) s->dup_ratio = std::max(1.0, s->dup_ratio * 0.5);
     const bool host_done = hs && !ovf_m;
     if (hs && ovf_m) e->host_rows.failed = true;               // rows of the sort path would have to be merged in: the caller falls back
     if (host_done) {

@@ -626,34 +626,53 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
         const u32 n = n_n, lo = lo_n;
         const uint2 d1 = __ldg(&r.l1[b >> HC_NB2_LOG2]);           // (used by the emit pass: fetched here so that its latency is hidden)
         ull kcur[RC_PREFETCH];
+        const u32 nrounds = (n + RC_ROUND - 1) / RC_ROUND;         // block-uniform; 1 at the default sizing
+        // The keys of the step after the current one are requested early and arrive while the current ones are counted.
+        // MODE 1 (one round at the default sizing; its registers are spoken for): the first round of this CTA's next
+        // bucket, requested here; a further round of a bucket loads its keys as it goes.  MODE 0 (duplicate-rich data may
+        // use large buckets): every round hands over to the bucket's next round or to the next bucket's first round.
+        if (MODE == 1) {
 #pragma unroll
-        for (int j = 0; j < RC_PREFETCH; ++j) kcur[j] = knext[j];
-        const u32 bn = b + gridDim.x;
-        if (bn < nb) {
-            lo_n = sub_base[bn];
-            n_n = sub_base[bn + 1] - lo_n;
+            for (int j = 0; j < RC_PREFETCH; ++j) kcur[j] = knext[j];
+            const u32 bn = b + gridDim.x;
+            if (bn < nb) {
+                lo_n = sub_base[bn];
+                n_n = sub_base[bn + 1] - lo_n;
 #pragma unroll
-            for (int j = 0; j < RC_PREFETCH; ++j) {
-                const u32 i = j * RC_THREADS + threadIdx.x;
-                knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+                for (int j = 0; j < RC_PREFETCH; ++j) {
+                    const u32 i = j * RC_THREADS + threadIdx.x;
+                    knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+                }
             }
         }
-        const u32 nrounds = (n + RC_ROUND - 1) / RC_ROUND;         // block-uniform; 1 at the default sizing
         // ---- pass 1 ----
         for (u32 rd = 0; rd < max(nrounds, 1u); ++rd) {
             const u32 off = rd * RC_ROUND;
-            if (rd > 0) {                                        // (uniform) a further round: its loads are in flight together
+            if (MODE == 0) {
 #pragma unroll
-                for (int j = 0; j < RC_PREFETCH; ++j) {
-                    const u32 i = off + j * RC_THREADS + threadIdx.x;
-                    kcur[j] = i < n ? keys2[lo + i] : 0ull;
+                for (int j = 0; j < RC_PREFETCH; ++j) kcur[j] = knext[j];
+                if (rd + 1 < nrounds) {                          // (uniform)
+#pragma unroll
+                    for (int j = 0; j < RC_PREFETCH; ++j) {
+                        const u32 i = off + RC_ROUND + j * RC_THREADS + threadIdx.x;
+                        knext[j] = i < n ? keys2[lo + i] : 0ull;
+                    }
+                } else if (b + gridDim.x < nb) {
+                    const u32 bn = b + gridDim.x;
+                    lo_n = sub_base[bn];
+                    n_n = sub_base[bn + 1] - lo_n;
+#pragma unroll
+                    for (int j = 0; j < RC_PREFETCH; ++j) {
+                        const u32 i = j * RC_THREADS + threadIdx.x;
+                        knext[j] = i < n_n ? keys2[lo_n + i] : 0ull;
+                    }
                 }
             }
 #pragma unroll
             for (int j = 0; j < RC_PREFETCH; ++j) {
                 const u32 i = off + j * RC_THREADS + threadIdx.x;
                 if (i < n) {
-                    const ull key = kcur[j];
+                    const ull key = (MODE == 0 || rd == 0) ? kcur[j] : keys2[lo + i];
                     if (MODE == 1) rc_pass1(key, bm, tkeys, tcnt, claimed, flist, scal, need_at);
                     else if (key == HC_EMPTY) smem_red_inc(&scal[4]);
                     else rc_insert0(key, tkeys, tcnt, scal);
@@ -692,7 +711,7 @@ rc_count_kernel(const u64* __restrict__ keys2, const u32* __restrict__ sub_base,
 #pragma unroll
                     for (int j = 0; j < RC_PREFETCH; ++j) {
                         const u32 i = off + j * RC_THREADS + threadIdx.x;
-                        if (i < n) rc_pass2(nrounds == 1 ? kcur[j] : keys2[lo + i], tkeys, tcnt, scal);
+                        if (i < n) rc_pass2(rd == 0 ? kcur[j] : keys2[lo + i], tkeys, tcnt, scal);
                     }
                 }
                 BLOCK_SYNC();
