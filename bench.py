@@ -114,7 +114,9 @@ def make_reads_text(device, genomes, n_reads, first_read_id, out=None):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi samples every 200 ms during the timed region."""
+    """nvidia-smi samples every 200 ms.  The process is started BEFORE the warm-up steps (its start-up enumerates every GPU
+    of the box and was seen to slow the first two timed steps by ~60 ms each when started at the timed region's edge); only
+    the samples that arrive inside the timed region [t0, t1] are used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -132,9 +134,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc:
             self.proc.terminate()
             try:
@@ -142,7 +144,8 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons = [], 0, set()
-        for line in self.lines:
+        inside = [ln for ts, ln in self.lines if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.2)]
+        for line in inside or [ln for _, ln in self.lines[-3:]]:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -336,6 +339,9 @@ def main():
     windows = n_reads * (READ_LEN - args.k + 1)
 
     engine = mercat2_b200.Engine(local)
+    for item in filter(None, os.environ.get("MC2_BENCH_OPTIONS", "").split(",")):       # experiments: "name=value,..." engine tunables
+        name, _, value = item.partition("=")
+        engine.set_option(name.strip(), int(value))
 
     def count(buf, k, c, s_mb, timings=None):
         """one pass of the hot path over this rank's reads -> this rank's part of the job's table"""
@@ -361,21 +367,24 @@ def main():
     if not args.no_check:
         check = run_check(engine, genomes, args, rank, world, dist if world > 1 else None, device)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         rows, n_chunks = step_resident()
     launches0 = engine.stat("launches")
     # CUDA events on the engine's stream around every kernel of the path (MC2_BENCH_PROFILE=3: only the long ones)
     engine.set_option("profile", int(os.environ.get("MC2_BENCH_PROFILE", "2")))
-    sampler = ClockSampler(local)
-    sampler.start()
     timings = {}
     barrier()
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(args.steps):
         rows, n_chunks = step_resident(timings if world > 1 and args.s == 0 else None)
+        step_ms.append(time.perf_counter())                           # (a step returns with its table finished: no extra synchronisation)
     barrier()
     elapsed = time.perf_counter() - t0
-    clocks = sampler.stop()
+    step_ms = [round((b - a) * 1e3, 2) for a, b in zip([t0] + step_ms[:-1], step_ms)]
+    clocks = sampler.stop(t0, t0 + elapsed)
     launches = engine.stat("launches") - launches0
     profile = engine.profile()
     engine.set_option("profile", 0)
@@ -576,6 +585,7 @@ def main():
             "kernels": {k2: {"launches": v["launches"], "ms": round(v["us"] / 1e3, 3)} for k2, v in
                         sorted(profile.items(), key=lambda kv: -kv[1]["us"])[:14]},
             "check": check,
+            "step_ms_rank0": step_ms,
         }
         if secondary:
             _, roof2 = roofline_of(secondary["profile"], secondary["steps"], secondary["rows"] / world, secondary["elapsed"] / secondary["steps"])

@@ -679,7 +679,12 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
     const u64 total = out.gbase[g0];
     if (total == 0) return true;
     if (out.gmax > group_max || out.gmax >= (1ull << 32)) return false;
-    {   // the level-0 array plus what follows must fit (free memory + what the pool holds unused)
+    const RangeWork& wq = range_work(e);
+    const bool fits_like_before = !wq.keys0_busy && wq.keys0.b.n >= total && total <= e->l0_fit_total && extra <= e->l0_fit_extra;
+    if (!fits_like_before) {
+        // the level-0 array plus what follows must fit (free memory + what the pool holds unused).  Asked only when this
+        // call needs more than an earlier one that fitted in the workspace the engine still holds: cudaMemGetInfo was
+        // seen to take ~55 ms every few calls while the pool has frees in flight.
         size_t free_b = 0, total_b = 0;
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         cudaMemPool_t pool;
@@ -691,6 +696,8 @@ static bool level0_partition(mc2_engine* e, int k, const std::vector<PackedView>
         const RangeWork& w0 = range_work(e);
         const u64 have = w0.keys0_busy ? 0 : w0.keys0.b.n * 8;              // the workspace array is re-used (it is freed first if it must grow)
         if (total * 8 + extra + (1ull << 30) > avail + have) return false;
+        e->l0_fit_total = std::max(e->l0_fit_total, total);
+        e->l0_fit_extra = std::max(e->l0_fit_extra, extra);
     }
     pt.mark("level-0 memory check");
     {

@@ -58,6 +58,7 @@ struct mc2_engine {
     int opt_group_sync = 0;                // very large chunks: 1 = one host round trip per level-0 group (the min_count 1 path) even for min_count >= 2
     HostRowSink host_rows;
     unsigned long long* pin_groups = nullptr;   // pinned: per-group row counters of the streaming download
+    u64 l0_fit_total = 0, l0_fit_extra = 0; // largest level-0 request that passed the memory check (see level0_partition)
     int opt_bucket_growth = 1;             // duplicate-rich data: size sub-buckets by the measured keys per distinct key (0 = fixed 1.25 x)
     int opt_row_merge = 0;                 // sums of (key, count) row sets: 0 = sort + segmented sum, 1 = range partition + shared-memory sums
     int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)
@@ -450,6 +451,7 @@ int mc2_engine_trim(mc2_engine* e) {
     if (e->work && e->work->keys0_busy) throw Mc2Error(MC2_ERR_INVALID, "a key partition (mc2_keys) still uses the workspace");
     delete e->work;
     e->work = nullptr;
+    e->l0_fit_total = e->l0_fit_extra = 0;
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
