@@ -27,7 +27,8 @@ for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 print("\n".join(lines[:14]))
 
 if rep:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # (a .csv argument is the raw page already exported on the GPU box: `ncu -i x.ncu-rep --page raw --csv`)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     data = list(csv.reader(raw.splitlines()))
     hdr, units = data[0], data[1]
     keep = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -42,7 +43,11 @@ if rep:
             "smsp__inst_executed_op_shared_atom.sum"]
     keep += [h for h in hdr if h.startswith("smsp__average_warp_latency_issue_stalled") or h.startswith("smsp__average_warps_issue_stalled")]
     md = [f"# ncu --set full: {Path(rep).name}", ""]
+    seen = defaultdict(int)
     for r in data[2:]:
+        seen[r[hdr.index('Kernel Name')]] += 1
+        if seen[r[hdr.index('Kernel Name')]] > 3:                 # (repeated launches of one kernel: the first three are kept)
+            continue
         md.append(f"## {r[hdr.index('Kernel Name')][:120]}")
         md.append("")
         md.append("| metric | value | unit |")

@@ -31,7 +31,7 @@ def main():
     fastq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 30, b"I" * 120) for i in range(200_000))
     s5 = [torch.frombuffer(bytearray(synth_s5.sample_text(j, 1000)), dtype=torch.uint8).to(dev) for j in range(16)]
     tmp = ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp") + "/mc2_profile.tsv"
-    for rep in range(2):                                   # pass 0 warms up (module load, pool growth)
+    for rep in range(int(os.environ.get("MC2_PROFILE_PASSES", "2"))):   # pass 0 warms up (module load, pool growth); ncu full captures use 1
         for text, k, c, s in ((genome, 3, 10, 0), (genome, 12, 10, 0), (reads, 12, 10, 100 << 20), (genome_n, 40, 1, 0), (genome_n, 31, 1, 0),
                               (prot, 5, 10, 0), (prot, 3, 10, 0), (prot, 8, 2, 0), (reads, 31, 2, 50 << 20)):
             table, _ = engine.count_sample(text, k, c, s)
