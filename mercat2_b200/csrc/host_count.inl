@@ -190,6 +190,11 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     int sample_bits = 0;                                         // batched samples: the sample index rides above the k-mer code
     if (v.sample_start) while ((1u << sample_bits) < v.n_samples) ++sample_bits;
     const int kb = k * EncTraits<ENC>::BITS + sample_bits;
+    // Persistent kernels divide their work statically over a grid that just fills the GPU.  When something else holds SMs
+    // (the NCCL kernels of a key exchange in flight) part of such a grid runs as a second wave and the kernel takes
+    // twice as long (measured: hk_hist 18 -> 35 ms, hk_scatter1 46 -> 81 ms per 10^10 keys); "grid_waves" = w launches w
+    // times the CTAs, so that a CTA that starts late costs 1 / w of the kernel instead.
+    const u64 waves = (u64)std::max(1, std::min(16, e->opt_grid_waves));
     const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
     if (cap == 0) return;
     const u32 c = (u32)std::min<u64>(s->c, 0xFFFFFFFFull);
@@ -221,7 +226,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)nb * 4 + sizeof(Tail), e->stream));
     const size_t hist_smem = sizeof(RpShared) + (size_t)nb * 4;
     if (ks) {
-        const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms);
+        const u64 grid = std::min<u64>(div_up(cap, HK_HIST_THREADS * 8), (u64)e->num_sms * waves);
         LAUNCHN(e, "hk_hist_kernel", hk_hist_kernel<true>, (unsigned)std::max<u64>(grid, 1), HK_HIST_THREADS, hist_smem, ks->keys, ks->n, rv, nb, ghist.p);
     } else if (pv) {
         const u64 nwords = div_up(cap, 16);
@@ -246,7 +251,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
         CUDA_CHECK(cudaMemsetAsync(keys2.p, 0xEE, cap * 8, e->stream));
     }
     if (ks) {
-        LAUNCH(e, hk_scatter1_kernel, (unsigned)std::min<u64>(div_up(cap, HC_TILE), (u64)e->num_sms * 3), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur1.p, keys1.p, (const u64*)nullptr);
+        LAUNCH(e, hk_scatter1_kernel, (unsigned)std::min<u64>(div_up(cap, HC_TILE), (u64)e->num_sms * 3 * waves), EX_THREADS, HC_SCATTER_SMEM_LUT, ks->keys, ks->n, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else if (pv) {
         LAUNCH(e, fn_scatter1_kernel, (unsigned)std::min<u64>(div_up(div_up(cap, 16), EX_THREADS), (u64)e->num_sms * 3), EX_THREADS, HC_SCATTER_SMEM_LUT, *pv, k, rv, cur1.p, keys1.p, (const u64*)nullptr);
     } else {
@@ -276,7 +281,7 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
         fprintf(stderr, "[range] checksum stream (%llx %llx %llu) keys1 (%llx %llx %llu) keys2 (%llx %llx %llu)%s\n", h[0], h[1], h[2], h[3],
                 h[4], h[5], h[6], h[7], h[8], ((pv && (h[0] != h[6] || h[1] != h[7] || h[0] != h[3])) || b1 || b2) ? "  MISMATCH" : "");
     }
-    const unsigned cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms);
+    const unsigned cgrid = (unsigned)std::min<u64>(nb, 2ull * e->num_sms * waves);
     ull* flagged_dev = sink ? sink->counters + (mode == 1 ? 2 : 5) : &tail.p->flagged;      // (MODE 0 reports distinct keys there)
     if (mode == 1)
         LAUNCHN(e, "rc_count_kernel<1>", rc_count_kernel<1>, cgrid, RC_THREADS, RC_SMEM, (const u64*)keys2.p, (const u32*)sub_base.p, nb, c, rv, slots, rows.p,

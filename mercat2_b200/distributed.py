@@ -487,21 +487,29 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
         work = dist.all_to_all(outs, ins, async_op=True)
         return work, buf[:at], at
 
-    pending = start_round(0)
-    for j in range(m):
-        work, part, n = pending
-        if work is not None:
-            work.wait()
-            torch.cuda.current_stream(device).synchronize()
-        mark("exchange_wait_ms")
-        if j + 1 < m:
-            pending = start_round(j + 1)          # in flight while round j is counted
-        g = rank * m + j
-        sent += sum(keys.sizes[r * m + j] for r in range(world) if r != rank) * 8
-        received += sum(all_sizes[src][g] for src in range(world) if src != rank) * 8
-        if n:
-            sample.add_keys(part.data_ptr(), n, True, keys.bounds[g], max(keys.bounds[g + 1], keys.bounds[g] + 1))
-        mark("count_ms")
+    # the exchange's NCCL kernels hold SMs while a round is counted: the engine's persistent kernels launch several waves
+    # of CTAs so that a late CTA costs a fraction of the kernel, not a second pass (see "grid_waves" in host_count.inl)
+    if world > 1:
+        engine.set_option("grid_waves", 4)
+    try:
+        pending = start_round(0)
+        for j in range(m):
+            work, part, n = pending
+            if work is not None:
+                work.wait()
+                torch.cuda.current_stream(device).synchronize()
+            mark("exchange_wait_ms")
+            if j + 1 < m:
+                pending = start_round(j + 1)          # in flight while round j is counted
+            g = rank * m + j
+            sent += sum(keys.sizes[r * m + j] for r in range(world) if r != rank) * 8
+            received += sum(all_sizes[src][g] for src in range(world) if src != rank) * 8
+            if n:
+                sample.add_keys(part.data_ptr(), n, True, keys.bounds[g], max(keys.bounds[g + 1], keys.bounds[g] + 1))
+            mark("count_ms")
+    finally:
+        if world > 1:
+            engine.set_option("grid_waves", 1)
     bounds = keys.bounds
     del send_all
     keys.close()

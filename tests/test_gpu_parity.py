@@ -40,6 +40,8 @@ def reset(engine):
     engine.set_option("parse_single", 0)
     engine.set_option("count_mode", -1)
     engine.set_option("row_merge", 0)
+    engine.set_option("grid_waves", 1)
+    engine.set_option("bucket_growth", 1)
 
 
 def diff_msg(got, want):
@@ -900,6 +902,35 @@ def test_full_piece_known_answer(engine, genome_len, dup_every, c):
         assert np.array_equal(got_c, want_c), f"mode {mode}: {int((got_c != want_c).sum())} counts differ"
         if mode == -1 and genome_len >= 20_000_000:
             assert engine.stat("overflow_buckets") == ovf0          # the common case never needs the sort fallback
+
+
+def test_duplicate_rich_sample_grows_buckets(engine):
+    """36x coverage in 8 pieces: from the third piece on the sub-buckets are sized by the measured keys per distinct key
+    (the default size would need more than 192 level-1 bins here), persistent kernels launch 4 waves of CTAs (the setting
+    of the multi-GPU exchange); every piece is filtered on its own and the sums must equal numpy's"""
+    import torch
+    reset(engine)
+    text, codes = numpy_piece(120_000, 400_000, seed=31)
+    dev = torch.from_numpy(text).cuda()
+    results = {}
+    for growth in (1, 0):
+        engine.set_option("hash_bucket_keys", 40)
+        engine.set_option("grid_waves", 4)
+        engine.set_option("bucket_growth", growth)
+        try:
+            table, offs = engine.count_sample(dev, 31, 2, len(text) // 8)
+            results[growth] = table.packed_arrays()
+            table.close()
+        finally:
+            reset(engine)
+    bounds = [o // 164 for o in offs] + [120_000]
+    parts = [numpy_table(codes[a:b], 31, 2) for a, b in zip(bounds[:-1], bounds[1:])]
+    uk, inv = np.unique(np.concatenate([p[0] for p in parts]), return_inverse=True)
+    uc = np.zeros(len(uk), dtype=np.uint64)
+    np.add.at(uc, inv, np.concatenate([p[1] for p in parts]))
+    assert len(offs) >= 8 and len(uk) > 100_000
+    for growth, (got_k, got_c) in results.items():
+        assert np.array_equal(got_k, uk) and np.array_equal(got_c, uc), growth
 
 
 def test_full_piece_determinism(engine):
