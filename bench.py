@@ -369,9 +369,13 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
+    warm_ms = []
     for _ in range(args.warmup):
+        tw = time.perf_counter()
         rows, n_chunks = step_resident()
+        warm_ms.append(round((time.perf_counter() - tw) * 1e3, 2))
     launches0 = engine.stat("launches")
+    ovf0, merges0 = engine.stat("overflow_buckets"), engine.stat("row_merges")
     # CUDA events on the engine's stream around every kernel of the path (MC2_BENCH_PROFILE=3: only the long ones)
     engine.set_option("profile", int(os.environ.get("MC2_BENCH_PROFILE", "2")))
     timings = {}
@@ -386,6 +390,7 @@ def main():
     step_ms = [round((b - a) * 1e3, 2) for a, b in zip([t0] + step_ms[:-1], step_ms)]
     clocks = sampler.stop(t0, t0 + elapsed)
     launches = engine.stat("launches") - launches0
+    overflow_buckets = engine.stat("overflow_buckets") - ovf0
     profile = engine.profile()
     engine.set_option("profile", 0)
     kernel_us = sum(v["us"] for v in profile.values())
@@ -585,7 +590,7 @@ def main():
             "kernels": {k2: {"launches": v["launches"], "ms": round(v["us"] / 1e3, 3)} for k2, v in
                         sorted(profile.items(), key=lambda kv: -kv[1]["us"])[:14]},
             "check": check,
-            "step_ms_rank0": step_ms,
+            "step_ms_rank0": step_ms, "warmup_ms_rank0": warm_ms, "overflow_buckets_rank0": overflow_buckets,
         }
         if secondary:
             _, roof2 = roofline_of(secondary["profile"], secondary["steps"], secondary["rows"] / world, secondary["elapsed"] / secondary["steps"])
