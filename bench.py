@@ -323,7 +323,7 @@ def main():
     numa_bound = mercat2_b200.bind_to_gpu_numa(local) if world > 1 else False     # pinned shards next to their GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        mcd.init_nccl(device, dist)
 
     def barrier():
         if world > 1:

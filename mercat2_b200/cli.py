@@ -86,7 +86,7 @@ def mercat_main(argv=None):
         if torch.cuda.is_available():
             local = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(local)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            mcd.init_nccl(torch.device("cuda", local), dist)
         else:
             dist.init_process_group("gloo")                      # (CPU-only hosts: the CLI's own tests)
         dist.barrier()

@@ -40,7 +40,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    mcd.init_nccl(dev, dist)
     engine = mercat2_b200.Engine(local)
     reads = synth(6000, 5)
     pieces = [b"".join(reads[i::8]) for i in range(8)]
