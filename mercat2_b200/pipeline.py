@@ -80,6 +80,10 @@ def sample_metric_rows(file, chunk_size_mb: int = 0, engine=None):
 # ---------------------------------------------------------------------------------------------------
 BATCH_BYTES = 96 << 20          # text of one batched pass (about one ordinary 100 MB piece)
 BATCH_SAMPLES = 256
+# A sample joins a batched pass only below this much text.  Measured on a B200 (profiles/r02_workloads.jsonl, 64 proteomes,
+# k=5): 1.6 MB samples 11 ms batched against 59 ms one by one, 15.6 MB samples 158 ms batched against 42 ms one by one (a
+# sample of that size pays for its own dense table); the lines cross near 6 MB.
+BATCH_TEXT_MAX = 6 << 20
 
 
 def run_samples(samples: dict, out_dir, kmer: int, min_count: int, chunk_size_mb: int = 0, engine=None, quiet: bool = False) -> dict:
@@ -113,13 +117,20 @@ def run_samples(samples: dict, out_dir, kmer: int, min_count: int, chunk_size_mb
         batch, batch_bytes = [], 0
 
     for base, file in samples.items():
-        small = not chunk_trigger(file, chunk_size_mb) and os.stat(file).st_size <= BATCH_BYTES // 8
+        small = not chunk_trigger(file, chunk_size_mb) and os.stat(file).st_size <= BATCH_TEXT_MAX
         if not small:
             flush()
             results[base] = run_mercat2(base, [file], os.path.join(out_dir, f"{base}_counts.tsv"), kmer, min_count,
                                         chunk_size_mb=chunk_size_mb, engine=engine, quiet=quiet)[1]
             continue
         text = read_text_bytes(Path(file))
+        if len(text) > BATCH_TEXT_MAX:                         # (a small file that inflates to a large text)
+            small = False
+        if not small:
+            flush()
+            results[base] = run_mercat2(base, [file], os.path.join(out_dir, f"{base}_counts.tsv"), kmer, min_count,
+                                        chunk_size_mb=chunk_size_mb, engine=engine, quiet=quiet)[1]
+            continue
         if batch and (batch_bytes + len(text) > BATCH_BYTES or len(batch) >= BATCH_SAMPLES):
             flush()
         batch.append((base, text))
