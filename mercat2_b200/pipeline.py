@@ -81,8 +81,8 @@ def sample_metric_rows(file, chunk_size_mb: int = 0, engine=None):
 BATCH_BYTES = 96 << 20          # text of one batched pass (about one ordinary 100 MB piece)
 BATCH_SAMPLES = 256
 # A sample joins a batched pass only below this much text.  Measured on a B200 (profiles/r02_workloads.jsonl, 64 proteomes,
-# k=5): 1.6 MB samples 11 ms batched against 59 ms one by one, 15.6 MB samples 158 ms batched against 42 ms one by one (a
-# sample of that size pays for its own dense table); the lines cross near 6 MB.
+# k=5): 1.6 MB samples 11 ms batched against 59 ms one by one, 15.6 MB samples 85 ms batched against 42 ms one by one (a
+# sample of that size pays for its own dense table); the lines cross at 6-8 MB.
 BATCH_TEXT_MAX = 6 << 20
 
 
