@@ -194,7 +194,8 @@ static void sparse_chunk_range(mc2_engine* e, mc2_sample* s, SymView v, const Pa
     // (the NCCL kernels of a key exchange in flight) part of such a grid runs as a second wave and the kernel takes
     // twice as long (measured: hk_hist 18 -> 35 ms, hk_scatter1 46 -> 81 ms per 10^10 keys); "grid_waves" = w launches w
     // times the CTAs, so that a CTA that starts late costs 1 / w of the kernel instead.
-    const u64 waves = (u64)std::max(1, std::min(16, e->opt_grid_waves));
+    // (0 = the default, 2: measured 310.2 against 312.1 ms per headline step at N = 1; the key exchange asks for 4)
+    const u64 waves = e->opt_grid_waves > 0 ? (u64)std::min(16, e->opt_grid_waves) : 2;
     const u64 cap = ks ? ks->n : pv ? pv->n : v.n;              // upper bound on the number of windows
     if (cap == 0) return;
     const u32 c = (u32)std::min<u64>(s->c, 0xFFFFFFFFull);

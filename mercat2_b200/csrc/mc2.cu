@@ -59,7 +59,7 @@ struct mc2_engine {
     HostRowSink host_rows;
     unsigned long long* pin_groups = nullptr;   // pinned: per-group row counters of the streaming download
     u64 l0_fit_total = 0, l0_fit_extra = 0; // largest level-0 request that passed the memory check (see level0_partition)
-    int opt_grid_waves = 1;                // persistent kernels of the range path: CTAs launched = this x the resident slots (see sparse_chunk_range)
+    int opt_grid_waves = 0;                // persistent kernels of the range path: CTAs launched = this x the resident slots (see sparse_chunk_range)
     int opt_bucket_growth = 1;             // duplicate-rich data: size sub-buckets by the measured keys per distinct key (0 = fixed 1.25 x)
     int opt_row_merge = 0;                 // sums of (key, count) row sets: 0 = sort + segmented sum, 1 = range partition + shared-memory sums
     int opt_count_mode = -1;               // counting kernel: -1 auto, 0 every key into the table, 1 bitmap pre-filter (min_count >= 2 only)

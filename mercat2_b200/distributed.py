@@ -525,7 +525,7 @@ def count_piece_position_sharded(engine, my_text, k: int, min_count: int, dist, 
             mark("count_ms")
     finally:
         if world > 1:
-            engine.set_option("grid_waves", 1)
+            engine.set_option("grid_waves", 0)        # (0 = the engine's default)
     bounds = keys.bounds
     del send_all
     keys.close()

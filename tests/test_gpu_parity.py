@@ -40,7 +40,7 @@ def reset(engine):
     engine.set_option("parse_single", 0)
     engine.set_option("count_mode", -1)
     engine.set_option("row_merge", 0)
-    engine.set_option("grid_waves", 1)
+    engine.set_option("grid_waves", 0)
     engine.set_option("bucket_growth", 1)
 
 
