@@ -4,6 +4,7 @@ made by the reference, and the product refuses to run without a GPU (no CPU fall
 import gzip
 import hashlib
 import re
+import sys
 
 import pytest
 
@@ -180,3 +181,26 @@ def test_c_example_links_against_the_abi(tmp_path):
         run = subprocess.run([str(exe), str(root / "tests/golden/data/fna_gz/DJ.fna.gz"), "3", "10", "0", str(tmp_path / "x.tsv")],
                              capture_output=True, text=True)
         assert run.returncode != 0 and "no CPU fallback" in run.stderr and not (tmp_path / "x.tsv").exists()
+
+
+def test_bench_accounting_helpers():
+    """the roofline accounting of bench.py: algorithmic bytes per kernel and the phase split"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    reads = 1_000_000
+    text_bytes = reads * bench.REC_BYTES
+    windows = reads * (bench.READ_LEN - 31 + 1)
+    rows = windows // 10
+    assert bench.algorithmic_bytes_per_step("hk_scatter1_kernel", windows, text_bytes, rows) == 16.0 * windows      # key read once, written once
+    assert bench.algorithmic_bytes_per_step("rc_count_kernel<0>", windows, text_bytes, rows) == 8.0 * windows + 16.0 * rows
+    assert bench.algorithmic_bytes_per_step("fn_parse_kernel<2>", windows, text_bytes, rows) == text_bytes
+    packed = bench.algorithmic_bytes_per_step("fn_hist_kernel", windows, text_bytes, rows)
+    assert 0.37 * reads * bench.READ_LEN < packed < 0.39 * reads * (bench.READ_LEN + 1)                                # 3 bits per symbol
+    assert bench.algorithmic_bytes_per_step("not_a_kernel", windows, text_bytes, rows) is None
+    profile = {"fn_parse_kernel<1>": {"us": 2000.0, "launches": 2}, "hk_scatter1_kernel": {"us": 4000.0, "launches": 4},
+               "rc_count_kernel<0>": {"us": 6000.0, "launches": 4}, "rc_gather_kernel": {"us": 500.0, "launches": 4},
+               "mystery_kernel": {"us": 100.0, "launches": 1}}
+    ph = bench.phases_from_profile(profile, 2)
+    assert ph == {"parse_ms": 1.0, "partition_ms": 2.0, "count_ms": 3.0, "emit_ms": 0.25, "other_ms": 0.05}
+    assert "-s 0" in bench.workload_name(31, 2, 0) and "one global table" in bench.workload_name(31, 2, 0)
+    assert "per-chunk filter" in bench.workload_name(31, 10, 100)
