@@ -438,6 +438,7 @@ def main():
             host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             host.copy_(text)
             out_rows = torch.empty((out_rows_cap, 2), dtype=torch.int64, pin_memory=True)      # (key, count) per row
+            split_rows = world == 1 and args.s == 0 and os.environ.get("MC2_BENCH_ROWS16", "0") != "1"
             torch.cuda.synchronize()
             e_steps = max(1, min(args.steps, 5))
 
@@ -445,6 +446,10 @@ def main():
                 if world == 1 and args.s == 0:
                     # the public call that delivers the table to host memory: rows of finished key ranges stream out
                     # while later ranges are still being counted
+                    # (as uint64 keys + uint32 counts: 12 bytes per row over PCIe; MC2_BENCH_ROWS16=1 asks for 16-byte rows)
+                    if split_rows:
+                        flat = out_rows.view(-1)
+                        return engine.count_text_rows_split(host, args.k, args.c, flat.data_ptr(), flat[out_rows_cap:].data_ptr(), out_rows_cap) * 12
                     return engine.count_text_rows(host, args.k, args.c, out_rows.data_ptr(), out_rows_cap) * 16
                 table, _ = count(host, args.k, args.c, args.s)
                 n = table.rows
@@ -472,7 +477,8 @@ def main():
             barrier()
             h2d_gbs = 3 * dst.numel() / (time.perf_counter() - t1) / 1e9
             del dst
-            e2e = {"steps": e_steps, "times": times, "h2d": nbytes, "d2h": d2h, "h2d_ceiling_gbs": h2d_gbs}
+            e2e = {"steps": e_steps, "times": times, "h2d": nbytes, "d2h": d2h, "h2d_ceiling_gbs": h2d_gbs,
+                   "rows_format": "uint64 key + uint32 count, 12 B per row" if split_rows else "uint64 key + uint64 count, 16 B per row"}
             del host, out_rows
 
     # ---- max over ranks -------------------------------------------------------------------------------
@@ -616,7 +622,7 @@ def main():
             out["e2e"] = {"value": total_bases * len(ts) / sum(ts), "unit": "bases/s",
                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": len(ts),
                           "min_s": ts[0], "median_s": med, "max_s": ts[-1], "value_at_median": total_bases / med,
-                          "h2d_ceiling_gbs": e2e["h2d_ceiling_gbs"],
+                          "h2d_ceiling_gbs": e2e["h2d_ceiling_gbs"], "rows_format": e2e["rows_format"],
                           "pcie_floor_s": (e2e["h2d"] + e2e["d2h"]) / world / (e2e["h2d_ceiling_gbs"] / world * 1e9),
                           "note": "pcie_floor_s = (H2D + D2H bytes of one rank) / measured pinned-H2D rate of one rank when all ranks copy at once"}
 

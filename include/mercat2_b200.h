@@ -77,6 +77,11 @@ int mc2_count_text(mc2_engine* e, const void* text, uint64_t nbytes, int space, 
  * conventions, 2 bits per base for nucleotide text). */
 int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
                         uint64_t capacity, uint64_t* rows);
+/* The same table as two HOST arrays -- host_keys[capacity] (uint64) and host_counts[capacity] (uint32): 12 bytes per row
+ * over PCIe instead of 16 (the download is what bounds an end-to-end run of one global table).  A count that does not fit
+ * 32 bits fails the call with MC2_ERR_LIMIT (use mc2_count_text_rows). */
+int mc2_count_text_rows_split(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
+                              uint64_t* host_keys, uint32_t* host_counts, uint64_t capacity, uint64_t* rows);
 
 /* Replaces the sample loop of bin/mercat2.py:411-448 (one find_kmers task per sample file, each file smaller than
  * the -s trigger, i.e. ONE piece) for n samples at once: out[j] is the table of texts[j], identical to n calls of

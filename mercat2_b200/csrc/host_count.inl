@@ -777,6 +777,15 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     u64 copied = 0;
     u32 next_copy = 0, launched = 0;
     ull* pin = nullptr;
+    const u64 SPLIT_STAGE_ROWS = 16ull << 20;
+    DBuf<u64> stage_keys;
+    DBuf<u32> stage_counts, split_flag;
+    if (hs && hs->keys64) {
+        stage_keys.alloc(e, SPLIT_STAGE_ROWS);
+        stage_counts.alloc(e, SPLIT_STAGE_ROWS);
+        split_flag.alloc(e, 1);
+        split_flag.zero();
+    }
     if (hs) {
         if (!e->pin_groups) CUDA_CHECK(cudaMallocHost((void**)&e->pin_groups, (HC_MAX_NB1 + 8) * sizeof(ull)));
         pin = e->pin_groups;
@@ -789,8 +798,22 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
             if (upto > hs->capacity) { hs->failed = true; hs = nullptr; break; }
             if (upto > copied) {
                 CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, evs[next_copy], 0));
-                CUDA_CHECK(cudaMemcpyAsync((RcRow*)hs->rows + copied, sink.arena + copied, (upto - copied) * sizeof(RcRow), cudaMemcpyDeviceToHost, e->copy_stream));
-                e->d2h_bytes += (upto - copied) * sizeof(RcRow);
+                if (!hs->keys64) {
+                    CUDA_CHECK(cudaMemcpyAsync((RcRow*)hs->rows + copied, sink.arena + copied, (upto - copied) * sizeof(RcRow), cudaMemcpyDeviceToHost, e->copy_stream));
+                    e->d2h_bytes += (upto - copied) * sizeof(RcRow);
+                } else {
+                    // split delivery: rows -> (key, 32-bit count) in a staging pair on the copy stream, 12 bytes per row leave
+                    // (the split kernel and its two copies run in stream order, so one staging pair is enough)
+                    for (u64 at = copied; at < upto; at += SPLIT_STAGE_ROWS) {
+                        const u64 n = std::min<u64>(SPLIT_STAGE_ROWS, upto - at);
+                        rc_split_rows32_kernel<<<(unsigned)div_up(n, 256), 256, 0, e->copy_stream>>>((const RcRow*)(sink.arena + at), n, stage_keys.p, stage_counts.p, split_flag.p);
+                        CUDA_CHECK(cudaGetLastError());
+                        e->launches++;
+                        CUDA_CHECK(cudaMemcpyAsync(hs->keys64 + at, stage_keys.p, n * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+                        CUDA_CHECK(cudaMemcpyAsync(hs->counts32 + at, stage_counts.p, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+                    }
+                    e->d2h_bytes += (upto - copied) * 12;
+                }
                 copied = upto;
             }
             ++next_copy;
@@ -846,6 +869,7 @@ static bool sparse_chunk_big(mc2_engine* e, mc2_sample* s, const std::vector<Pac
     if (hs && ovf_m) e->host_rows.failed = true;               // rows of the sort path would have to be merged in: the caller falls back
     if (host_done) {
         CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+        if (hs->keys64 && read_scalar<u32>(e, split_flag.p)) e->host_rows.too_big = true;
         e->host_rows.delivered = R;
         e->host_rows.complete = true;
     } else if (R) {

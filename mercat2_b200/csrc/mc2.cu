@@ -35,6 +35,9 @@ struct RangeWork;
 struct HostRowSink {
     bool active = false, failed = false, complete = false;
     void* rows = nullptr;                  // 16 bytes per row: key, count
+    u64* keys64 = nullptr;                 // split delivery (mc2_count_text_rows_split): 8 + 4 bytes per row in two arrays
+    u32* counts32 = nullptr;
+    bool too_big = false;                  // split delivery: some count needs more than 32 bits
     u64 capacity = 0, delivered = 0;
 };
 struct mc2_engine {
@@ -1495,11 +1498,12 @@ int mc2_count_batch(mc2_engine* e, const void* const* texts, const uint64_t* nby
     API_END
 }
 
-int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
-                        uint64_t capacity, uint64_t* rows) {
-    API_BEGIN
+// host_rows (16-byte rows) or host_keys + host_counts (split delivery, 12 bytes per row)
+static void count_text_rows_impl(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
+                                 uint64_t* host_keys, uint32_t* host_counts, uint64_t capacity, uint64_t* rows) {
     check_count_args(e, text, nbytes, k);
-    if (!rows || (capacity && !host_rows)) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    const bool split = host_keys != nullptr || host_counts != nullptr;
+    if (!rows || (capacity && (split ? (!host_keys || !host_counts) : !host_rows))) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
     CUDA_CHECK(cudaSetDevice(e->device));
     mc2_sample s;
     s.e = e;
@@ -1509,6 +1513,8 @@ int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int sp
     e->host_rows = HostRowSink();
     e->host_rows.active = true;
     e->host_rows.rows = host_rows;
+    e->host_rows.keys64 = split ? host_keys : nullptr;
+    e->host_rows.counts32 = split ? host_counts : nullptr;
     e->host_rows.capacity = capacity;
     HostRowSink hs;
     try {
@@ -1523,17 +1529,27 @@ int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int sp
         throw;
     }
     if (hs.complete && s.fast.empty() && s.wide.empty() && s.plan.path == PATH_SPARSE) {
+        if (hs.too_big) throw Mc2Error(MC2_ERR_LIMIT, "a count does not fit 32 bits: use mc2_count_text_rows");
         *rows = hs.delivered;                                   // every row already sits in the caller's buffer
     } else {
         std::unique_ptr<mc2_table> t(sample_finish(&s));
         if (t->wide.n) throw Mc2Error(MC2_ERR_LIMIT, "the table holds literal-byte rows (k-mers outside the packed alphabet): use mc2_count_text");
         if (t->fast.n > capacity) throw Mc2Error(MC2_ERR_INVALID, "buffer too small");
-        if (t->fast.n) {
+        if (t->fast.n && !split) {
             DBuf<RcRow> aos(e, t->fast.n);
             LAUNCH(e, rc_join_rows_kernel, (unsigned)div_up(t->fast.n, 256), 256, 0, (const u64*)t->fast.keys.p, (const u64*)t->fast.counts.p, (u64)t->fast.n, aos.p);
             CUDA_CHECK(cudaMemcpyAsync(host_rows, aos.p, t->fast.n * sizeof(RcRow), cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
             e->d2h_bytes += t->fast.n * sizeof(RcRow);
+        } else if (t->fast.n) {
+            DBuf<u32> narrow(e, t->fast.n), flag(e, 1);
+            flag.zero();
+            LAUNCH(e, narrow_counts_kernel, (unsigned)div_up(t->fast.n, 256), 256, 0, (const u64*)t->fast.counts.p, (u64)t->fast.n, narrow.p, flag.p);
+            CUDA_CHECK(cudaMemcpyAsync(host_keys, t->fast.keys.p, t->fast.n * 8, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(host_counts, narrow.p, t->fast.n * 4, cudaMemcpyDeviceToHost, e->stream));
+            const u32 too_big = read_scalar<u32>(e, flag.p);
+            e->d2h_bytes += t->fast.n * 12;
+            if (too_big) throw Mc2Error(MC2_ERR_LIMIT, "a count does not fit 32 bits: use mc2_count_text_rows");
         }
         *rows = t->fast.n;
     }
@@ -1543,6 +1559,20 @@ int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int sp
     CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->device_us = ms * 1000.0;
     e->resolve_profile();
+}
+
+int mc2_count_text_rows(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count, void* host_rows,
+                        uint64_t capacity, uint64_t* rows) {
+    API_BEGIN
+    count_text_rows_impl(e, text, nbytes, space, k, min_count, host_rows, nullptr, nullptr, capacity, rows);
+    API_END
+}
+
+int mc2_count_text_rows_split(mc2_engine* e, const void* text, uint64_t nbytes, int space, int k, int64_t min_count,
+                              uint64_t* host_keys, uint32_t* host_counts, uint64_t capacity, uint64_t* rows) {
+    API_BEGIN
+    if (!host_keys || !host_counts) throw Mc2Error(MC2_ERR_INVALID, "NULL argument");
+    count_text_rows_impl(e, text, nbytes, space, k, min_count, nullptr, host_keys, host_counts, capacity, rows);
     API_END
 }
 

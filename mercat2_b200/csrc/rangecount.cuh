@@ -904,6 +904,25 @@ __global__ void rc_split_rows_kernel(const RcRow* __restrict__ in, u64 n, u64* _
     if (i < n) { const RcRow row = in[i]; keys[i] = row.key; counts[i] = row.count; }
 }
 
+// rows -> (key, 32-bit count) arrays; *too_big is set when a count needs more than 32 bits
+__global__ void rc_split_rows32_kernel(const RcRow* __restrict__ in, u64 n, u64* __restrict__ keys, u32* __restrict__ counts, u32* __restrict__ too_big) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const RcRow row = in[i];
+        keys[i] = row.key;
+        counts[i] = (u32)row.count;
+        if (row.count >> 32) *too_big = 1u;
+    }
+}
+__global__ void narrow_counts_kernel(const u64* __restrict__ counts, u64 n, u32* __restrict__ out, u32* __restrict__ too_big) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const u64 c = counts[i];
+        out[i] = (u32)c;
+        if (c >> 32) *too_big = 1u;
+    }
+}
+
 __global__ void rc_join_rows_kernel(const u64* __restrict__ keys, const u64* __restrict__ counts, u64 n, RcRow* __restrict__ out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { RcRow row; row.key = keys[i]; row.count = counts[i]; out[i] = row; }

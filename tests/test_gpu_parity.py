@@ -1124,12 +1124,17 @@ def test_big_chunk_async_groups_and_row_streaming(engine):
                 table.close()
                 rows = torch.empty((len(want_k) + 8, 2), dtype=torch.int64, pin_memory=True)
                 n = engine.count_text_rows(dev, 31, c, rows.data_ptr(), rows.shape[0])
+                keys64 = torch.empty(len(want_k) + 8, dtype=torch.int64, pin_memory=True)
+                counts32 = torch.empty(len(want_k) + 8, dtype=torch.int32, pin_memory=True)
+                n2 = engine.count_text_rows_split(dev, 31, c, keys64.data_ptr(), counts32.data_ptr(), len(keys64))
             finally:
                 engine.set_option("group_sync", 0)
                 reset(engine)
             assert np.array_equal(got_k, want_k) and np.array_equal(got_c, want_c), (c, opts)
             got = rows[:n].numpy().view(np.uint64)
             assert n == len(want_k) and np.array_equal(got[:, 0], want_k) and np.array_equal(got[:, 1], want_c), (c, opts, n)
+            assert n2 == len(want_k) and np.array_equal(keys64[:n2].numpy().view(np.uint64), want_k), (c, opts, n2)       # 12-byte rows
+            assert np.array_equal(counts32[:n2].numpy().view(np.uint32).astype(np.uint64), want_c), (c, opts)
     # a text with k-mers outside ACGT cannot be delivered as packed rows; small texts take the ordinary path
     import mercat2_b200
     rows = torch.empty((1024, 2), dtype=torch.int64, pin_memory=True)
@@ -1140,6 +1145,13 @@ def test_big_chunk_async_groups_and_row_streaming(engine):
     assert n == len(want)
     with pytest.raises(mercat2_b200.Mc2Error):
         engine.count_text_rows(dev, 31, 2, rows.data_ptr(), 16)                                  # buffer too small
+    k64 = torch.empty(1024, dtype=torch.int64, pin_memory=True)
+    c32 = torch.empty(1024, dtype=torch.int32, pin_memory=True)
+    n = engine.count_text_rows_split(b">r\nACGTACGTACGT\n", 3, 2, k64.data_ptr(), c32.data_ptr(), 1024)                # the ordinary (small) path
+    assert n == len(want) and [c32[i].item() for i in range(n)] == [want[kmer] for kmer in sorted(want)]          # rows are in k-mer order
+    assert k64[:n].tolist() == sorted(k64[:n].tolist())
+    with pytest.raises(mercat2_b200.Mc2Error):
+        engine.count_text_rows_split(dev, 31, 2, k64.data_ptr(), c32.data_ptr(), 16)                                  # buffer too small
 
 
 def test_fastq_to_fasta_on_device(engine, golden_configs, tmp_path):
