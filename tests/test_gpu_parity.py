@@ -798,7 +798,8 @@ def test_bench_json_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 700000 * 164 and line["e2e"]["value"] > 0
     # the headline is config 4 as written: one global table (-s 0 -c 2) with survivors, the table read back, checked first
     assert "-c 2 -s 0" in line["config"]["workload"] and line["config"]["surviving_rows"] > 0
-    assert line["e2e"]["d2h_bytes_per_step"] == 16 * line["config"]["surviving_rows"]
+    assert line["e2e"]["d2h_bytes_per_step"] == 12 * line["config"]["surviving_rows"]      # uint64 key + uint32 count per row
+    assert "12 B per row" in line["e2e"]["rows_format"]
     assert line["check"]["ok"] and line["check"]["oracle_md5"] == line["check"]["engine_md5"] and line["check"]["rows"] > 0
     assert set(("parse_ms", "partition_ms", "count_ms", "emit_ms")) <= set(line["phases"]) and line["limiting_phase"] in line["phases"]
     assert "-c 10 -s 100" in line["secondary"]["workload"] and line["secondary"]["value"] > 0
